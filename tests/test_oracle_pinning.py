@@ -1,0 +1,90 @@
+"""CPU: the librosa-0.9.2 restatement (oracle/librosa_port.py) is pinned against an independent
+implementation (torchaudio) and against algebraic known answers -- librosa itself is not
+installable here (no network) and the reference holds no vectors for it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hotpath as hp
+from oracle import librosa_port as lp
+
+torchaudio = pytest.importorskip("torchaudio")
+
+
+def _signal(n=144000, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / 48000.0
+    return (0.05 * rng.standard_normal(n) + 0.2 * np.sin(2 * np.pi * 2600 * t) * (np.sin(2 * np.pi * 7 * t) > 0)).astype(np.float32)
+
+
+def test_mel_filterbank_vs_torchaudio():
+    ours = lp.mel_filterbank(sr=48000, n_fft=2048, n_mels=64, fmin=150.0, fmax=15000.0)
+    ta = torchaudio.functional.melscale_fbanks(1025, 150.0, 15000.0, 64, 48000, norm="slaney", mel_scale="slaney").T.numpy()
+    assert ours.shape == (64, 1025) and ours.dtype == np.float32
+    assert np.max(np.abs(ours - ta)) < 1e-7
+    nz = np.nonzero(ours.sum(axis=0))[0]
+    assert (nz.min(), nz.max()) == (7, 640)           # SURVEY.md section 7 hard part 3
+    assert int((ours > 0).sum()) == 1231
+    assert ((ours > 0).sum(axis=0) <= 2).all()        # every FFT bin feeds at most two adjacent filters
+
+
+def test_melspectrogram_vs_torchaudio():
+    y = _signal()
+    ours = hp.mel_power(y)
+    tr = torchaudio.transforms.MelSpectrogram(sample_rate=48000, n_fft=2048, hop_length=384, f_min=150.0, f_max=15000.0,
+                                              n_mels=64, power=2.0, center=True, pad_mode="reflect", norm="slaney",
+                                              mel_scale="slaney")
+    ta = tr(torch.from_numpy(y)).numpy()
+    assert ours.shape == ta.shape == (64, 376)
+    assert np.max(np.abs(ours - ta)) / np.max(np.abs(ta)) < 5e-6
+
+
+def test_pure_tone_lands_in_expected_mel_band():
+    k = 300                                              # FFT bin centre: 300 * 48000 / 2048 Hz
+    t = np.arange(144000) / 48000.0
+    y = (0.1 * np.sin(2 * np.pi * (k * 48000 / 2048) * t)).astype(np.float32)
+    S = hp.mel_power(y)
+    fb = lp.mel_filterbank(sr=48000, n_fft=2048, n_mels=64, fmin=150.0, fmax=15000.0)
+    assert int(np.argmax(S.mean(axis=1))) == int(np.argmax(fb[:, k]))
+
+
+def test_power_to_db_and_zscore_known_answers():
+    S = np.array([[1.0, 1e-3], [1e-12, 1e-9]], dtype=np.float32)
+    db = lp.power_to_db(S, ref=np.max)
+    assert np.allclose(db, [[0.0, -30.0], [-80.0, -80.0]], atol=1e-5)      # amin clamp then top_db floor
+    feat = hp.logmel_features(np.zeros(144000, dtype=np.float32))
+    assert feat.shape == (64, 192) and not feat.any()                       # all-silent -> 0 / 1e-8 = 0
+    y = _signal(seed=3)
+    S_db = lp.power_to_db(hp.mel_power(y), ref=np.max)
+    zs = (S_db - S_db.mean()) / (S_db.std() + 1e-8)
+    assert abs(float(zs.mean())) < 1e-4 and abs(float(zs.std()) - 1.0) < 1e-4   # stats over the uncropped matrix
+    assert np.array_equal(hp.logmel_features(y), zs[:, 92:92 + 192])        # centre crop start (376-192)//2
+
+
+def test_pcm16_roundtrip_semantics(tmp_path):
+    y = np.array([0.0, 1.0, -1.0, 0.5, 1.0 / 32767, 0.123456], dtype=np.float32)
+    s = lp.float_to_pcm16(y)
+    assert s.tolist() == [0, 32767, -32767, 16384, 1, 4045]              # lrintf(x * 0x7FFF), half-to-even
+    assert lp.pcm16_to_float(s)[1] == np.float32(32767 / 32768)           # read-back divides by 0x8000
+    lp.write_wav(tmp_path / "a.wav", y, 48000)
+    back, sr = lp.load(tmp_path / "a.wav", sr=48000)
+    assert sr == 48000 and np.array_equal(back, lp.pcm16_roundtrip(y))
+
+
+def test_rms_unit_level_when_unclipped():
+    y, ok = hp.rms_normalize(_signal(seed=5) * np.float32(0.1))
+    assert ok and abs(float(np.sqrt(np.mean(y.astype(np.float64) ** 2))) - 0.05) < 1e-6
+    y1, _ = hp.rms_normalize(_signal(seed=5), numpy1_scalars=True)
+    y2, _ = hp.rms_normalize(_signal(seed=5))
+    assert np.max(np.abs(y1 - y2)) <= np.max(np.abs(y2)) * 2.0 ** -23       # numpy-1.26 variant: <= 1 ulp of the scale
+
+
+def test_fit_monotone_in_q_out():
+    rng = np.random.default_rng(0)
+    Z = rng.standard_normal((2000, 32)).astype(np.float32)
+    lab = np.arange(2000) % 4
+    prev = -1.0
+    for q in (0.05, 0.10, 0.15, 0.20, 0.25):
+        _, _, _, rk_out, _ = hp.fit_species_with_fp_control(Z[lab == 0], Z[lab != 0], 0.95, q)
+        assert rk_out >= prev
+        prev = rk_out
