@@ -1,0 +1,141 @@
+// api.cu -- whole-path entry points: device-resident encode, host-buffer encode+detect with
+// double-buffered copies, and the GEMM bring-up entry used by the tests.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "gemm3.cuh"
+
+using namespace avld;
+
+static int encode_pass(avld_ctx* c, const float* x, float* mu, uint8_t* ok, int m, float target_rms, float rms_min,
+                       float eps, int quantize, cudaStream_t st) {
+  AVLD_TRY(launch_prep(c, x, nullptr, true, true, ok, nullptr, m, target_rms, rms_min, eps, quantize, st));
+  AVLD_TRY(launch_stft_mel(c, m, st));
+  AVLD_TRY(launch_logmel_post(c, c->d_feat, m, st));
+  AVLD_TRY(launch_encoder(c, c->d_feat, mu, m, st));
+  return AVLD_OK;
+}
+
+extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, int64_t n, float target_rms,
+                           float rms_min, float eps, int quantize_pcm16, void* stream) {
+  AVLD_CHECK(c && x && mu, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
+  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t i = 0; i < n; i += c->max_batch) {
+    const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
+    AVLD_TRY(encode_pass(c, x + i * c->L, mu + i * c->latent_dim, ok ? ok + i : nullptr, m, target_rms, rms_min, eps,
+                         quantize_pcm16, st));
+  }
+  return AVLD_OK;
+}
+
+extern "C" int avld_encode_detect_host(avld_ctx* c, const float* x_host, int64_t n, int quantize_pcm16,
+                                       const float* centroid, const double* thr, const int32_t* priority_rank,
+                                       int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
+                                       uint8_t* ok_host) {
+  AVLD_CHECK(c && x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(n >= 0 && K >= 1 && K <= 64, AVLD_ERR_INVALID, "bad n / K");
+  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  AVLD_CUDA(cudaSetDevice(c->device));
+  const int D = c->latent_dim;
+  const size_t xbytes = static_cast<size_t>(c->max_batch) * c->L * sizeof(float);
+  for (int b = 0; b < 2; ++b)
+    if (!c->d_xbuf[b]) AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_xbuf[b]), xbytes));
+  if (!c->d_cent) {
+    AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_cent), 64 * 4096 * sizeof(float)));
+    AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_thr), 64 * sizeof(double)));
+    AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_prio), 64 * sizeof(int32_t)));
+  }
+  AVLD_CHECK(static_cast<size_t>(K) * D <= 64 * 4096, AVLD_ERR_UNSUPPORTED, "K*D too large");
+  cudaStream_t sc = c->s_compute, sx = c->s_copy;
+  AVLD_CUDA(cudaMemcpyAsync(c->d_cent, centroid, static_cast<size_t>(K) * D * sizeof(float), cudaMemcpyHostToDevice, sc));
+  AVLD_CUDA(cudaMemcpyAsync(c->d_thr, thr, K * sizeof(double), cudaMemcpyHostToDevice, sc));
+  AVLD_CUDA(cudaMemcpyAsync(c->d_prio, priority_rank, K * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
+
+  // slab i: H2D on the copy stream into buffer i&1 while the compute stream works on slab i-1;
+  // results of slab i are read back on the compute stream right after its kernels.
+  int64_t slab = 0;
+  for (int64_t i = 0; i < n; i += c->max_batch, ++slab) {
+    const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
+    const int b = static_cast<int>(slab & 1);
+    if (slab >= 2) AVLD_CUDA(cudaStreamWaitEvent(sx, c->ev_done[b], 0));   // buffer b free again
+    AVLD_CUDA(cudaMemcpyAsync(c->d_xbuf[b], x_host + i * c->L, static_cast<size_t>(m) * c->L * sizeof(float),
+                              cudaMemcpyHostToDevice, sx));
+    AVLD_CUDA(cudaEventRecord(c->ev_h2d[b], sx));
+    AVLD_CUDA(cudaStreamWaitEvent(sc, c->ev_h2d[b], 0));
+    AVLD_TRY(encode_pass(c, c->d_xbuf[b], c->d_mu, c->d_ok, m, 0.05f, 1e-4f, 1e-8f, quantize_pcm16, sc));
+    AVLD_CUDA(cudaEventRecord(c->ev_done[b], sc));                         // x buffer consumed by the prep kernel
+    AVLD_TRY(avld_radii(c, c->d_mu, c->d_cent, c->d_radii, m, K, D, sc));
+    AVLD_TRY(avld_decide(c, c->d_radii, c->d_thr, c->d_prio, c->d_pred, c->d_best, m, K, sc));
+    AVLD_CUDA(cudaMemcpyAsync(pred_host + i, c->d_pred, static_cast<size_t>(m) * sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
+    AVLD_CUDA(cudaMemcpyAsync(best_host + i, c->d_best, static_cast<size_t>(m) * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (mu_host)
+      AVLD_CUDA(cudaMemcpyAsync(mu_host + i * D, c->d_mu, static_cast<size_t>(m) * D * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    if (ok_host)
+      AVLD_CUDA(cudaMemcpyAsync(ok_host + i, c->d_ok, static_cast<size_t>(m), cudaMemcpyDeviceToHost, sc));
+  }
+  AVLD_CUDA(cudaStreamSynchronize(sc));
+  AVLD_CUDA(cudaStreamSynchronize(sx));
+  return AVLD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bring-up / test entry: C = A * B^T through the tcgen05 core with plain row-major operands
+// ------------------------------------------------------------------------------------------------
+extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float* C, int64_t M, int32_t N, int32_t K,
+                             int32_t mode, void* stream) {
+  AVLD_CHECK(c && A && B && C, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(M >= 1 && N >= 16 && N % 16 == 0 && K >= 64 && K % 64 == 0, AVLD_ERR_INVALID, "need N %% 16 == 0 and K %% 64 == 0");
+  AVLD_CHECK(mode == 0 || mode == 1, AVLD_ERR_INVALID, "mode must be 0 or 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr;
+  const size_t na = static_cast<size_t>(M) * K, nb = static_cast<size_t>(N) * K;
+  AVLD_CUDA(cudaMalloc(&a_hi, na * 2));
+  AVLD_CUDA(cudaMalloc(&a_lo, na * 2));
+  AVLD_CUDA(cudaMalloc(&b_hi, nb * 2));
+  AVLD_CUDA(cudaMalloc(&b_lo, nb * 2));
+  int rc = AVLD_OK;
+  do {
+    CUtensorMapDataType hi_t = mode == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (mode == 0) {
+      if ((rc = launch_split_f16(A, static_cast<__half*>(a_hi), static_cast<__nv_bfloat16*>(a_lo), na, st))) break;
+      if ((rc = launch_split_f16(B, static_cast<__half*>(b_hi), static_cast<__nv_bfloat16*>(b_lo), nb, st))) break;
+    } else {
+      if ((rc = launch_split_bf16(A, static_cast<__nv_bfloat16*>(a_hi), static_cast<__nv_bfloat16*>(a_lo), na, st))) break;
+      if ((rc = launch_split_bf16(B, static_cast<__nv_bfloat16*>(b_hi), static_cast<__nv_bfloat16*>(b_lo), nb, st))) break;
+    }
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if ((rc = encode_tmap_2d(&ta_hi, a_hi, hi_t, K, M, static_cast<uint64_t>(K) * 2, 64, 128, 128))) break;
+    if ((rc = encode_tmap_2d(&ta_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, M, static_cast<uint64_t>(K) * 2, 64, 128, 128))) break;
+    if ((rc = encode_tmap_2d(&tb_hi, b_hi, hi_t, K, N, static_cast<uint64_t>(K) * 2, 64, bn, 128))) break;
+    if ((rc = encode_tmap_2d(&tb_lo, b_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, N, static_cast<uint64_t>(K) * 2, 64, bn, 128))) break;
+    Gemm3Params P{};
+    P.num_m_tiles = static_cast<int>((M + 127) / 128);
+    P.num_n_tiles = (N + bn - 1) / bn;
+    P.num_k_blocks = K / 64;
+    const int hb = mode == 0 ? 0 : 1;
+    P.idesc_hh = avld_make_idesc(hb, hb, 128, bn);
+    P.idesc_lh = avld_make_idesc(1, hb, 128, bn);
+    P.idesc_hl = avld_make_idesc(hb, 1, 128, bn);
+    P.a_mode = 0;
+    P.M_total = M;
+    P.N_total = N;
+    P.out_f32 = C;
+    P.ldc = N;
+    rc = run_gemm3(bn, 128, EPI_PLAIN, ta_hi, ta_lo, tb_hi, tb_lo, P, c->sm_count, st);
+    if (rc) break;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_error("dbg_gemm kernel failed: %s", cudaGetErrorString(e));
+      rc = AVLD_ERR_CUDA;
+    }
+  } while (0);
+  cudaFree(a_hi);
+  cudaFree(a_lo);
+  cudaFree(b_hi);
+  cudaFree(b_lo);
+  return rc;
+}

@@ -1,0 +1,151 @@
+// common.cuh -- context, error plumbing and shared structs of libavld (host side).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/avld.h"
+
+namespace avld {
+
+void set_error(const char* fmt, ...);
+
+#define AVLD_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::avld::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return AVLD_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+#define AVLD_CHECK(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::avld::set_error(__VA_ARGS__);    \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define AVLD_TRY(expr)            \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != AVLD_OK) return _r; \
+  } while (0)
+
+// mel filterbank tap of one FFT bin: feeds filter `first` with w0 and `first + 1` with w1
+struct MelTap {
+  int32_t first;
+  float w0, w1;
+};
+
+struct PairNode {
+  int32_t a, b;  // indices into the value array (leaves first, then internal nodes by height)
+};
+
+// encoder layer on the device
+struct LayerDev {
+  int kind;  // 0 conv (tcgen05), 1 linear (tcgen05), 2 conv direct (CUDA cores, tiny C_in)
+  int c_in, c_out, ksize, stride, pad, relu, pool;
+  int in_h, in_w, out_h, out_w;  // out = after pooling
+  int bn, swz, cblk, cblocks;    // tcgen05 tiling
+  int tw, th, tiles_w, tiles_h;
+  float* w_f32 = nullptr;  // direct conv weights [c_out][k][k][c_in]
+  float* bias = nullptr;   // [c_out]
+  __nv_bfloat16* w_hi = nullptr;
+  __nv_bfloat16* w_lo = nullptr;  // [c_out][K]
+  int64_t K = 0;
+  CUtensorMap tm_w_hi, tm_w_lo;
+};
+
+}  // namespace avld
+
+struct avld_ctx {
+  int device = 0;
+  avld_params p{};
+  int sm_count = 0;
+  int smem_optin = 0;
+
+  // derived feature geometry
+  int L = 0, F = 0, R = 0, hpb = 0, kblocks = 0;
+  int bin_lo = 0, nbins_pad = 0, ncols = 0, n_tiles_n = 0;
+  int T = 0, M = 0;            // target_frames, n_mels
+  int crop_start = 0, pad_left = 0, frames_copy = 0;
+
+  // numpy pairwise-sum plan
+  int n_leaves = 0, n_nodes = 0, n_levels = 0;
+  int32_t* d_leaf_off = nullptr;
+  int32_t* d_leaf_len = nullptr;
+  avld::PairNode* d_nodes = nullptr;
+  int32_t* d_level_start = nullptr;  // [n_levels + 1]
+
+  avld::MelTap* d_taps = nullptr;  // [nbins_pad]
+  __half* d_Bhi = nullptr;         // DFT matrix [ncols][n_fft], hi part (fp16)
+  __nv_bfloat16* d_Blo = nullptr;  //                           lo part (bf16)
+  CUtensorMap tm_B_hi, tm_B_lo;
+
+  // per-pass scratch (max_batch chunks)
+  int max_batch = 0;
+  __half* d_Ahi = nullptr;         // padded, pow2-scaled audio rows [max_batch * R + 128][hop]
+  __nv_bfloat16* d_Alo = nullptr;
+  CUtensorMap tm_A_hi, tm_A_lo;
+  float* d_inv2 = nullptr;         // [max_batch] 2^(-2 s_c)
+  float* d_melpow = nullptr;       // [max_batch * R][n_mels]
+  float* d_feat = nullptr;         // [max_batch][T][M]
+  float* d_mu = nullptr;           // [max_batch][D]
+  float* d_radii = nullptr;        // [max_batch][K<=64]
+  uint8_t* d_ok = nullptr;
+  float* d_rms = nullptr;
+
+  // encoder
+  std::vector<avld::LayerDev> layers;
+  int latent_dim = 0;
+  size_t act_elems = 0;            // per-chunk max activation elements
+  __nv_bfloat16* d_act_hi[2] = {nullptr, nullptr};
+  __nv_bfloat16* d_act_lo[2] = {nullptr, nullptr};
+  std::vector<CUtensorMap> tm_act_hi, tm_act_lo;  // per layer input maps
+
+  // host end-to-end path
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  float* d_xbuf[2] = {nullptr, nullptr};
+  float* d_cent = nullptr;
+  double* d_thr = nullptr;
+  int32_t* d_prio = nullptr;
+  int32_t* d_pred = nullptr;
+  float* d_best = nullptr;
+
+  // order-statistics scratch
+  unsigned int* d_hist = nullptr;
+  size_t hist_bytes = 0;
+};
+
+namespace avld {
+
+// tensor-map helpers (driver entry point fetched at runtime; libcuda is not linked)
+int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0, uint64_t dim1,
+                   uint64_t stride1_bytes, uint32_t box0, uint32_t box1, uint32_t swizzle_bytes);
+int encode_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, const uint64_t dims[4],
+                   const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t swizzle_bytes);
+
+// host math
+int64_t pairwise_plan(int64_t n, std::vector<int64_t>& off, std::vector<int64_t>& len, std::vector<PairNode>& nodes,
+                      std::vector<int32_t>& level_start);
+int mel_taps_host(const avld_params& p, std::vector<int32_t>& first, std::vector<float>& w0, std::vector<float>& w1,
+                  int* bin_lo, int* bin_hi);
+
+// stage launchers (each in its own translation unit)
+int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
+                int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
+int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
+int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
+int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+int launch_split_f16(const float* src, __half* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+
+}  // namespace avld

@@ -1,0 +1,428 @@
+// ctx.cu -- context life cycle, host-side tables (numpy pairwise-sum plan, slaney mel taps,
+// windowed DFT matrix) and TMA descriptor encoding.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace avld {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_enum(uint32_t bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                   : bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0, uint64_t dim1,
+                   uint64_t stride1_bytes, uint32_t box0, uint32_t box1, uint32_t swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return AVLD_ERR_CUDA;
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride1_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_enum(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVLD_CHECK(r == CUDA_SUCCESS, AVLD_ERR_CUDA,
+             "cuTensorMapEncodeTiled(2d) failed with CUresult %d (dims %llu x %llu, stride %llu, box %u x %u)", (int)r,
+             (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride1_bytes, box0, box1);
+  return AVLD_OK;
+}
+
+int encode_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, const uint64_t dims_[4],
+                   const uint64_t strides_bytes[3], const uint32_t box_[4], uint32_t swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return AVLD_ERR_CUDA;
+  cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
+  cuuint64_t strides[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_enum(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVLD_CHECK(r == CUDA_SUCCESS, AVLD_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+  return AVLD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// numpy pairwise summation plan (numpy/core/src/umath/loops_utils.h.src::pairwise_sum):
+//   n < 8: plain loop; n <= 128: 8 interleaved accumulators; else split at n/2 rounded down to a
+//   multiple of 8.  This is the tree np.mean(y**2) walks in 00_normalize_dataset_rms.py:30.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct PlanBuilder {
+  std::vector<int64_t>* off;
+  std::vector<int64_t>* len;
+  struct Raw { int l, r, height; };
+  std::vector<Raw> raw;  // internal nodes; child id >= 0 -> leaf id, < 0 -> ~(raw index)
+  int build(int64_t o, int64_t n, int* height) {
+    if (n <= 128) {
+      off->push_back(o);
+      len->push_back(n);
+      *height = 0;
+      return static_cast<int>(off->size()) - 1;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    int hl, hr;
+    const int l = build(o, n2, &hl);
+    const int r = build(o + n2, n - n2, &hr);
+    *height = (hl > hr ? hl : hr) + 1;
+    raw.push_back({l, r, *height});
+    return ~static_cast<int>(raw.size() - 1);
+  }
+};
+}  // namespace
+
+int64_t pairwise_plan(int64_t n, std::vector<int64_t>& off, std::vector<int64_t>& len, std::vector<PairNode>& nodes,
+                      std::vector<int32_t>& level_start) {
+  off.clear();
+  len.clear();
+  nodes.clear();
+  level_start.clear();
+  PlanBuilder b{&off, &len, {}};
+  int height = 0;
+  b.build(0, n, &height);
+  const int n_leaves = static_cast<int>(off.size());
+  // order internal nodes by height so that each level only depends on earlier values
+  std::vector<int> new_index(b.raw.size(), -1);
+  level_start.push_back(0);
+  for (int h = 1; h <= height; ++h) {
+    for (size_t i = 0; i < b.raw.size(); ++i)
+      if (b.raw[i].height == h) new_index[i] = static_cast<int>(nodes.size()), nodes.push_back({0, 0});
+    level_start.push_back(static_cast<int32_t>(nodes.size()));
+  }
+  for (size_t i = 0; i < b.raw.size(); ++i) {
+    auto resolve = [&](int c) { return c >= 0 ? c : n_leaves + new_index[~c]; };
+    nodes[new_index[i]] = {resolve(b.raw[i].l), resolve(b.raw[i].r)};
+  }
+  return n_leaves;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slaney mel filterbank (librosa.filters.mel, norm="slaney", htk=False), reduced to <= 2 taps per bin
+// ------------------------------------------------------------------------------------------------
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+int mel_taps_host(const avld_params& p, std::vector<int32_t>& first, std::vector<float>& w0, std::vector<float>& w1,
+                  int* bin_lo, int* bin_hi) {
+  const int nb = p.n_fft / 2 + 1, nm = p.n_mels;
+  AVLD_CHECK(nm >= 1 && nb >= 2, AVLD_ERR_INVALID, "invalid n_mels / n_fft");
+  std::vector<double> mel_f(nm + 2), fftf(nb);
+  const double m0 = hz_to_mel(p.fmin), m1 = hz_to_mel(p.fmax);
+  const double mstep = (m1 - m0) / (nm + 1);
+  for (int i = 0; i < nm + 2; ++i) mel_f[i] = mel_to_hz(i == nm + 1 ? m1 : m0 + mstep * i);  // np.linspace
+  const double fstep = (p.sr / 2.0) / (nb - 1);
+  for (int b = 0; b < nb; ++b) fftf[b] = (b == nb - 1) ? p.sr / 2.0 : fstep * b;
+  first.assign(nb, -1);
+  w0.assign(nb, 0.f);
+  w1.assign(nb, 0.f);
+  *bin_lo = -1;
+  *bin_hi = -1;
+  int prev_first = 0;
+  for (int b = 0; b < nb; ++b) {
+    int cnt = 0, f0 = -1;
+    float ww[2] = {0.f, 0.f};
+    for (int m = 0; m < nm; ++m) {
+      const double lower = -(mel_f[m] - fftf[b]) / (mel_f[m + 1] - mel_f[m]);
+      const double upper = (mel_f[m + 2] - fftf[b]) / (mel_f[m + 2] - mel_f[m + 1]);
+      const double tri = std::fmax(0.0, std::fmin(lower, upper));
+      float wf = static_cast<float>(tri);                                             // weights[i] = ... (float32 row)
+      wf = static_cast<float>(static_cast<double>(wf) * (2.0 / (mel_f[m + 2] - mel_f[m])));  // weights *= enorm
+      if (wf != 0.f) {
+        if (cnt == 0) f0 = m;
+        AVLD_CHECK(m - f0 <= 1, AVLD_ERR_UNSUPPORTED, "FFT bin %d feeds non-adjacent mel filters", b);
+        ww[m - f0] = wf;
+        ++cnt;
+      }
+    }
+    if (cnt > 0) {
+      AVLD_CHECK(f0 >= prev_first, AVLD_ERR_UNSUPPORTED, "mel filter order is not monotone at bin %d", b);
+      first[b] = f0;
+      w0[b] = ww[0];
+      w1[b] = ww[1];
+      prev_first = f0;
+      if (*bin_lo < 0) *bin_lo = b;
+      *bin_hi = b;
+    }
+  }
+  AVLD_CHECK(*bin_lo >= 0, AVLD_ERR_INVALID, "mel filterbank is empty for these parameters");
+  return AVLD_OK;
+}
+
+}  // namespace avld
+
+using namespace avld;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int avld_abi_version(void) { return AVLD_ABI_VERSION; }
+extern "C" const char* avld_last_error(void) { return g_err; }
+
+extern "C" int64_t avld_pairwise_plan(int64_t n, int64_t* leaf_offset, int64_t* leaf_len, int64_t cap) {
+  if (n < 0) {
+    set_error("negative length");
+    return AVLD_ERR_INVALID;
+  }
+  std::vector<int64_t> off, len;
+  std::vector<PairNode> nodes;
+  std::vector<int32_t> ls;
+  const int64_t nl = pairwise_plan(n, off, len, nodes, ls);
+  for (int64_t i = 0; i < nl && i < cap; ++i) {
+    if (leaf_offset) leaf_offset[i] = off[i];
+    if (leaf_len) leaf_len[i] = len[i];
+  }
+  return nl;
+}
+
+extern "C" int avld_mel_taps(const avld_params* params, int32_t* first, float* w0, float* w1) {
+  AVLD_CHECK(params != nullptr, AVLD_ERR_INVALID, "params is NULL");
+  std::vector<int32_t> f;
+  std::vector<float> a, b;
+  int lo, hi;
+  AVLD_TRY(mel_taps_host(*params, f, a, b, &lo, &hi));
+  for (size_t i = 0; i < f.size(); ++i) {
+    if (first) first[i] = f[i];
+    if (w0) w0[i] = a[i];
+    if (w1) w1[i] = b[i];
+  }
+  return AVLD_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count) {
+  AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  return AVLD_OK;
+}
+
+static int build_ctx(avld_ctx* c) {
+  const avld_params& p = c->p;
+  AVLD_CHECK(p.sr > 0 && p.n_fft >= 64 && p.hop > 0 && p.n_mels > 0 && p.target_frames > 0 && p.chunk_len > 0,
+             AVLD_ERR_INVALID, "non-positive feature parameter");
+  AVLD_CHECK(p.n_fft % 64 == 0, AVLD_ERR_UNSUPPORTED, "n_fft must be a multiple of 64 (got %d)", p.n_fft);
+  AVLD_CHECK(p.hop % 64 == 0, AVLD_ERR_UNSUPPORTED, "hop_length must be a multiple of 64 (got %d)", p.hop);
+  AVLD_CHECK(p.chunk_len > p.n_fft / 2, AVLD_ERR_UNSUPPORTED, "chunk_len must exceed n_fft/2 (reflect padding)");
+  AVLD_CHECK(p.n_mels <= 256, AVLD_ERR_UNSUPPORTED, "n_mels > 256");
+  AVLD_CHECK(p.amin > 0.f && p.top_db >= 0.f, AVLD_ERR_INVALID, "amin must be > 0 and top_db >= 0");
+  AVLD_CHECK(p.max_batch >= 1, AVLD_ERR_INVALID, "max_batch must be >= 1");
+  c->L = p.chunk_len;
+  c->F = 1 + p.chunk_len / p.hop;
+  c->R = (p.chunk_len + p.n_fft + p.hop - 1) / p.hop;
+  c->hpb = p.hop / 64;
+  c->kblocks = p.n_fft / 64;
+  c->T = p.target_frames;
+  c->M = p.n_mels;
+  c->max_batch = p.max_batch;
+  if (c->F >= c->T) {
+    c->crop_start = (c->F - c->T) / 2;
+    c->pad_left = 0;
+    c->frames_copy = c->T;
+  } else {
+    c->crop_start = 0;
+    c->pad_left = (c->T - c->F) / 2;
+    c->frames_copy = c->F;
+  }
+  AVLD_CHECK(static_cast<size_t>(c->F) * c->M * sizeof(float) <= 200 * 1024, AVLD_ERR_UNSUPPORTED,
+             "chunk too long: %d frames x %d mels do not fit the log-mel kernel's shared memory", c->F, c->M);
+
+  // ---- pairwise plan
+  std::vector<int64_t> off, len;
+  std::vector<PairNode> nodes;
+  std::vector<int32_t> level_start;
+  c->n_leaves = static_cast<int>(pairwise_plan(c->L, off, len, nodes, level_start));
+  c->n_nodes = static_cast<int>(nodes.size());
+  c->n_levels = static_cast<int>(level_start.size()) - 1;
+  AVLD_CHECK(static_cast<size_t>(c->n_leaves + c->n_nodes) * 4 <= 160 * 1024, AVLD_ERR_UNSUPPORTED, "chunk_len too large");
+  std::vector<int32_t> off32(off.begin(), off.end()), len32(len.begin(), len.end());
+  AVLD_TRY(dev_alloc(&c->d_leaf_off, off32.size()));
+  AVLD_TRY(dev_alloc(&c->d_leaf_len, len32.size()));
+  AVLD_TRY(dev_alloc(&c->d_nodes, nodes.size() + 1));
+  AVLD_TRY(dev_alloc(&c->d_level_start, level_start.size()));
+  AVLD_CUDA(cudaMemcpy(c->d_leaf_off, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice));
+  AVLD_CUDA(cudaMemcpy(c->d_leaf_len, len32.data(), len32.size() * 4, cudaMemcpyHostToDevice));
+  if (!nodes.empty())
+    AVLD_CUDA(cudaMemcpy(c->d_nodes, nodes.data(), nodes.size() * sizeof(PairNode), cudaMemcpyHostToDevice));
+  AVLD_CUDA(cudaMemcpy(c->d_level_start, level_start.data(), level_start.size() * 4, cudaMemcpyHostToDevice));
+
+  // ---- mel taps, restricted to the FFT bins that carry weight
+  std::vector<int32_t> first;
+  std::vector<float> w0, w1;
+  int bin_lo, bin_hi;
+  AVLD_TRY(mel_taps_host(p, first, w0, w1, &bin_lo, &bin_hi));
+  c->bin_lo = bin_lo;
+  const int nbins = bin_hi - bin_lo + 1;
+  c->nbins_pad = (nbins + 127) / 128 * 128;
+  c->n_tiles_n = c->nbins_pad / 128;
+  c->ncols = 2 * c->nbins_pad;
+  AVLD_CHECK(static_cast<size_t>(c->nbins_pad) * sizeof(MelTap) <= 14000, AVLD_ERR_UNSUPPORTED, "too many FFT bins");
+  std::vector<MelTap> taps(c->nbins_pad);
+  int run_first = 0;
+  for (int i = 0; i < c->nbins_pad; ++i) {
+    const int b = bin_lo + i;
+    if (b <= bin_hi && first[b] >= 0) {
+      run_first = first[b];
+      taps[i] = {first[b], w0[b], w1[b]};
+    } else {
+      taps[i] = {run_first, 0.f, 0.f};
+    }
+  }
+  AVLD_TRY(dev_alloc(&c->d_taps, taps.size()));
+  AVLD_CUDA(cudaMemcpy(c->d_taps, taps.data(), taps.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
+
+  // ---- windowed DFT matrix B[col][k]; N tile t holds Re of bins [128t, 128t+128) then Im of the same bins
+  {
+    const int nf = p.n_fft;
+    std::vector<double> win(nf), ct(nf), stab(nf);
+    for (int k = 0; k < nf; ++k) {
+      win[k] = 0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf);  // scipy get_window('hann', n, fftbins=True)
+      ct[k] = std::cos(2.0 * M_PI * k / nf);
+      stab[k] = std::sin(2.0 * M_PI * k / nf);
+    }
+    std::vector<__half> hi(static_cast<size_t>(c->ncols) * nf);
+    std::vector<__nv_bfloat16> lo(hi.size());
+    for (int col = 0; col < c->ncols; ++col) {
+      const int tile = col / 256, part = (col % 256) / 128, j = col % 128;
+      const int bin = bin_lo + tile * 128 + j;
+      for (int k = 0; k < nf; ++k) {
+        double v = 0.0;
+        if (bin <= nf / 2) {
+          const int ph = static_cast<int>((static_cast<long long>(k) * bin) % nf);
+          v = win[k] * (part == 0 ? ct[ph] : -stab[ph]);
+        }
+        const float vf = static_cast<float>(v);
+        const __half h = __float2half_rn(vf);
+        hi[static_cast<size_t>(col) * nf + k] = h;
+        lo[static_cast<size_t>(col) * nf + k] = __float2bfloat16_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+      }
+    }
+    AVLD_TRY(dev_alloc(&c->d_Bhi, hi.size()));
+    AVLD_TRY(dev_alloc(&c->d_Blo, lo.size()));
+    AVLD_CUDA(cudaMemcpy(c->d_Bhi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    AVLD_CUDA(cudaMemcpy(c->d_Blo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B_hi, c->d_Bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B_lo, c->d_Blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
+  }
+
+  // ---- per-pass scratch
+  const size_t rows = static_cast<size_t>(c->max_batch) * c->R + 136;
+  AVLD_TRY(dev_alloc(&c->d_Ahi, rows * p.hop));
+  AVLD_TRY(dev_alloc(&c->d_Alo, rows * p.hop));
+  AVLD_CUDA(cudaMemset(c->d_Ahi, 0, rows * p.hop * 2));
+  AVLD_CUDA(cudaMemset(c->d_Alo, 0, rows * p.hop * 2));
+  AVLD_TRY(encode_tmap_2d(&c->tm_A_hi, c->d_Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+  AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+  AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
+  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->max_batch) * c->R * c->M));
+  AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
+  AVLD_TRY(dev_alloc(&c->d_ok, c->max_batch));
+  AVLD_TRY(dev_alloc(&c->d_rms, c->max_batch));
+  AVLD_TRY(dev_alloc(&c->d_radii, static_cast<size_t>(c->max_batch) * 64));
+  AVLD_TRY(dev_alloc(&c->d_pred, c->max_batch));
+  AVLD_TRY(dev_alloc(&c->d_best, c->max_batch));
+  AVLD_CUDA(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+  AVLD_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    AVLD_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+    AVLD_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  }
+  return AVLD_OK;
+}
+
+extern "C" int avld_ctx_create(int device, const avld_params* params, avld_ctx** out) {
+  AVLD_CHECK(params != nullptr && out != nullptr, AVLD_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  AVLD_CHECK(e == cudaSuccess && ndev > 0, AVLD_ERR_CUDA,
+             "no CUDA device available (%s); libavld has no CPU fallback", cudaGetErrorString(e));
+  AVLD_CHECK(device >= 0 && device < ndev, AVLD_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  AVLD_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  AVLD_CUDA(cudaGetDeviceProperties(&prop, device));
+  AVLD_CHECK(prop.major == 10, AVLD_ERR_UNSUPPORTED,
+             "libavld is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+  avld_ctx* c = new avld_ctx();
+  c->device = device;
+  c->p = *params;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  const int r = build_ctx(c);
+  if (r != AVLD_OK) {
+    avld_ctx_destroy(c);
+    return r;
+  }
+  *out = c;
+  return AVLD_OK;
+}
+
+extern "C" void avld_ctx_destroy(avld_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
+                  c->d_Alo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
+                  c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
+                  c->d_prio, c->d_pred, c->d_best, c->d_hist};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (auto& l : c->layers) {
+    if (l.w_f32) cudaFree(l.w_f32);
+    if (l.bias) cudaFree(l.bias);
+    if (l.w_hi) cudaFree(l.w_hi);
+    if (l.w_lo) cudaFree(l.w_lo);
+  }
+  if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
+  delete c;
+}
+
+extern "C" int avld_ctx_info(const avld_ctx* c, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count) {
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n_frames) *n_frames = c->F;
+  if (latent_dim) *latent_dim = c->latent_dim;
+  if (sm_count) *sm_count = c->sm_count;
+  return AVLD_OK;
+}

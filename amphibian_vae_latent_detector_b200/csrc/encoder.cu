@@ -1,0 +1,329 @@
+// encoder.cu -- L1/E1/E2: the VAE encoder forward to the latent mean (map_detector_core.py:270-300)
+// for an arbitrary chain of Conv2d(+folded BN)(+ReLU)(+MaxPool2d(2)) and Linear(+ReLU) layers.
+//
+//   first conv (tiny C_in, e.g. 1)  conv_direct_kernel on CUDA cores: fp32 feature map in, NHWC
+//                                   bf16 hi/lo activations out (K = 9 is no tensor-core shape)
+//   other convs                     implicit GEMM on tcgen05: one TMA box of the NHWC activation per
+//                                   filter tap (zero padding = TMA out-of-bounds fill), weights
+//                                   [C_out][kh*kw*C_in] K-major, epilogue bias + ReLU + 2x2 max pool
+//                                   (warp shuffles) + hi/lo split
+//   linears                         plain GEMM on tcgen05 over the flattened NHWC activations
+// Activations and weights are bf16 hi + bf16 lo pairs (3 MMAs per K step, ~2^-17 relative error).
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm3.cuh"
+
+namespace avld {
+
+__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = src[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __half2float(h));
+  }
+}
+int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return AVLD_OK;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
+  split_bf16_kernel<<<grid, 256, 0, st>>>(src, hi, lo, n);
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+int launch_split_f16(const float* src, __half* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return AVLD_OK;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
+  split_f16_kernel<<<grid, 256, 0, st>>>(src, hi, lo, n);
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct convolution for the first layer (fp32 NHWC input with a handful of channels)
+// one thread = one (pooled) output pixel, all output channels in groups of 8
+// ------------------------------------------------------------------------------------------------
+struct DirectConvParams {
+  const float* in;          // [n][H][W][Cin] fp32
+  const float* w;           // [Cout][k][k][Cin]
+  const float* bias;        // [Cout]
+  __nv_bfloat16* out_hi;    // [n][OH][OW][Cout]
+  __nv_bfloat16* out_lo;
+  int H, W, Cin, Cout, k, pad, relu, pool, OH, OW, rows_per_block;
+};
+
+__global__ void __launch_bounds__(256) conv_direct_kernel(const DirectConvParams P) {
+  extern __shared__ float s_mem[];
+  const int in_rows = P.rows_per_block * P.pool + P.k - 1;
+  const int in_cols = P.W + P.k - 1;
+  float* s_in = s_mem;                                           // [in_rows][in_cols][Cin]
+  float* s_w = s_in + in_rows * in_cols * P.Cin;                 // [Cout][k*k*Cin]
+  float* s_b = s_w + P.Cout * P.k * P.k * P.Cin;                 // [Cout]
+  const int img = blockIdx.y;
+  const int orow0 = blockIdx.x * P.rows_per_block;               // first (pooled) output row of this block
+  const int irow0 = orow0 * P.pool - P.pad;
+  const float* __restrict__ src = P.in + static_cast<size_t>(img) * P.H * P.W * P.Cin;
+  for (int i = threadIdx.x; i < in_rows * in_cols * P.Cin; i += blockDim.x) {
+    const int ci = i % P.Cin, cc = (i / P.Cin) % in_cols, rr = i / (P.Cin * in_cols);
+    const int h = irow0 + rr, w = cc - P.pad;
+    s_in[i] = (h >= 0 && h < P.H && w >= 0 && w < P.W) ? src[(static_cast<size_t>(h) * P.W + w) * P.Cin + ci] : 0.f;
+  }
+  const int kk = P.k * P.k * P.Cin;
+  for (int i = threadIdx.x; i < P.Cout * kk; i += blockDim.x) s_w[i] = P.w[i];
+  for (int i = threadIdx.x; i < P.Cout; i += blockDim.x) s_b[i] = P.bias[i];
+  __syncthreads();
+
+  const int npix = P.rows_per_block * P.OW;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    const int orl = pix / P.OW, oc = pix - orl * P.OW;
+    const int orow = orow0 + orl;
+    if (orow >= P.OH) continue;
+    const size_t obase = ((static_cast<size_t>(img) * P.OH + orow) * P.OW + oc) * P.Cout;
+    for (int co0 = 0; co0 < P.Cout; co0 += 8) {
+      float best[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) best[q] = -INFINITY;
+      for (int ph = 0; ph < P.pool; ++ph) {
+        for (int pw = 0; pw < P.pool; ++pw) {
+          float a[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a[q] = (co0 + q < P.Cout) ? s_b[co0 + q] : 0.f;
+          const int r0 = orl * P.pool + ph, c0 = oc * P.pool + pw;
+          for (int kh = 0; kh < P.k; ++kh)
+            for (int kw = 0; kw < P.k; ++kw)
+              for (int ci = 0; ci < P.Cin; ++ci) {
+                const float v = s_in[((r0 + kh) * in_cols + (c0 + kw)) * P.Cin + ci];
+                const int wi = (kh * P.k + kw) * P.Cin + ci;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (co0 + q < P.Cout) a[q] = fmaf(v, s_w[(co0 + q) * kk + wi], a[q]);
+              }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) best[q] = fmaxf(best[q], a[q]);
+        }
+      }
+      for (int q = 0; q < 8 && co0 + q < P.Cout; ++q) {
+        float t = best[q];
+        if (P.relu) t = fmaxf(t, 0.f);
+        const __nv_bfloat16 h = __float2bfloat16_rn(t);
+        P.out_hi[obase + co0 + q] = h;
+        P.out_lo[obase + co0 + q] = __float2bfloat16_rn(t - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+static int pick_bn(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 256); }
+
+int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st) {
+  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  if (n <= 0) return AVLD_OK;
+  for (size_t li = 0; li < c->layers.size(); ++li) {
+    const LayerDev& L = c->layers[li];
+    __nv_bfloat16* out_hi = c->d_act_hi[li & 1];
+    __nv_bfloat16* out_lo = c->d_act_lo[li & 1];
+    const bool last = (li + 1 == c->layers.size());
+    if (L.kind == 2) {
+      DirectConvParams P{};
+      P.in = feat;
+      P.w = L.w_f32;
+      P.bias = L.bias;
+      P.out_hi = out_hi;
+      P.out_lo = out_lo;
+      P.H = L.in_h; P.W = L.in_w; P.Cin = L.c_in; P.Cout = L.c_out; P.k = L.ksize; P.pad = L.pad;
+      P.relu = L.relu; P.pool = L.pool; P.OH = L.out_h; P.OW = L.out_w;
+      P.rows_per_block = std::max(1, 256 / L.out_w);
+      const int in_rows = P.rows_per_block * P.pool + P.k - 1, in_cols = P.W + P.k - 1;
+      const size_t smem = (static_cast<size_t>(in_rows) * in_cols * P.Cin + static_cast<size_t>(P.Cout) * P.k * P.k * P.Cin + P.Cout) * sizeof(float);
+      AVLD_CHECK(smem <= 48 * 1024, AVLD_ERR_UNSUPPORTED, "first-layer direct convolution tile does not fit shared memory");
+      dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
+      conv_direct_kernel<<<grid, 256, smem, st>>>(P);
+      AVLD_CUDA(cudaGetLastError());
+    } else if (L.kind == 0) {
+      Gemm3Params P{};
+      const int H = L.in_h, W = L.in_w;  // same-size convolution
+      P.num_m_tiles = n * L.tiles_w * L.tiles_h;
+      P.num_n_tiles = (L.c_out + L.bn - 1) / L.bn;
+      P.num_k_blocks = L.ksize * L.ksize * L.cblocks;
+      P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(1, 1, 128, L.bn);
+      P.a_mode = 2;
+      P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.tw = L.tw; P.th = L.th; P.ksize = L.ksize;
+      P.cblocks = L.cblocks; P.cblk = L.cblk; P.pad = L.pad;
+      P.M_total = static_cast<long long>(P.num_m_tiles) * 128;
+      P.N_total = L.c_out;
+      P.bias = L.bias;
+      P.relu = L.relu;
+      P.out_hi = out_hi;
+      P.out_lo = out_lo;
+      P.H = H; P.W = W; P.Cout = L.c_out; P.pool = L.pool;
+      AVLD_TRY(run_gemm3(L.bn, L.swz, EPI_CONV, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
+    } else {
+      Gemm3Params P{};
+      P.num_m_tiles = (n + 127) / 128;
+      P.num_n_tiles = (L.c_out + L.bn - 1) / L.bn;
+      P.num_k_blocks = static_cast<int>(L.K / 64);
+      P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(1, 1, 128, L.bn);
+      P.a_mode = 0;
+      P.M_total = n;
+      P.N_total = L.c_out;
+      P.bias = L.bias;
+      P.relu = L.relu;
+      P.ldc = L.c_out;
+      if (last) {
+        P.out_f32 = mu;
+      } else {
+        P.out_hi = out_hi;
+        P.out_lo = out_lo;
+      }
+      AVLD_TRY(run_gemm3(L.bn, 128, EPI_PLAIN, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
+    }
+  }
+  return AVLD_OK;
+}
+
+}  // namespace avld
+
+using namespace avld;
+
+extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t n_layers) {
+  AVLD_CHECK(c && layers && n_layers > 0, AVLD_ERR_INVALID, "NULL / empty layer list");
+  AVLD_CHECK(c->layers.empty(), AVLD_ERR_STATE, "an encoder is already loaded into this context");
+  AVLD_CUDA(cudaSetDevice(c->device));
+  std::vector<LayerDev> out;
+  int h = c->T, w = c->M, ch = 1;
+  bool flat = false;
+  size_t act_elems = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const avld_layer& s = layers[i];
+    LayerDev L{};
+    L.c_in = s.c_in; L.c_out = s.c_out; L.ksize = s.ksize; L.stride = s.stride; L.pad = s.pad;
+    L.relu = s.relu; L.pool = s.pool > 1 ? s.pool : 1;
+    AVLD_CHECK(s.weight && s.bias, AVLD_ERR_INVALID, "layer %d: NULL weights", i);
+    size_t out_elems = 0;
+    if (s.kind == 0) {
+      AVLD_CHECK(!flat, AVLD_ERR_UNSUPPORTED, "layer %d: convolution after a linear layer", i);
+      AVLD_CHECK(s.in_h == h && s.in_w == w && s.c_in == ch, AVLD_ERR_INVALID,
+                 "layer %d: expects input %dx%dx%d but the previous layer produces %dx%dx%d", i, s.in_h, s.in_w, s.c_in, h, w, ch);
+      AVLD_CHECK(s.stride == 1 && s.ksize % 2 == 1 && s.pad == s.ksize / 2, AVLD_ERR_UNSUPPORTED,
+                 "layer %d: only stride-1 'same' convolutions are implemented", i);
+      AVLD_CHECK(L.pool == 1 || L.pool == 2, AVLD_ERR_UNSUPPORTED, "layer %d: pool must be 1 or 2", i);
+      AVLD_CHECK(L.pool == 1 || (h % 2 == 0 && w % 2 == 0), AVLD_ERR_UNSUPPORTED, "layer %d: pooling an odd map", i);
+      L.in_h = h; L.in_w = w; L.out_h = h / L.pool; L.out_w = w / L.pool;
+      const size_t wcount = static_cast<size_t>(s.c_out) * s.ksize * s.ksize * s.c_in;
+      L.K = static_cast<int64_t>(s.ksize) * s.ksize * s.c_in;
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.bias), s.c_out * sizeof(float)));
+      AVLD_CUDA(cudaMemcpy(L.bias, s.bias, s.c_out * sizeof(float), cudaMemcpyHostToDevice));
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_f32), wcount * sizeof(float)));
+      AVLD_CUDA(cudaMemcpy(L.w_f32, s.weight, wcount * sizeof(float), cudaMemcpyHostToDevice));
+      if (i == 0 && s.c_in <= 4) {
+        L.kind = 2;
+      } else {
+        AVLD_CHECK(i > 0, AVLD_ERR_UNSUPPORTED, "layer 0 must have <= 4 input channels");
+        AVLD_CHECK(s.c_in == 32 || s.c_in % 64 == 0, AVLD_ERR_UNSUPPORTED,
+                   "layer %d: C_in must be 32 or a multiple of 64 for the tensor-core path (got %d)", i, s.c_in);
+        AVLD_CHECK(s.c_out % 16 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: C_out must be a multiple of 16", i);
+        L.kind = 0;
+        L.cblk = s.c_in == 32 ? 32 : 64;
+        L.swz = L.cblk * 2;
+        L.cblocks = s.c_in / L.cblk;
+        L.bn = pick_bn(s.c_out);
+        L.tw = (w % 16 == 0) ? 16 : 8;
+        AVLD_CHECK(w % L.tw == 0, AVLD_ERR_UNSUPPORTED, "layer %d: width %d is not a multiple of 8", i, w);
+        L.th = 128 / L.tw;
+        L.tiles_w = w / L.tw;
+        L.tiles_h = (h + L.th - 1) / L.th;
+        AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_hi), wcount * 2));
+        AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_lo), wcount * 2));
+        AVLD_TRY(launch_split_bf16(L.w_f32, L.w_hi, L.w_lo, wcount, nullptr));
+        AVLD_TRY(encode_tmap_2d(&L.tm_w_hi, L.w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, L.cblk, L.bn, L.swz));
+        AVLD_TRY(encode_tmap_2d(&L.tm_w_lo, L.w_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, L.cblk, L.bn, L.swz));
+      }
+      h = L.out_h; w = L.out_w; ch = s.c_out;
+      out_elems = static_cast<size_t>(h) * w * ch;
+    } else if (s.kind == 1) {
+      const int in_features = flat ? ch : h * w * ch;
+      AVLD_CHECK(i > 0, AVLD_ERR_UNSUPPORTED, "the first layer must be a convolution");
+      AVLD_CHECK(s.c_in == in_features, AVLD_ERR_INVALID, "layer %d: linear expects %d inputs, previous layer gives %d", i, s.c_in, in_features);
+      AVLD_CHECK(s.c_in % 64 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: linear in_features must be a multiple of 64", i);
+      AVLD_CHECK(s.c_out % 16 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: linear out_features must be a multiple of 16", i);
+      L.kind = 1;
+      L.K = s.c_in;
+      L.bn = pick_bn(s.c_out);
+      L.swz = 128;
+      const size_t wcount = static_cast<size_t>(s.c_out) * s.c_in;
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.bias), s.c_out * sizeof(float)));
+      AVLD_CUDA(cudaMemcpy(L.bias, s.bias, s.c_out * sizeof(float), cudaMemcpyHostToDevice));
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_f32), wcount * sizeof(float)));
+      AVLD_CUDA(cudaMemcpy(L.w_f32, s.weight, wcount * sizeof(float), cudaMemcpyHostToDevice));
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_hi), wcount * 2));
+      AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.w_lo), wcount * 2));
+      AVLD_TRY(launch_split_bf16(L.w_f32, L.w_hi, L.w_lo, wcount, nullptr));
+      AVLD_TRY(encode_tmap_2d(&L.tm_w_hi, L.w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, 64, L.bn, 128));
+      AVLD_TRY(encode_tmap_2d(&L.tm_w_lo, L.w_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, 64, L.bn, 128));
+      flat = true;
+      ch = s.c_out;
+      out_elems = ch;
+    } else {
+      AVLD_CHECK(false, AVLD_ERR_INVALID, "layer %d: unknown kind %d", i, s.kind);
+    }
+    act_elems = std::max(act_elems, out_elems);
+    out.push_back(L);
+  }
+  AVLD_CHECK(out.back().kind == 1, AVLD_ERR_UNSUPPORTED, "the last layer must be the linear latent-mean head");
+  AVLD_CUDA(cudaDeviceSynchronize());
+
+  // ping-pong activation buffers + per-layer input tensor maps
+  c->act_elems = act_elems;
+  const size_t total = act_elems * static_cast<size_t>(c->max_batch) + 128 * 256;
+  for (int b = 0; b < 2; ++b) {
+    AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_act_hi[b]), total * 2));
+    AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_act_lo[b]), total * 2));
+    AVLD_CUDA(cudaMemset(c->d_act_hi[b], 0, total * 2));
+    AVLD_CUDA(cudaMemset(c->d_act_lo[b], 0, total * 2));
+  }
+  c->tm_act_hi.assign(out.size(), CUtensorMap{});
+  c->tm_act_lo.assign(out.size(), CUtensorMap{});
+  for (size_t li = 1; li < out.size(); ++li) {
+    const LayerDev& L = out[li];
+    const __nv_bfloat16* in_hi = c->d_act_hi[(li - 1) & 1];
+    const __nv_bfloat16* in_lo = c->d_act_lo[(li - 1) & 1];
+    if (L.kind == 0) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(L.c_in), static_cast<uint64_t>(L.in_w), static_cast<uint64_t>(L.in_h),
+                                static_cast<uint64_t>(c->max_batch)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(L.c_in) * 2, static_cast<uint64_t>(L.in_w) * L.c_in * 2,
+                                   static_cast<uint64_t>(L.in_h) * L.in_w * L.c_in * 2};
+      const uint32_t box[4] = {static_cast<uint32_t>(L.cblk), static_cast<uint32_t>(L.tw), static_cast<uint32_t>(L.th), 1};
+      AVLD_TRY(encode_tmap_4d(&c->tm_act_hi[li], in_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims, strides, box, L.swz));
+      AVLD_TRY(encode_tmap_4d(&c->tm_act_lo[li], in_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims, strides, box, L.swz));
+    } else if (L.kind == 1) {
+      const uint64_t rows = static_cast<uint64_t>(c->max_batch);   // rows past n: TMA zero fill
+      AVLD_TRY(encode_tmap_2d(&c->tm_act_hi[li], in_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, rows, L.K * 2, 64, 128, 128));
+      AVLD_TRY(encode_tmap_2d(&c->tm_act_lo[li], in_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, rows, L.K * 2, 64, 128, 128));
+    }
+  }
+  c->latent_dim = out.back().c_out;
+  AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_mu), static_cast<size_t>(c->max_batch) * c->latent_dim * sizeof(float)));
+  c->layers = std::move(out);
+  return AVLD_OK;
+}
+
+extern "C" int avld_encoder_forward(avld_ctx* c, const float* feat, float* mu, int64_t n, void* stream) {
+  AVLD_CHECK(c && feat && mu, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t i = 0; i < n; i += c->max_batch) {
+    const int m = static_cast<int>(n - i < c->max_batch ? n - i : c->max_batch);
+    AVLD_TRY(launch_encoder(c, feat + i * c->T * c->M, mu + i * c->latent_dim, m, st));
+  }
+  return AVLD_OK;
+}

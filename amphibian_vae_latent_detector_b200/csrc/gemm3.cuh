@@ -1,0 +1,380 @@
+// gemm3.cuh -- split-precision GEMM core on tcgen05 / TMEM (sm_100a), shared by the STFT
+// (windowed DFT as a GEMM), the encoder's implicit-GEMM convolutions and its dense layers.
+//
+//   D[128 x BN] (fp32, TMEM) += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo       per 16-wide K step
+//
+// Every fp32 operand is pre-split into a 16-bit "hi" part and a bf16 "lo" remainder, so three
+// kind::f16 MMAs reproduce an fp32-accurate product (error ~2^-20) at the 16-bit tensor rate.
+// The reference computes this path in float64 FFT / float32 torch, and the parity target is
+// 1e-3 on latents behind an 80 dB log floor: one 16-bit pass is not enough.
+//
+// Structure (one CTA per SM, persistent over M tiles, 192 threads):
+//   warp 0 / lane 0 : TMA producer  -- A (hi, lo) and B (hi, lo) boxes into a STAGES-deep smem ring
+//   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma, tcgen05.commit frees smem slots / publishes TMEM
+//   warps 2..5      : epilogue      -- tcgen05.ld from a double-buffered TMEM accumulator
+// A tiles are addressed three ways (a_mode):
+//   0  plain row-major [M, K]                      box (k0, m0)
+//   1  audio rows [n_rows, hop] (frame g, tap k lives at row g + k / hop, column k % hop: the STFT's
+//      im2col is free -- frames are overlapping windows, so no frame matrix is ever materialised)
+//   2  NHWC activations [N, H, W, C]: one box per filter tap, shifted by (kh - pad, kw - pad);
+//      TMA out-of-bounds zero fill *is* the convolution's zero padding
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace avld {
+
+enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2 };
+
+struct Gemm3Params {
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
+  int a_mode;
+  int hpb;  // a_mode 1: 64-sample blocks per hop
+  // a_mode 2 geometry
+  int tiles_w, tiles_h, tw, th, ksize, cblocks, cblk, pad;
+  // common epilogue
+  long long M_total;
+  int N_total;
+  const float* bias;
+  int relu;
+  float* out_f32;           // PLAIN: C[M_total][ldc]
+  int ldc;
+  __nv_bfloat16* out_hi;    // PLAIN/CONV: split output for the next tensor-core layer
+  __nv_bfloat16* out_lo;
+  // DFT epilogue
+  const float* inv2;        // per chunk 2^(-2 s)
+  const MelTap* taps;       // [nbins_pad]
+  float* melpow;            // [rows][n_mels]
+  int R, F, n_mels, nbins_pad;
+  // CONV epilogue
+  int H, W, Cout, pool;     // H, W: conv output size before pooling
+};
+
+// non-template dispatcher (all instantiations live in gemm3.cu)
+int run_gemm3(int bn, int swz, int epi, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+              const CUtensorMap& tmB_lo, const Gemm3Params& P, int sm_count, cudaStream_t st);
+
+#ifdef AVLD_GEMM3_IMPL
+template <int BN, int SWZ>
+struct Gemm3Cfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = SWZ / 2;                       // 16-bit elements per swizzle row
+  static constexpr int A_BYTES = BM * SWZ;                 // one of hi / lo
+  static constexpr int B_BYTES = BN * SWZ;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int EXTRA = 16384;                      // barriers, taps, alignment slack
+  static constexpr int STAGES_RAW = (227 * 1024 - EXTRA) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static_assert(STAGES >= 2, "tile too large for shared memory");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+};
+
+template <int BN, int SWZ, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+             const Gemm3Params P) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL)
+  using Cfg = Gemm3Cfg<BN, SWZ>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* tail = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
+  uint64_t* tmem_full = empty_bar + STAGES;                          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);            // EPI_DFT only (<= 12 KB)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (EPI == EPI_DFT) {
+    for (int i = threadIdx.x; i < P.nbins_pad; i += blockDim.x) s_taps[i] = P.taps[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = P.num_k_blocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
+        int img = 0, h0 = 0, w0 = 0;
+        if (P.a_mode == 2) {
+          const int per_img = P.tiles_w * P.tiles_h;
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          h0 = (r / P.tiles_w) * P.th;
+          w0 = (r % P.tiles_w) * P.tw;
+        }
+        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+            uint8_t* sa_hi = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sa_lo = sa_hi + Cfg::A_BYTES;
+            uint8_t* sb_hi = sa_lo + Cfg::A_BYTES;
+            uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (P.a_mode == 0) {
+              tma_load_2d(sa_hi, &tmA_hi, &full_bar[stage], kb * Cfg::BK, mt * Cfg::BM);
+              tma_load_2d(sa_lo, &tmA_lo, &full_bar[stage], kb * Cfg::BK, mt * Cfg::BM);
+            } else if (P.a_mode == 1) {
+              const int x = (kb % P.hpb) * Cfg::BK;
+              const int y = mt * Cfg::BM + kb / P.hpb;
+              tma_load_2d(sa_hi, &tmA_hi, &full_bar[stage], x, y);
+              tma_load_2d(sa_lo, &tmA_lo, &full_bar[stage], x, y);
+            } else {
+              const int tap = kb / P.cblocks;
+              const int cb = kb - tap * P.cblocks;
+              const int kh = tap / P.ksize, kw = tap - kh * P.ksize;
+              tma_load_4d(sa_hi, &tmA_hi, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
+              tma_load_4d(sa_lo, &tmA_lo, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
+            }
+            tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
+            tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase, 300 + stage);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+            const uint32_t b_hi = a_lo + Cfg::A_BYTES;
+            const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+            const uint64_t da_hi = make_smem_desc(a_hi, SWZ), da_lo = make_smem_desc(a_lo, SWZ);
+            const uint64_t db_hi = make_smem_desc(b_hi, SWZ), db_lo = make_smem_desc(b_lo, SWZ);
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B, in 16 B units
+              umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc_hh, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc_lh, 1u);
+              umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc_hl, 1u);
+            }
+            umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
+      // ---- per M-tile state
+      [[maybe_unused]] int cur = 0;
+      [[maybe_unused]] float acc0 = 0.f, acc1 = 0.f, s2 = 0.f;
+      [[maybe_unused]] bool valid = false;
+      [[maybe_unused]] long long g = 0;
+      if (EPI == EPI_DFT) {
+        g = static_cast<long long>(mt) * Cfg::BM + row;
+        const long long c = g / P.R;
+        const int f = static_cast<int>(g - c * P.R);
+        valid = (g < P.M_total) && (f < P.F);
+        s2 = valid ? P.inv2[c] : 0.f;
+      }
+      for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+        mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+        tcgen05_fence_after();
+        const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
+
+        if (EPI == EPI_PLAIN) {
+          const long long m = static_cast<long long>(mt) * Cfg::BM + row;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + c0, v);
+            tmem_ld_wait();
+            const int n0 = nt * BN + c0;
+            if (m < P.M_total && n0 < P.N_total) {
+              float o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float t = __uint_as_float(v[j]);
+                if (P.bias != nullptr && n0 + j < P.N_total) t += P.bias[n0 + j];
+                if (P.relu) t = fmaxf(t, 0.f);
+                o[j] = t;
+              }
+              if (P.out_f32 != nullptr) {
+                float* dst = P.out_f32 + m * P.ldc + n0;
+                if (n0 + 16 <= P.N_total && (P.ldc & 3) == 0) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                } else {
+                  for (int j = 0; j < 16 && n0 + j < P.N_total; ++j) dst[j] = o[j];
+                }
+              }
+              if (P.out_hi != nullptr) {
+                for (int j = 0; j < 16 && n0 + j < P.N_total; ++j) {
+                  const __nv_bfloat16 hi = __float2bfloat16_rn(o[j]);
+                  P.out_hi[m * P.ldc + n0 + j] = hi;
+                  P.out_lo[m * P.ldc + n0 + j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi));
+                }
+              }
+            }
+          }
+        } else if (EPI == EPI_DFT) {
+          // columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins
+          constexpr int HB = BN / 2;
+#pragma unroll 1
+          for (int c0 = 0; c0 < HB; c0 += 16) {
+            uint32_t re[16], im[16];
+            tmem_ld16(t_acc + c0, re);
+            tmem_ld16(t_acc + HB + c0, im);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const MelTap tp = s_taps[nt * HB + c0 + j];
+              const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+              const float pw = (a * a + b * b) * s2;
+              while (cur < tp.first) {               // warp-uniform: taps and cur do not depend on the row
+                if (valid) P.melpow[g * P.n_mels + cur] = acc0;
+                acc0 = acc1;
+                acc1 = 0.f;
+                ++cur;
+              }
+              acc0 = fmaf(tp.w0, pw, acc0);
+              acc1 = fmaf(tp.w1, pw, acc1);
+            }
+          }
+          if (nt == P.num_n_tiles - 1) {
+            while (cur < P.n_mels) {
+              if (valid) P.melpow[g * P.n_mels + cur] = acc0;
+              acc0 = acc1;
+              acc1 = 0.f;
+              ++cur;
+            }
+          }
+        } else {
+          // EPI_CONV: row = pixel (h_local * tw + w_local) of a th x tw output tile, tw in {8, 16}:
+          // the 2x2 pooling partners are lane ^ 1 (w) and lane ^ tw (h) of the same warp.
+          const int per_img = P.tiles_w * P.tiles_h;
+          const int img = mt / per_img;
+          const int r = mt - img * per_img;
+          const int h = (r / P.tiles_w) * P.th + row / P.tw;
+          const int w = (r % P.tiles_w) * P.tw + row % P.tw;
+          const bool inb = (h < P.H) && (w < P.W);
+          const int OH = P.H / P.pool, OW = P.W / P.pool;
+          const bool writer = inb && (P.pool == 1 || (((h | w) & 1) == 0));
+          const size_t opix = (static_cast<size_t>(img) * OH + h / P.pool) * OW + w / P.pool;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + c0, v);
+            tmem_ld_wait();
+            const int n0 = nt * BN + c0;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = __uint_as_float(v[j]);
+              if (n0 + j < P.Cout) t += P.bias[n0 + j];
+              if (P.relu) t = fmaxf(t, 0.f);
+              if (P.pool == 2) {
+                t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
+                t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, P.tw));
+              }
+              o[j] = t;
+            }
+            if (writer && n0 < P.Cout) {
+              __align__(16) __nv_bfloat16 hi[16];
+              __align__(16) __nv_bfloat16 lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                hi[j] = __float2bfloat16_rn(o[j]);
+                lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
+              }
+              __nv_bfloat16* dh = P.out_hi + opix * P.Cout + n0;
+              __nv_bfloat16* dl = P.out_lo + opix * P.Cout + n0;
+              if (n0 + 16 <= P.Cout) {
+                reinterpret_cast<uint4*>(dh)[0] = reinterpret_cast<const uint4*>(hi)[0];
+                reinterpret_cast<uint4*>(dh)[1] = reinterpret_cast<const uint4*>(hi)[1];
+                reinterpret_cast<uint4*>(dl)[0] = reinterpret_cast<const uint4*>(lo)[0];
+                reinterpret_cast<uint4*>(dl)[1] = reinterpret_cast<const uint4*>(lo)[1];
+              } else {
+                for (int j = 0; j < 16 && n0 + j < P.Cout; ++j) { dh[j] = hi[j]; dl[j] = lo[j]; }
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+#endif
+}
+
+template <int BN, int SWZ, int EPI>
+int launch_gemm3(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                 const CUtensorMap& tmB_lo, const Gemm3Params& P, int sm_count, cudaStream_t st) {
+  using Cfg = Gemm3Cfg<BN, SWZ>;
+  static bool configured = false;
+  auto kfn = gemm3_kernel<BN, SWZ, EPI>;
+  if (!configured) {
+    AVLD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int grid = P.num_m_tiles < sm_count ? P.num_m_tiles : sm_count;
+  if (grid < 1) return AVLD_OK;
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, P);
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+
+#endif  // AVLD_GEMM3_IMPL
+
+}  // namespace avld

@@ -1,0 +1,240 @@
+// rms.cu -- R1/R2: bit-exact batched rms_normalize (00_normalize_dataset_rms.py:29-38) and the
+// operand preparation for the STFT GEMM (reflect padding of librosa.stft's center=True, per-chunk
+// power-of-two scaling, fp16-hi / bf16-lo split), fused in one kernel: one CTA per chunk.
+//
+// Bit-exactness: np.mean(y**2) on contiguous float32 walks numpy's pairwise-summation tree
+// (8 interleaved accumulators per <=128-element leaf, halves rounded down to a multiple of 8).
+// The host builds that tree once per chunk length (ctx.cu::pairwise_plan); the kernel evaluates the
+// leaves with the same accumulator order and combines them level by level, every operation an
+// explicitly rounded __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn (no FMA contraction), following
+// numpy-2 float32 scalar semantics for `rms + eps` and `target / (...)`.
+//
+// Memory: phase 1 streams the chunk once (4*L bytes), phase 2 re-reads it (L2-resident: 148 CTAs x
+// 576 KB < 126 MB L2) and writes either y (4*L bytes) or the 16-bit operand pair (4*(L+n_fft) bytes).
+#include "common.cuh"
+
+namespace avld {
+
+struct PrepParams {
+  const float* x;
+  float* y;               // nullable
+  __half* a_hi;           // nullable (operand mode)
+  __nv_bfloat16* a_lo;
+  float* inv2;
+  uint8_t* ok;            // nullable
+  float* rms;             // nullable
+  const int32_t* leaf_off;
+  const int32_t* leaf_len;
+  const PairNode* nodes;
+  const int32_t* level_start;
+  int n_leaves, n_nodes, n_levels;
+  int L, n_fft, hop, R;
+  float target_rms, rms_min, eps;
+  int normalize, quantize;
+};
+
+__device__ __forceinline__ float finish_sample(float v, float scale, int scaled, int quantize) {
+  if (scaled) {
+    v = __fmul_rn(v, scale);
+    v = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);   // np.clip keeps NaN
+  }
+  if (quantize) v = __fmul_rn(rintf(__fmul_rn(v, 32767.0f)), 1.0f / 32768.0f);  // sf.write PCM_16 + read back
+  return v;
+}
+
+__global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
+  extern __shared__ float s_val[];            // [n_leaves + n_nodes]
+  __shared__ float s_red[16];
+  __shared__ float s_scale, s_pow2;
+  __shared__ int s_scaled;
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* __restrict__ xc = P.x + static_cast<size_t>(c) * P.L;
+
+  // ---------------------------------------------------------------- phase 1: leaves
+  float mx = 0.f;
+  const int j = tid & 7;
+  const unsigned gmask = 0xFFu << (8 * ((tid & 31) >> 3));
+  for (int leaf = tid >> 3; leaf < P.n_leaves; leaf += blockDim.x >> 3) {
+    const int off = P.leaf_off[leaf], len = P.leaf_len[leaf];
+    float r;
+    if (len < 8) {
+      r = 0.f;
+      if (j == 0) {
+        for (int i = 0; i < len; ++i) {
+          const float v = xc[off + i];
+          mx = fmaxf(mx, fabsf(v));
+          r = __fadd_rn(r, __fmul_rn(v, v));
+        }
+      }
+    } else {
+      const int n8 = len & ~7;
+      float v = xc[off + j];
+      mx = fmaxf(mx, fabsf(v));
+      r = __fmul_rn(v, v);
+#pragma unroll 4
+      for (int i = 8; i < n8; i += 8) {
+        v = xc[off + i + j];
+        mx = fmaxf(mx, fabsf(v));
+        r = __fadd_rn(r, __fmul_rn(v, v));
+      }
+      // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
+      r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1, 8));
+      r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2, 8));
+      r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4, 8));
+      if (j == 0) {
+        for (int i = n8; i < len; ++i) {
+          v = xc[off + i];
+          mx = fmaxf(mx, fabsf(v));
+          r = __fadd_rn(r, __fmul_rn(v, v));
+        }
+      }
+    }
+    if (j == 0) s_val[leaf] = r;
+  }
+  // block max of |x| (only used to pick the power-of-two operand scale; any upper bound is valid)
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- tree combine, level by level
+  for (int lv = 0; lv < P.n_levels; ++lv) {
+    const int b = P.level_start[lv], e = P.level_start[lv + 1];
+    for (int i = b + tid; i < e; i += blockDim.x) {
+      const PairNode nd = P.nodes[i];
+      s_val[P.n_leaves + i] = __fadd_rn(s_val[nd.a], s_val[nd.b]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    float m = s_red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+    const float root = s_val[P.n_leaves + P.n_nodes - 1];   // last node = root (a single leaf when n_nodes == 0)
+    const float mean = __fdiv_rn(root, static_cast<float>(P.L));
+    const float rms = __fsqrt_rn(mean);
+    int scaled = 0;
+    float scale = 1.0f;
+    if (P.normalize && !(rms < P.rms_min)) {           // silence gate: `if rms < rms_min: return y, False`
+      scaled = 1;
+      scale = __fdiv_rn(P.target_rms, __fadd_rn(rms, P.eps));
+    }
+    float bound = scaled ? fminf(__fmul_rn(m, scale), 1.0f) : m;
+    int s = 0;
+    if (bound > 0.f && bound < 3.0e38f) {
+      s = 14 - ilogbf(bound);
+      s = s > 60 ? 60 : (s < -60 ? -60 : s);
+    }
+    s_scale = scale;
+    s_scaled = scaled;
+    s_pow2 = ldexpf(1.0f, s);
+    if (P.inv2) P.inv2[c] = ldexpf(1.0f, -2 * s);
+    if (P.ok) P.ok[c] = P.normalize ? static_cast<uint8_t>(scaled) : static_cast<uint8_t>(1);
+    if (P.rms) P.rms[c] = rms;
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const int scaled = s_scaled;
+
+  // ---------------------------------------------------------------- phase 2a: y (float32)
+  if (P.y != nullptr) {
+    float* __restrict__ yc = P.y + static_cast<size_t>(c) * P.L;
+    if ((P.L & 3) == 0) {
+      const float4* x4 = reinterpret_cast<const float4*>(xc);
+      float4* y4 = reinterpret_cast<float4*>(yc);
+      for (int i = tid; i < (P.L >> 2); i += blockDim.x) {
+        float4 v = x4[i];
+        v.x = finish_sample(v.x, scale, scaled, P.quantize);
+        v.y = finish_sample(v.y, scale, scaled, P.quantize);
+        v.z = finish_sample(v.z, scale, scaled, P.quantize);
+        v.w = finish_sample(v.w, scale, scaled, P.quantize);
+        y4[i] = v;
+      }
+    } else {
+      for (int i = tid; i < P.L; i += blockDim.x) yc[i] = finish_sample(xc[i], scale, scaled, P.quantize);
+    }
+  }
+
+  // ---------------------------------------------------------------- phase 2b: GEMM operand rows
+  if (P.a_hi != nullptr) {
+    const float pow2 = s_pow2;
+    const int half = P.n_fft / 2;
+    const int total = P.R * P.hop;                       // multiple of 64
+    __half* __restrict__ ah = P.a_hi + static_cast<size_t>(c) * total;
+    __nv_bfloat16* __restrict__ al = P.a_lo + static_cast<size_t>(c) * total;
+    for (int v8 = tid; v8 < (total >> 3); v8 += blockDim.x) {
+      const int p0 = v8 << 3;
+      __align__(16) __half hi[8];
+      __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int p = p0 + q;
+        int src = p - half;                              // np.pad(y, n_fft//2, mode="reflect")
+        if (src < 0) src = -src;
+        if (src >= P.L) src = 2 * (P.L - 1) - src;
+        float v = 0.f;
+        if (p < P.L + P.n_fft) v = finish_sample(xc[src], scale, scaled, P.quantize) * pow2;
+        const __half h = __float2half_rn(v);
+        hi[q] = h;
+        lo[q] = __float2bfloat16_rn(v - __half2float(h));
+      }
+      *reinterpret_cast<uint4*>(ah + p0) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(al + p0) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
+
+int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
+                int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st) {
+  if (n <= 0) return AVLD_OK;
+  PrepParams P{};
+  P.x = x;
+  P.y = y_out;
+  P.a_hi = write_operand ? c->d_Ahi : nullptr;
+  P.a_lo = write_operand ? c->d_Alo : nullptr;
+  P.inv2 = write_operand ? c->d_inv2 : nullptr;
+  P.ok = ok;
+  P.rms = rms;
+  P.leaf_off = c->d_leaf_off;
+  P.leaf_len = c->d_leaf_len;
+  P.nodes = c->d_nodes;
+  P.level_start = c->d_level_start;
+  P.n_leaves = c->n_leaves;
+  P.n_nodes = c->n_nodes;
+  P.n_levels = c->n_levels;
+  P.L = c->L;
+  P.n_fft = c->p.n_fft;
+  P.hop = c->p.hop;
+  P.R = c->R;
+  P.target_rms = target_rms;
+  P.rms_min = rms_min;
+  P.eps = eps;
+  P.normalize = normalize ? 1 : 0;
+  P.quantize = quantize ? 1 : 0;
+  const size_t smem = static_cast<size_t>(c->n_leaves + c->n_nodes + 1) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    AVLD_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
+    configured = true;
+  }
+  prep_kernel<<<n, 512, smem, st>>>(P);
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+
+}  // namespace avld
+
+using namespace avld;
+
+extern "C" int avld_rms_normalize(avld_ctx* c, const float* x, float* y, uint8_t* ok, float* rms, int64_t n,
+                                  float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream) {
+  AVLD_CHECK(c && x && y, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t step = 1 << 20;   // grid size limit is far above this; chunk the launch only for int safety
+  for (int64_t i = 0; i < n; i += step) {
+    const int m = static_cast<int>(n - i < step ? n - i : step);
+    AVLD_TRY(launch_prep(c, x + i * c->L, y + i * c->L, false, true, ok ? ok + i : nullptr, rms ? rms + i : nullptr, m,
+                         target_rms, rms_min, eps, quantize_pcm16, st));
+  }
+  return AVLD_OK;
+}

@@ -1,0 +1,169 @@
+/* avld.h -- C ABI of the B200-native encode+detect hot path ("amphibian VAE latent detector").
+ *
+ * The reference (vpobleteacustica/amphibian-vae-latent-detector) is pure Python and has no FFI;
+ * its de-facto interface for this path is a set of Python functions.  Each
+ * entry point below names the reference function(s) it replaces (paths relative to
+ * latent_space_exploration/ in the reference).  A Python maintainer binds these with ctypes --
+ * see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every function returns AVLD_OK (0) or a negative error code; nothing throws across the ABI;
+ *     avld_last_error() returns a thread-local message for the last failure.
+ *   - pointers documented "dev" are caller-owned CUDA device memory, valid on ctx's device, never
+ *     freed or retained past the call (exception: none -- encoder weights are copied at load).
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous unless
+ *     the function is documented as synchronous.
+ *   - one ctx per (device, host thread); a ctx is not safe for concurrent calls.
+ *   - per-chunk failures never fail the call: they are reported in `ok`/`pred`, mirroring the
+ *     reference's count-and-continue loops (08_fit_radial_detector.py:489-506,
+ *     10_benchmark_folder_detection.py:397-418).
+ *   - there is no CPU fallback: without a CUDA device avld_ctx_create fails with AVLD_ERR_CUDA.
+ */
+#ifndef AVLD_H
+#define AVLD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVLD_ABI_VERSION 1
+
+enum {
+  AVLD_OK = 0,
+  AVLD_ERR_INVALID = -1,      /* bad argument                                                     */
+  AVLD_ERR_CUDA = -2,         /* CUDA runtime/driver error (message has the CUDA error string)     */
+  AVLD_ERR_UNSUPPORTED = -3,  /* valid request the kernels do not implement (e.g. hop % 64 != 0)   */
+  AVLD_ERR_STATE = -4,        /* call order (e.g. forward before encoder_load)                     */
+  AVLD_ERR_NOMEM = -5
+};
+
+typedef struct avld_ctx avld_ctx;
+
+/* Feature parameters = the CLI defaults shared by 07/08/09/10 (07_encode_wav_to_latent.py:424-432,
+ * 08_fit_radial_detector.py:348-354) plus librosa.power_to_db's amin/top_db
+ * (map_detector_core.py:229). chunk_len = int(sr * duration) (map_detector_core.py:213). */
+typedef struct avld_params {
+  int32_t sr;             /* 48000 */
+  int32_t chunk_len;      /* samples per chunk, e.g. 144000 (3 s) or 240000 (5 s) */
+  int32_t n_fft;          /* 2048 */
+  int32_t hop;            /* 384 */
+  int32_t n_mels;         /* 64 */
+  float fmin;             /* 150 */
+  float fmax;             /* 15000 */
+  int32_t target_frames;  /* 192 */
+  float amin;             /* 1e-10 */
+  float top_db;           /* 80 */
+  int32_t max_batch;      /* chunks per internal pass; device scratch is sized from this */
+} avld_params;
+
+/* One encoder layer, BatchNorm already folded (host pointers; copied during avld_encoder_load).
+ * kind 0 = Conv2d(+ReLU)(+MaxPool2d(2)) on NHWC activations, weight [c_out][k][k][c_in];
+ * kind 1 = Linear(+ReLU), weight [c_out][c_in] with c_in in NHWC-flatten order. */
+typedef struct avld_layer {
+  int32_t kind;
+  int32_t c_in, c_out;
+  int32_t ksize, stride, pad;
+  int32_t relu, pool;
+  int32_t in_h, in_w;
+  const float* weight;
+  const float* bias;
+} avld_layer;
+
+/* A requested order statistic: the `rank`-th smallest (0-based) of radii[:, species] over the rows
+ * whose label == species (side 0, "in class") or label != species and label >= 0 (side 1). */
+typedef struct avld_rank_query {
+  int32_t species;
+  int32_t side;
+  int64_t rank;
+} avld_rank_query;
+
+int avld_abi_version(void);
+const char* avld_last_error(void);
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int avld_ctx_create(int device, const avld_params* params, avld_ctx** out);
+void avld_ctx_destroy(avld_ctx* ctx);
+/* derived sizes: frames per chunk F = 1 + chunk_len / hop, latent dim D (0 before encoder_load) */
+int avld_ctx_info(const avld_ctx* ctx, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count);
+
+/* ---- R1/R2: rms_normalize (00_normalize_dataset_rms.py:29-38), batched -------------------------
+ * x, y: dev float32 [n, chunk_len]; ok: dev uint8 [n] (1 = scaled, 0 = silence gate: copied
+ * unchanged); rms: dev float32 [n] or NULL.  Bit-exact with numpy-2 float32 semantics (pairwise
+ * sum tree, non-fused ops).  quantize_pcm16 != 0 additionally applies the sf.write -> librosa.load
+ * PCM_16 round trip of process_folder (00:55-57): y = rint(y * 32767) / 32768. */
+int avld_rms_normalize(avld_ctx* ctx, const float* x, float* y, uint8_t* ok, float* rms, int64_t n,
+                       float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream);
+
+/* ---- M2-M5 + E0: wav_to_mel after the load (map_detector_core.py:219-237) and the transpose of
+ * map_detector_core.py:267-268.  y: dev float32 [n, chunk_len] -> feat: dev float32
+ * [n, target_frames, n_mels] (the encoder's [B,1,T,M] input). */
+int avld_logmel(avld_ctx* ctx, const float* y, float* feat, int64_t n, void* stream);
+
+/* fused R1(+R2) + features: x -> feat; ok/rms as in avld_rms_normalize (either may be NULL). */
+int avld_normalize_logmel(avld_ctx* ctx, const float* x, float* feat, uint8_t* ok, float* rms,
+                          int64_t n, float target_rms, float rms_min, float eps, int quantize_pcm16,
+                          void* stream);
+
+/* ---- L1/E1/E2: encoder (map_detector_core.py:150-179, :270-300) --------------------------------
+ * encoder_load is synchronous (copies and pre-splits the weights, builds TMA descriptors). */
+int avld_encoder_load(avld_ctx* ctx, const avld_layer* layers, int32_t n_layers);
+/* feat: dev float32 [n, target_frames, n_mels] -> mu: dev float32 [n, D] (the latent mean). */
+int avld_encoder_forward(avld_ctx* ctx, const float* feat, float* mu, int64_t n, void* stream);
+
+/* whole encode half in one call: x dev [n, chunk_len] -> mu dev [n, D]
+ * (= rms_normalize + sf.write/load + encode_wav_to_latent, map_detector_core.py:240-300). */
+int avld_encode(avld_ctx* ctx, const float* x, float* mu, uint8_t* ok, int64_t n, float target_rms,
+                float rms_min, float eps, int quantize_pcm16, void* stream);
+
+/* ---- F1-F3: radial fit pieces (08_fit_radial_detector.py:105-106, :310-333, :530-558) ----------
+ * per-species latent sums for the centroid (np.mean(Z_in, axis=0), 08:316): ACCUMULATES into
+ * sum (dev float64 [K, D]) and cnt (dev int64 [K]); rows with label < 0 or >= K are skipped. */
+int avld_centroid_accumulate(avld_ctx* ctx, const float* Z, const int32_t* label, double* sum,
+                             int64_t* cnt, int64_t n, int32_t K, int32_t D, void* stream);
+/* radii[i, k] = || Z[i] - centroid[k] ||_2 (08:105-106, :318, :325; 09:354-355). */
+int avld_radii(avld_ctx* ctx, const float* Z, const float* centroid, float* radii, int64_t n,
+               int32_t K, int32_t D, void* stream);
+/* exact order statistics of radii columns (np.quantile's partition step, 08:109-112); the caller
+ * interpolates.  radii dev [n, K], label dev [n], queries HOST [n_q], out HOST float32 [n_q].
+ * Synchronous on `stream`. */
+int avld_order_stats(avld_ctx* ctx, const float* radii, const int32_t* label, int64_t n, int32_t K,
+                     const avld_rank_query* queries, int32_t n_q, float* out, void* stream);
+
+/* ---- D2: decision (09_evaluate_wav_detection.py:416-436; 10_benchmark_folder_detection.py:175-199)
+ * accept k iff (double)radii[i,k] <= thr[k]; pred[i] = accepted k with the smallest
+ * priority_rank[k] or -1 (NO_DETECT); best_d[i] = min_k radii[i,k].  thr dev float64 [K] (NaN =
+ * species without threshold: skipped), priority_rank dev int32 [K]. */
+int avld_decide(avld_ctx* ctx, const float* radii, const double* thr, const int32_t* priority_rank,
+                int32_t* pred, float* best_d, int64_t n, int32_t K, void* stream);
+
+/* ---- end to end with HOST buffers (the call the drop-in Python layer makes per batch) -----------
+ * x_host float32 [n, chunk_len] (pinned or pageable) -> pred_host int32 [n], best_host float32 [n],
+ * mu_host float32 [n, D] (nullable), ok_host uint8 [n] (nullable).  centroid/thr/priority_rank are
+ * HOST arrays ([K, D] float32, [K] float64, [K] int32).  Copies are double-buffered against compute.
+ * Synchronous. */
+int avld_encode_detect_host(avld_ctx* ctx, const float* x_host, int64_t n, int quantize_pcm16,
+                            const float* centroid, const double* thr, const int32_t* priority_rank,
+                            int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
+                            uint8_t* ok_host);
+
+/* ---- host-side helpers (no device work; used by tests and by the Python layer) -----------------*/
+/* numpy's float32 pairwise-summation plan for a length-n reduction: writes up to cap leaves
+ * (offset, length) in in-order traversal; returns the number of leaves (or a negative error). */
+int64_t avld_pairwise_plan(int64_t n, int64_t* leaf_offset, int64_t* leaf_len, int64_t cap);
+/* slaney mel filterbank taps: for FFT bin b, weight[0] feeds filter first[b], weight[1] feeds
+ * first[b] + 1 (first[b] = -1 when the bin feeds nothing).  Arrays of n_fft/2 + 1 entries. */
+int avld_mel_taps(const avld_params* params, int32_t* first, float* w0, float* w1);
+
+/* ---- test / bring-up entry (exercises the tcgen05 split-precision GEMM core on plain matrices) --
+ * C[M,N] = A[M,K] * B[N,K]^T, all dev float32 row-major, K % 64 == 0, N % 16 == 0, N <= 256*tiles.
+ * mode 0: fp16 hi + bf16 lo operands; mode 1: bf16 hi + bf16 lo. Synchronous. */
+int avld_dbg_gemm(avld_ctx* ctx, const float* A, const float* B, float* C, int64_t M, int32_t N,
+                  int32_t K, int32_t mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVLD_H */
