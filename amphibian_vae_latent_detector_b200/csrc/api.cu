@@ -100,8 +100,8 @@ extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float*
   do {
     CUtensorMapDataType hi_t = mode == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (mode == 0) {
-      if ((rc = launch_split_f16(A, static_cast<__half*>(a_hi), static_cast<__nv_bfloat16*>(a_lo), na, st))) break;
-      if ((rc = launch_split_f16(B, static_cast<__half*>(b_hi), static_cast<__nv_bfloat16*>(b_lo), nb, st))) break;
+      if ((rc = launch_split_f16(A, static_cast<__half*>(a_hi), static_cast<__half*>(a_lo), na, st))) break;
+      if ((rc = launch_split_f16(B, static_cast<__half*>(b_hi), static_cast<__half*>(b_lo), nb, st))) break;
     } else {
       if ((rc = launch_split_bf16(A, static_cast<__nv_bfloat16*>(a_hi), static_cast<__nv_bfloat16*>(a_lo), na, st))) break;
       if ((rc = launch_split_bf16(B, static_cast<__nv_bfloat16*>(b_hi), static_cast<__nv_bfloat16*>(b_lo), nb, st))) break;
@@ -109,22 +109,21 @@ extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float*
     const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if ((rc = encode_tmap_2d(&ta_hi, a_hi, hi_t, K, M, static_cast<uint64_t>(K) * 2, 64, 128, 128))) break;
-    if ((rc = encode_tmap_2d(&ta_lo, a_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, M, static_cast<uint64_t>(K) * 2, 64, 128, 128))) break;
+    if ((rc = encode_tmap_2d(&ta_lo, a_lo, hi_t, K, M, static_cast<uint64_t>(K) * 2, 64, 128, 128))) break;
     if ((rc = encode_tmap_2d(&tb_hi, b_hi, hi_t, K, N, static_cast<uint64_t>(K) * 2, 64, bn, 128))) break;
-    if ((rc = encode_tmap_2d(&tb_lo, b_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, K, N, static_cast<uint64_t>(K) * 2, 64, bn, 128))) break;
+    if ((rc = encode_tmap_2d(&tb_lo, b_lo, hi_t, K, N, static_cast<uint64_t>(K) * 2, 64, bn, 128))) break;
     Gemm3Params P{};
     P.num_m_tiles = static_cast<int>((M + 127) / 128);
     P.num_n_tiles = (N + bn - 1) / bn;
     P.num_k_blocks = K / 64;
     const int hb = mode == 0 ? 0 : 1;
-    P.idesc_hh = avld_make_idesc(hb, hb, 128, bn);
-    P.idesc_lh = avld_make_idesc(1, hb, 128, bn);
-    P.idesc_hl = avld_make_idesc(hb, 1, 128, bn);
+    P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(hb, hb, 128, bn);
     P.a_mode = 0;
     P.M_total = M;
     P.N_total = N;
     P.out_f32 = C;
     P.ldc = N;
+    LaunchScope ls(c, ST_DENSE_GEMM, st);
     rc = run_gemm3(bn, 128, EPI_PLAIN, ta_hi, ta_lo, tb_hi, tb_lo, P, c->sm_count, st);
     if (rc) break;
     cudaError_t e = cudaStreamSynchronize(st);

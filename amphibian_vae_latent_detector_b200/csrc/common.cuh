@@ -15,6 +15,12 @@ namespace avld {
 
 void set_error(const char* fmt, ...);
 
+// kernel families, for the launch counter and the optional per-stage CUDA-event timing
+enum Stage {
+  ST_PREP = 0, ST_STFT_MEL, ST_LOGMEL_POST, ST_CONV_DIRECT, ST_CONV_GEMM, ST_DENSE_GEMM, ST_RADII, ST_DECIDE,
+  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_COUNT
+};
+
 #define AVLD_CUDA(expr)                                                                       \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -85,14 +91,15 @@ struct avld_ctx {
   int32_t* d_level_start = nullptr;  // [n_levels + 1]
 
   avld::MelTap* d_taps = nullptr;  // [nbins_pad]
-  __half* d_Bhi = nullptr;         // DFT matrix [ncols][n_fft], hi part (fp16)
-  __nv_bfloat16* d_Blo = nullptr;  //                           lo part (bf16)
+  __half* d_Bhi = nullptr;         // windowed DFT matrix * 2^dft_scale_log2, [ncols][n_fft], fp16 hi part
+  __half* d_Blo = nullptr;         //                                                        fp16 lo part
+  int dft_scale_log2 = 10;
   CUtensorMap tm_B_hi, tm_B_lo;
 
   // per-pass scratch (max_batch chunks)
   int max_batch = 0;
   __half* d_Ahi = nullptr;         // padded, pow2-scaled audio rows [max_batch * R + 128][hop]
-  __nv_bfloat16* d_Alo = nullptr;
+  __half* d_Alo = nullptr;
   CUtensorMap tm_A_hi, tm_A_lo;
   float* d_inv2 = nullptr;         // [max_batch] 2^(-2 s_c)
   float* d_melpow = nullptr;       // [max_batch * R][n_mels]
@@ -123,6 +130,13 @@ struct avld_ctx {
   // order-statistics scratch
   unsigned int* d_hist = nullptr;
   size_t hist_bytes = 0;
+
+  // launch accounting (always on) and per-stage event timing (avld_profile_enable)
+  uint64_t launches[avld::ST_COUNT] = {};
+  bool profiling = false;
+  struct TimedLaunch { int stage; cudaEvent_t start, stop; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace avld {
@@ -139,6 +153,16 @@ int64_t pairwise_plan(int64_t n, std::vector<int64_t>& off, std::vector<int64_t>
 int mel_taps_host(const avld_params& p, std::vector<int32_t>& first, std::vector<float>& w0, std::vector<float>& w1,
                   int* bin_lo, int* bin_hi);
 
+// RAII bracket around one kernel launch: counts it and, when profiling, records CUDA events on the
+// launching stream (so the measured duration is that kernel's, inside the real step).
+struct LaunchScope {
+  avld_ctx* c;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  LaunchScope(avld_ctx* ctx, int stage, cudaStream_t stream);
+  ~LaunchScope();
+};
+
 // stage launchers (each in its own translation unit)
 int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
@@ -146,6 +170,6 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
-int launch_split_f16(const float* src, __half* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
+int launch_split_f16(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t st);
 
 }  // namespace avld

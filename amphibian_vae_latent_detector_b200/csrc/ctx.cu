@@ -19,6 +19,33 @@ void set_error(const char* fmt, ...) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// launch accounting / per-stage timing
+// ------------------------------------------------------------------------------------------------
+static cudaEvent_t take_event(avld_ctx* c) {
+  if (!c->event_pool.empty()) {
+    cudaEvent_t e = c->event_pool.back();
+    c->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchScope::LaunchScope(avld_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), st(stream) {
+  c->launches[stage] += 1;
+  if (c->profiling) {
+    cudaEvent_t a = take_event(c);
+    stop = take_event(c);
+    cudaEventRecord(a, st);
+    c->timed.push_back({stage, a, stop});
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (stop) cudaEventRecord(stop, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA descriptors
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -318,7 +345,8 @@ static int build_ctx(avld_ctx* c) {
       stab[k] = std::sin(2.0 * M_PI * k / nf);
     }
     std::vector<__half> hi(static_cast<size_t>(c->ncols) * nf);
-    std::vector<__nv_bfloat16> lo(hi.size());
+    std::vector<__half> lo(hi.size());
+    const double bscale = std::ldexp(1.0, c->dft_scale_log2);   // keeps the lo parts out of the fp16 subnormals
     for (int col = 0; col < c->ncols; ++col) {
       const int tile = col / 256, part = (col % 256) / 128, j = col % 128;
       const int bin = bin_lo + tile * 128 + j;
@@ -326,12 +354,12 @@ static int build_ctx(avld_ctx* c) {
         double v = 0.0;
         if (bin <= nf / 2) {
           const int ph = static_cast<int>((static_cast<long long>(k) * bin) % nf);
-          v = win[k] * (part == 0 ? ct[ph] : -stab[ph]);
+          v = bscale * win[k] * (part == 0 ? ct[ph] : -stab[ph]);
         }
         const float vf = static_cast<float>(v);
         const __half h = __float2half_rn(vf);
         hi[static_cast<size_t>(col) * nf + k] = h;
-        lo[static_cast<size_t>(col) * nf + k] = __float2bfloat16_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+        lo[static_cast<size_t>(col) * nf + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
       }
     }
     AVLD_TRY(dev_alloc(&c->d_Bhi, hi.size()));
@@ -339,7 +367,7 @@ static int build_ctx(avld_ctx* c) {
     AVLD_CUDA(cudaMemcpy(c->d_Bhi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     AVLD_CUDA(cudaMemcpy(c->d_Blo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
     AVLD_TRY(encode_tmap_2d(&c->tm_B_hi, c->d_Bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B_lo, c->d_Blo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B_lo, c->d_Blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
   }
 
   // ---- per-pass scratch
@@ -349,7 +377,7 @@ static int build_ctx(avld_ctx* c) {
   AVLD_CUDA(cudaMemset(c->d_Ahi, 0, rows * p.hop * 2));
   AVLD_CUDA(cudaMemset(c->d_Alo, 0, rows * p.hop * 2));
   AVLD_TRY(encode_tmap_2d(&c->tm_A_hi, c->d_Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
-  AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+  AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->max_batch) * c->R * c->M));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
@@ -416,7 +444,49 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
     if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
   }
+  for (auto& t : c->timed) {
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   delete c;
+}
+
+extern "C" int avld_profile_enable(avld_ctx* c, int on) {
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  c->profiling = on != 0;
+  return AVLD_OK;
+}
+
+extern "C" int avld_profile_collect(avld_ctx* c, double* ms, int64_t* timed_launches, uint64_t* launches, int reset) {
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_CUDA(cudaSetDevice(c->device));
+  for (int i = 0; i < ST_COUNT; ++i) {
+    if (ms) ms[i] = 0.0;
+    if (timed_launches) timed_launches[i] = 0;
+    if (launches) launches[i] = c->launches[i];
+  }
+  for (auto& t : c->timed) {
+    AVLD_CUDA(cudaEventSynchronize(t.stop));
+    float e = 0.f;
+    AVLD_CUDA(cudaEventElapsedTime(&e, t.start, t.stop));
+    if (ms) ms[t.stage] += e;
+    if (timed_launches) timed_launches[t.stage] += 1;
+    c->event_pool.push_back(t.start);
+    c->event_pool.push_back(t.stop);
+  }
+  c->timed.clear();
+  if (reset)
+    for (int i = 0; i < ST_COUNT; ++i) c->launches[i] = 0;
+  return AVLD_OK;
+}
+
+extern "C" int avld_stage_count(void) { return ST_COUNT; }
+extern "C" const char* avld_stage_name(int stage) {
+  static const char* names[ST_COUNT] = {"prep_kernel", "gemm3_kernel<DFT>", "logmel_post_kernel", "conv_direct_kernel",
+                                        "gemm3_kernel<CONV>", "gemm3_kernel<PLAIN>", "radii_kernel", "decide_kernel",
+                                        "centroid_kernel", "select_hist_kernel", "split_kernel"};
+  return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 
 extern "C" int avld_ctx_info(const avld_ctx* c, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count) {

@@ -25,13 +25,13 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* 
     lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
-__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+__global__ void split_f16_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
                                  size_t n) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float v = src[i];
     const __half h = __float2half_rn(v);
     hi[i] = h;
-    lo[i] = __float2bfloat16_rn(v - __half2float(h));
+    lo[i] = __float2half_rn(v - __half2float(h));
   }
 }
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
@@ -41,7 +41,7 @@ int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, si
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
-int launch_split_f16(const float* src, __half* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st) {
+int launch_split_f16(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t st) {
   if (n == 0) return AVLD_OK;
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 8));
   split_f16_kernel<<<grid, 256, 0, st>>>(src, hi, lo, n);
@@ -147,7 +147,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       const size_t smem = (static_cast<size_t>(in_rows) * in_cols * P.Cin + static_cast<size_t>(P.Cout) * P.k * P.k * P.Cin + P.Cout) * sizeof(float);
       AVLD_CHECK(smem <= 48 * 1024, AVLD_ERR_UNSUPPORTED, "first-layer direct convolution tile does not fit shared memory");
       dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
-      conv_direct_kernel<<<grid, 256, smem, st>>>(P);
+      { LaunchScope ls(c, ST_CONV_DIRECT, st); conv_direct_kernel<<<grid, 256, smem, st>>>(P); }
       AVLD_CUDA(cudaGetLastError());
     } else if (L.kind == 0) {
       Gemm3Params P{};
@@ -166,6 +166,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       P.out_hi = out_hi;
       P.out_lo = out_lo;
       P.H = H; P.W = W; P.Cout = L.c_out; P.pool = L.pool;
+      LaunchScope ls(c, ST_CONV_GEMM, st);
       AVLD_TRY(run_gemm3(L.bn, L.swz, EPI_CONV, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
     } else {
       Gemm3Params P{};
@@ -185,6 +186,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
         P.out_hi = out_hi;
         P.out_lo = out_lo;
       }
+      LaunchScope ls(c, ST_DENSE_GEMM, st);
       AVLD_TRY(run_gemm3(L.bn, 128, EPI_PLAIN, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
     }
   }

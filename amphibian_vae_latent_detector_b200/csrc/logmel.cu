@@ -18,9 +18,8 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
   P.num_m_tiles = static_cast<int>((rows + 127) / 128);
   P.num_n_tiles = c->n_tiles_n;
   P.num_k_blocks = c->kblocks;
-  P.idesc_hh = avld_make_idesc(0, 0, 128, 256);   // fp16 x fp16
-  P.idesc_lh = avld_make_idesc(1, 0, 128, 256);   // bf16 (A lo) x fp16
-  P.idesc_hl = avld_make_idesc(0, 1, 128, 256);   // fp16 x bf16 (B lo)
+  // all four operands fp16 (kind::f16 rejects mixed fp16 / bf16 operands: "illegal instruction" on sm_100a)
+  P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(0, 0, 128, 256);
   P.a_mode = 1;
   P.hpb = c->hpb;
   P.M_total = rows;
@@ -32,6 +31,7 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
   P.F = c->F;
   P.n_mels = c->M;
   P.nbins_pad = c->nbins_pad;
+  LaunchScope ls(c, ST_STFT_MEL, st);
   return run_gemm3(256, 128, EPI_DFT, c->tm_A_hi, c->tm_A_lo, c->tm_B_hi, c->tm_B_lo, P, c->sm_count, st);
 }
 
@@ -128,7 +128,7 @@ int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st) {
     AVLD_CUDA(cudaFuncSetAttribute(logmel_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  logmel_post_kernel<<<n, 512, smem, st>>>(P);
+  { LaunchScope ls(c, ST_LOGMEL_POST, st); logmel_post_kernel<<<n, 512, smem, st>>>(P); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }

@@ -162,7 +162,7 @@ extern "C" int avld_centroid_accumulate(avld_ctx* c, const float* Z, const int32
   }
   const long long rows_per_block = std::max<long long>(64, (n + c->sm_count * 4 - 1) / (c->sm_count * 4));
   const int grid = static_cast<int>((n + rows_per_block - 1) / rows_per_block);
-  centroid_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, label, sum, reinterpret_cast<long long*>(cnt), n, K, D, rows_per_block);
+  { LaunchScope ls(c, ST_CENTROID, static_cast<cudaStream_t>(stream)); centroid_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, label, sum, reinterpret_cast<long long*>(cnt), n, K, D, rows_per_block); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
@@ -180,7 +180,7 @@ extern "C" int avld_radii(avld_ctx* c, const float* Z, const float* centroid, fl
   }
   const long long want = (n + 7) / 8;
   const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(c->sm_count) * 8));
-  radii_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, centroid, radii, n, K, D);
+  { LaunchScope ls(c, ST_RADII, static_cast<cudaStream_t>(stream)); radii_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, centroid, radii, n, K, D); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
@@ -191,7 +191,7 @@ extern "C" int avld_decide(avld_ctx* c, const float* radii, const double* thr, c
   AVLD_CHECK(K >= 1, AVLD_ERR_INVALID, "K must be >= 1");
   if (n <= 0) return AVLD_OK;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(c->sm_count) * 8));
-  decide_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(radii, thr, priority_rank, pred, best_d, n, K);
+  { LaunchScope ls(c, ST_DECIDE, static_cast<cudaStream_t>(stream)); decide_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(radii, thr, priority_rank, pred, best_d, n, K); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
@@ -243,7 +243,7 @@ extern "C" int avld_order_stats(avld_ctx* c, const float* radii, const int32_t* 
       BucketGroup G{};
       G.nb = static_cast<int>(std::min<size_t>(8, buckets.size() - g0));
       for (int b = 0; b < G.nb; ++b) G.b[b] = buckets[g0 + b];
-      select_hist_kernel<<<grid, 512, static_cast<size_t>(G.nb) * 2048 * 4, st>>>(radii, label, n, K, G, c->d_hist + g0 * 2048);
+      { LaunchScope ls(c, ST_SELECT, st); select_hist_kernel<<<grid, 512, static_cast<size_t>(G.nb) * 2048 * 4, st>>>(radii, label, n, K, G, c->d_hist + g0 * 2048); }
       AVLD_CUDA(cudaGetLastError());
     }
     h_hist.resize(buckets.size() * 2048);

@@ -19,7 +19,7 @@ struct PrepParams {
   const float* x;
   float* y;               // nullable
   __half* a_hi;           // nullable (operand mode)
-  __nv_bfloat16* a_lo;
+  __half* a_lo;
   float* inv2;
   uint8_t* ok;            // nullable
   float* rms;             // nullable
@@ -31,6 +31,7 @@ struct PrepParams {
   int L, n_fft, hop, R;
   float target_rms, rms_min, eps;
   int normalize, quantize;
+  int dft_scale_log2;
 };
 
 __device__ __forceinline__ float finish_sample(float v, float scale, int scaled, int quantize) {
@@ -38,7 +39,11 @@ __device__ __forceinline__ float finish_sample(float v, float scale, int scaled,
     v = __fmul_rn(v, scale);
     v = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);   // np.clip keeps NaN
   }
-  if (quantize) v = __fmul_rn(rintf(__fmul_rn(v, 32767.0f)), 1.0f / 32768.0f);  // sf.write PCM_16 + read back
+  if (quantize) {   // sf.write PCM_16 (lrintf(x * 0x7FFF)) + librosa.load (s / 0x8000); through int so that -0.0 -> +0.0
+    int q = __float2int_rn(__fmul_rn(v, 32767.0f));
+    q = q < -32768 ? -32768 : (q > 32767 ? 32767 : q);
+    v = __fmul_rn(static_cast<float>(q), 1.0f / 32768.0f);
+  }
   return v;
 }
 
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
     s_scale = scale;
     s_scaled = scaled;
     s_pow2 = ldexpf(1.0f, s);
-    if (P.inv2) P.inv2[c] = ldexpf(1.0f, -2 * s);
+    if (P.inv2) P.inv2[c] = ldexpf(1.0f, -2 * (s + P.dft_scale_log2));
     if (P.ok) P.ok[c] = P.normalize ? static_cast<uint8_t>(scaled) : static_cast<uint8_t>(1);
     if (P.rms) P.rms[c] = rms;
   }
@@ -160,11 +165,11 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
     const int half = P.n_fft / 2;
     const int total = P.R * P.hop;                       // multiple of 64
     __half* __restrict__ ah = P.a_hi + static_cast<size_t>(c) * total;
-    __nv_bfloat16* __restrict__ al = P.a_lo + static_cast<size_t>(c) * total;
+    __half* __restrict__ al = P.a_lo + static_cast<size_t>(c) * total;
     for (int v8 = tid; v8 < (total >> 3); v8 += blockDim.x) {
       const int p0 = v8 << 3;
       __align__(16) __half hi[8];
-      __align__(16) __nv_bfloat16 lo[8];
+      __align__(16) __half lo[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int p = p0 + q;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
         if (p < P.L + P.n_fft) v = finish_sample(xc[src], scale, scaled, P.quantize) * pow2;
         const __half h = __float2half_rn(v);
         hi[q] = h;
-        lo[q] = __float2bfloat16_rn(v - __half2float(h));
+        lo[q] = __float2half_rn(v - __half2float(h));
       }
       *reinterpret_cast<uint4*>(ah + p0) = *reinterpret_cast<const uint4*>(hi);
       *reinterpret_cast<uint4*>(al + p0) = *reinterpret_cast<const uint4*>(lo);
@@ -210,13 +215,14 @@ int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, b
   P.eps = eps;
   P.normalize = normalize ? 1 : 0;
   P.quantize = quantize ? 1 : 0;
+  P.dft_scale_log2 = c->dft_scale_log2;
   const size_t smem = static_cast<size_t>(c->n_leaves + c->n_nodes + 1) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     AVLD_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
     configured = true;
   }
-  prep_kernel<<<n, 512, smem, st>>>(P);
+  { LaunchScope ls(c, ST_PREP, st); prep_kernel<<<n, 512, smem, st>>>(P); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }

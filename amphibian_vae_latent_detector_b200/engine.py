@@ -1,0 +1,281 @@
+"""Host-side engine: torch tensors in, torch tensors out, every operation a call into ``libavld.so``.
+
+PyTorch is used for device memory, streams and ``torch.distributed`` only.  There is no fallback: a
+missing library raises at import of :mod:`_lib`, a failing call raises :class:`AvldError`, CPU tensors
+are rejected (except by :meth:`Engine.encode_detect_host`, whose contract is host buffers).
+
+Reference functions behind each method (paths relative to ``latent_space_exploration/``):
+
+=============================  =====================================================================
+``rms_normalize``              ``rms_normalize`` 00_normalize_dataset_rms.py:29-38 (+ ``sf.write`` :57)
+``logmel`` / ``normalize_logmel``  ``wav_to_mel`` map_detector_core.py:198-237 after the file load
+``load_encoder`` / ``encoder_forward``  ``load_encoder`` core:150-179, ``encoder(x)`` core:270-300
+``encode``                     ``encode_wav_to_latent`` core:240-300 on in-memory chunks
+``centroid_accumulate``/``radii``/``order_stats``  ``fit_species_with_fp_control`` 08:310-333
+``decide``                     ``detect_species`` 09:416-436, ``predict_one`` 10:175-199
+``fit_radial``                 the fit loop 08:530-558 (+ the q_out grid of run_qout_grid.sh:13)
+=============================  =====================================================================
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .radial_fit import RadialFit, fit_radial
+from .encoder import ConvOp, EncoderProgram, LinearOp, export_program
+
+DEFAULTS = dict(sr=48000, n_fft=2048, hop_length=384, n_mels=64, fmin=150.0, fmax=15000.0, target_frames=192,
+                amin=1e-10, top_db=80.0)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    def __init__(self, device: int | torch.device = 0, *, chunk_len: int = 144000, max_batch: int = 256,
+                 sr: int = 48000, n_fft: int = 2048, hop_length: int = 384, n_mels: int = 64, fmin: float = 150.0,
+                 fmax: float = 15000.0, target_frames: int = 192, amin: float = 1e-10, top_db: float = 80.0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("amphibian_vae_latent_detector_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+        self.params = _lib.Params(sr, chunk_len, n_fft, hop_length, n_mels, fmin, fmax, target_frames, amin, top_db,
+                                  max_batch)
+        self.chunk_len, self.max_batch = int(chunk_len), int(max_batch)
+        self.target_frames, self.n_mels = int(target_frames), int(n_mels)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.avld_ctx_create(self.device.index, C.byref(self.params), C.byref(h)))
+        self._h = h
+        nf, ld, sm = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self.lib.avld_ctx_info(self._h, C.byref(nf), C.byref(ld), C.byref(sm)))
+        self.n_frames, self.sm_count = nf.value, sm.value
+        self.latent_dim = 0
+        self.program: Optional[EncoderProgram] = None
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.avld_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor) or t.device != self.device:
+            raise ValueError(f"{name} must be a tensor on {self.device} (got {getattr(t, 'device', type(t))})")
+        if t.dtype != dtype:
+            raise ValueError(f"{name} must be {dtype} (got {t.dtype})")
+        return t.contiguous()
+
+    # ------------------------------------------------------------------ accounting
+    def profile(self, on: bool) -> None:
+        _lib.check(self.lib.avld_profile_enable(self._h, int(on)))
+
+    def collect(self, reset: bool = True) -> Dict[str, Dict[str, float]]:
+        """-> ``{kernel family: {ms, timed_launches, launches}}`` (launch counts since the last reset)."""
+        ns = self.lib.avld_stage_count()
+        ms = (C.c_double * ns)()
+        tl = (C.c_int64 * ns)()
+        ln = (C.c_uint64 * ns)()
+        _lib.check(self.lib.avld_profile_collect(self._h, ms, tl, ln, int(reset)))
+        return {self.lib.avld_stage_name(i).decode(): dict(ms=ms[i], timed_launches=int(tl[i]), launches=int(ln[i]))
+                for i in range(ns)}
+
+    # ------------------------------------------------------------------ R1 / R2
+    def rms_normalize(self, x: torch.Tensor, target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8,
+                      pcm16: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> ``(y [n,L] f32, ok [n] uint8, rms [n] f32)``; bit-exact with numpy-2 float32 semantics."""
+        x = self._dev(x, torch.float32, "x")
+        if x.ndim != 2 or x.shape[1] != self.chunk_len:
+            raise ValueError(f"x must be [n, {self.chunk_len}]")
+        n = x.shape[0]
+        y = torch.empty_like(x)
+        ok = torch.empty(n, dtype=torch.uint8, device=self.device)
+        rms = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_rms_normalize(self._h, _ptr(x), _ptr(y), _ptr(ok), _ptr(rms), n, target_rms, rms_min,
+                                               eps, int(pcm16), _stream()))
+        return y, ok, rms
+
+    # ------------------------------------------------------------------ M2-M5 + E0
+    def logmel(self, y: torch.Tensor) -> torch.Tensor:
+        """-> features ``[n, T, M]`` float32 (= ``wav_to_mel(...).T`` per chunk)."""
+        y = self._dev(y, torch.float32, "y")
+        if y.ndim != 2 or y.shape[1] != self.chunk_len:
+            raise ValueError(f"y must be [n, {self.chunk_len}]")
+        feat = torch.empty(y.shape[0], self.target_frames, self.n_mels, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_logmel(self._h, _ptr(y), _ptr(feat), y.shape[0], _stream()))
+        return feat
+
+    def normalize_logmel(self, x: torch.Tensor, target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8,
+                         pcm16: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        x = self._dev(x, torch.float32, "x")
+        n = x.shape[0]
+        feat = torch.empty(n, self.target_frames, self.n_mels, dtype=torch.float32, device=self.device)
+        ok = torch.empty(n, dtype=torch.uint8, device=self.device)
+        rms = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_normalize_logmel(self._h, _ptr(x), _ptr(feat), _ptr(ok), _ptr(rms), n, target_rms,
+                                                  rms_min, eps, int(pcm16), _stream()))
+        return feat, ok, rms
+
+    # ------------------------------------------------------------------ L1 / E1 / E2
+    def load_encoder(self, module_or_program) -> EncoderProgram:
+        """Accepts the ``nn.Module`` the reference's ``load_encoder`` returns (core:150-179) or an
+        already exported :class:`EncoderProgram`."""
+        prog = module_or_program if isinstance(module_or_program, EncoderProgram) else \
+            export_program(module_or_program, self.target_frames, self.n_mels)
+        layers = (_lib.Layer * len(prog.ops))()
+        keep = []
+        for i, op in enumerate(prog.ops):
+            w = np.ascontiguousarray(op.weight, dtype=np.float32)
+            b = np.ascontiguousarray(op.bias, dtype=np.float32)
+            keep += [w, b]
+            L = layers[i]
+            if isinstance(op, ConvOp):
+                cout, kh, _, cin = w.shape
+                L.kind, L.c_in, L.c_out, L.ksize, L.stride, L.pad = 0, cin, cout, kh, op.stride, op.pad
+                L.relu, L.pool, L.in_h, L.in_w = int(op.relu), op.pool, op.in_hw[0], op.in_hw[1]
+            elif isinstance(op, LinearOp):
+                L.kind, L.c_in, L.c_out, L.ksize, L.stride, L.pad = 1, w.shape[1], w.shape[0], 1, 1, 0
+                L.relu, L.pool, L.in_h, L.in_w = int(op.relu), 1, 1, 1
+            else:
+                raise TypeError(type(op))
+            L.weight = w.ctypes.data_as(C.POINTER(C.c_float))
+            L.bias = b.ctypes.data_as(C.POINTER(C.c_float))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.avld_encoder_load(self._h, layers, len(prog.ops)))
+        self.latent_dim = prog.latent_dim
+        self.program = prog
+        return prog
+
+    def encoder_forward(self, feat: torch.Tensor) -> torch.Tensor:
+        feat = self._dev(feat, torch.float32, "feat")
+        if feat.ndim == 4 and feat.shape[1] == 1:
+            feat = feat[:, 0]
+        if feat.ndim != 3 or tuple(feat.shape[1:]) != (self.target_frames, self.n_mels):
+            raise ValueError(f"feat must be [n, {self.target_frames}, {self.n_mels}]")
+        feat = feat.contiguous()
+        mu = torch.empty(feat.shape[0], self.latent_dim, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_encoder_forward(self._h, _ptr(feat), _ptr(mu), feat.shape[0], _stream()))
+        return mu
+
+    def encode(self, x: torch.Tensor, *, pcm16: bool = True, target_rms: float = 0.05, rms_min: float = 1e-4,
+               eps: float = 1e-8) -> Tuple[torch.Tensor, torch.Tensor]:
+        """raw chunks ``[n, L]`` -> ``(mu [n, D], ok [n])``: normalise (+ PCM_16 round trip of the
+        ``*_norm`` dataset on disk) -> log-mel -> encoder."""
+        x = self._dev(x, torch.float32, "x")
+        n = x.shape[0]
+        mu = torch.empty(n, self.latent_dim, dtype=torch.float32, device=self.device)
+        ok = torch.empty(n, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.avld_encode(self._h, _ptr(x), _ptr(mu), _ptr(ok), n, target_rms, rms_min, eps, int(pcm16),
+                                        _stream()))
+        return mu, ok
+
+    # ------------------------------------------------------------------ F1-F3
+    def centroid_accumulate(self, Z: torch.Tensor, label: torch.Tensor, K: int,
+                            out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        Z = self._dev(Z, torch.float32, "Z")
+        label = self._dev(label, torch.int32, "label")
+        D = Z.shape[1]
+        if out is None:
+            out = (torch.zeros(K, D, dtype=torch.float64, device=self.device),
+                   torch.zeros(K, dtype=torch.int64, device=self.device))
+        _lib.check(self.lib.avld_centroid_accumulate(self._h, _ptr(Z), _ptr(label), _ptr(out[0]), _ptr(out[1]),
+                                                     Z.shape[0], K, D, _stream()))
+        return out
+
+    def radii(self, Z: torch.Tensor, centroid: torch.Tensor) -> torch.Tensor:
+        Z = self._dev(Z, torch.float32, "Z")
+        centroid = self._dev(centroid, torch.float32, "centroid")
+        K, D = centroid.shape
+        if Z.shape[1] != D:
+            raise ValueError("latent / centroid dimension mismatch")
+        r = torch.empty(Z.shape[0], K, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_radii(self._h, _ptr(Z), _ptr(centroid), _ptr(r), Z.shape[0], K, D, _stream()))
+        return r
+
+    def order_stats(self, radii: torch.Tensor, label: torch.Tensor,
+                    queries: Sequence[Tuple[int, int, int]]) -> np.ndarray:
+        """``queries`` = (species, side, rank) triples -> float32 values (exact selection)."""
+        radii = self._dev(radii, torch.float32, "radii")
+        label = self._dev(label, torch.int32, "label")
+        arr = (_lib.RankQuery * len(queries))(*[_lib.RankQuery(int(k), int(s), int(r)) for k, s, r in queries])
+        out = np.empty(len(queries), dtype=np.float32)
+        _lib.check(self.lib.avld_order_stats(self._h, _ptr(radii), _ptr(label), radii.shape[0], radii.shape[1], arr,
+                                             len(queries), out.ctypes.data_as(C.POINTER(C.c_float)), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ D2
+    def decide(self, radii: torch.Tensor, thr: torch.Tensor, priority_rank: torch.Tensor):
+        radii = self._dev(radii, torch.float32, "radii")
+        thr = self._dev(thr, torch.float64, "thr")
+        priority_rank = self._dev(priority_rank, torch.int32, "priority_rank")
+        n, K = radii.shape
+        pred = torch.empty(n, dtype=torch.int32, device=self.device)
+        best = torch.empty(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_decide(self._h, _ptr(radii), _ptr(thr), _ptr(priority_rank), _ptr(pred), _ptr(best), n,
+                                        K, _stream()))
+        return pred, best
+
+    def encode_detect_host(self, x_host, centroid: np.ndarray, thr: np.ndarray, priority_rank: np.ndarray, *,
+                           pcm16: bool = True, want_mu: bool = False):
+        """HOST buffers in / out (the call the drop-in layer makes per batch of decoded files):
+        ``x_host [n, L]`` float32 (numpy or CPU tensor, pinned for full copy/compute overlap) ->
+        ``(pred [n] int32, best_d [n] f32, ok [n] uint8, mu [n, D] f32 | None)`` as numpy arrays."""
+        xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host, np.float32))
+        if xt.device.type != "cpu" or xt.dtype != torch.float32 or xt.ndim != 2 or xt.shape[1] != self.chunk_len:
+            raise ValueError(f"x_host must be a CPU float32 [n, {self.chunk_len}] array")
+        xt = xt.contiguous()
+        n = xt.shape[0]
+        centroid = np.ascontiguousarray(centroid, dtype=np.float32)
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        priority_rank = np.ascontiguousarray(priority_rank, dtype=np.int32)
+        K = centroid.shape[0]
+        pred = np.empty(n, dtype=np.int32)
+        best = np.empty(n, dtype=np.float32)
+        ok = np.empty(n, dtype=np.uint8)
+        mu = np.empty((n, self.latent_dim), dtype=np.float32) if want_mu else None
+        _lib.check(self.lib.avld_encode_detect_host(
+            self._h, xt.data_ptr(), n, int(pcm16), centroid.ctypes.data, thr.ctypes.data, priority_rank.ctypes.data, K,
+            pred.ctypes.data, best.ctypes.data, None if mu is None else mu.ctypes.data, ok.ctypes.data))
+        return pred, best, ok, mu
+
+    # ------------------------------------------------------------------ bring-up entry of the tcgen05 GEMM core
+    def dbg_gemm(self, A: torch.Tensor, B: torch.Tensor, mode: int = 1) -> torch.Tensor:
+        """``C[M,N] = A[M,K] @ B[N,K]^T`` through the split-precision tcgen05 core (tests only)."""
+        A = self._dev(A, torch.float32, "A")
+        B = self._dev(B, torch.float32, "B")
+        M, K = A.shape
+        N = B.shape[0]
+        Cm = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_dbg_gemm(self._h, _ptr(A), _ptr(B), _ptr(Cm), M, N, K, mode, _stream()))
+        return Cm
+
+    # ------------------------------------------------------------------ the fit (08:530-558), grid-aware, multi-GPU
+    def fit_radial(self, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 0.95,
+                   q_out: float | Sequence[float] = 0.01, *, group=None, semantics: str = "numpy2") -> RadialFit:
+        """See :func:`radial_fit.fit_radial` (this engine supplies the CUDA kernels)."""
+        Z = self._dev(Z, torch.float32, "Z")
+        label = self._dev(label, torch.int32, "label")
+        return fit_radial(self, Z, label, K, q_in, q_out, group=group, semantics=semantics)
+
+
+def priority_ranks(species: Sequence[str], priority: Sequence[str]) -> np.ndarray:
+    """Rank of each species under 09:428-436: first the species listed in ``PRIORITY_ORDER`` (in that
+    order), then every other name in ``sorted()`` order."""
+    rest = sorted(s for s in species if s not in priority)
+    order = [s for s in priority if s in species] + rest
+    return np.array([order.index(s) for s in species], dtype=np.int32)

@@ -89,6 +89,16 @@ void avld_ctx_destroy(avld_ctx* ctx);
 /* derived sizes: frames per chunk F = 1 + chunk_len / hop, latent dim D (0 before encoder_load) */
 int avld_ctx_info(const avld_ctx* ctx, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count);
 
+/* ---- accounting -------------------------------------------------------------------------------
+ * Every kernel launch is counted per kernel family ("stage"); with profiling enabled each launch is
+ * additionally bracketed by CUDA events on its own stream.  avld_profile_collect synchronises on the
+ * recorded events and returns, per stage, the summed device time (ms), the number of timed launches
+ * and the total launch count; arrays of avld_stage_count() entries, any may be NULL. */
+int avld_profile_enable(avld_ctx* ctx, int on);
+int avld_profile_collect(avld_ctx* ctx, double* ms, int64_t* timed_launches, uint64_t* launches, int reset);
+int avld_stage_count(void);
+const char* avld_stage_name(int stage);
+
 /* ---- R1/R2: rms_normalize (00_normalize_dataset_rms.py:29-38), batched -------------------------
  * x, y: dev float32 [n, chunk_len]; ok: dev uint8 [n] (1 = scaled, 0 = silence gate: copied
  * unchanged); rms: dev float32 [n] or NULL.  Bit-exact with numpy-2 float32 semantics (pairwise
@@ -159,7 +169,7 @@ int avld_mel_taps(const avld_params* params, int32_t* first, float* w0, float* w
 
 /* ---- test / bring-up entry (exercises the tcgen05 split-precision GEMM core on plain matrices) --
  * C[M,N] = A[M,K] * B[N,K]^T, all dev float32 row-major, K % 64 == 0, N % 16 == 0, N <= 256*tiles.
- * mode 0: fp16 hi + bf16 lo operands; mode 1: bf16 hi + bf16 lo. Synchronous. */
+ * mode 0: fp16 hi + fp16 lo operands; mode 1: bf16 hi + bf16 lo. Synchronous. */
 int avld_dbg_gemm(avld_ctx* ctx, const float* A, const float* B, float* C, int64_t M, int32_t N,
                   int32_t K, int32_t mode, void* stream);
 

@@ -32,3 +32,33 @@ def load_pcm_case(path):
 def standin_encoder():
     from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
     return build_standin_encoder(seed=123)
+
+
+def _cuda_ok():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def engine3s(standin_encoder):
+    """Engine for 3 s chunks with the stand-in encoder loaded (GPU tests only)."""
+    if not _cuda_ok():
+        pytest.skip("no CUDA device")
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    eng = Engine(0, chunk_len=144000, max_batch=64)
+    eng.load_encoder(standin_encoder)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
+def engine5s():
+    if not _cuda_ok():
+        pytest.skip("no CUDA device")
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    eng = Engine(0, chunk_len=240000, max_batch=16)
+    yield eng
+    eng.close()

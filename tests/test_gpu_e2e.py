@@ -1,0 +1,44 @@
+"""GPU: whole path through the host-buffer C-ABI call (avld_encode_detect_host): raw chunks on the host ->
+decisions, vs the numpy oracle run chunk by chunk the way the reference does (config 1, reduced to 64 chunks
+so the CPU side finishes in seconds)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hotpath as hp
+from amphibian_vae_latent_detector_b200 import synth
+from amphibian_vae_latent_detector_b200.engine import priority_ranks
+
+pytestmark = pytest.mark.gpu
+MEL_KW = dict(sr=48000, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048, target_frames=192)
+SPECIES = ["Batrachyla_leptopus", "Batrachyla_taeniata", "Calyptocephalella_gayi", "Pleurodema_thaul"]
+
+
+def test_encode_fit_detect_vs_oracle(engine3s, standin_encoder):
+    n = 96
+    x, label = synth.make_chunks(n, 144000, seed=123, special_every=25)
+    # ---- oracle, per chunk (the reference's execution model)
+    yo, oko, _ = hp.rms_normalize_batch(x.numpy(), pcm16=True)
+    Zo = hp.encode_batch(standin_encoder, yo, **MEL_KW)
+    cent_o, rk_o, rk_in_o, rk_out_o = hp.fit_radial(Zo, label.numpy(), 4, 0.95, 0.10)
+    pred_o, best_o, radii_o = hp.decide_batch(Zo, SPECIES, cent_o, rk_o)
+
+    # ---- GPU: encode on device, fit, then the host-buffer end-to-end detect call
+    Z, ok = engine3s.encode(x.cuda(), pcm16=True)
+    assert np.array_equal(ok.cpu().numpy(), oko)
+    Zn = Z.cpu().numpy()
+    assert np.max(np.abs(Zn - Zo)) / np.max(np.abs(Zo)) < 1e-3
+    fit = engine3s.fit_radial(Z, label.cuda(), 4, 0.95, 0.10)
+    assert np.max(np.abs(fit.centroids - cent_o)) / np.max(np.abs(cent_o)) < 1e-3
+    assert np.allclose(fit.rk[0], rk_o, rtol=1e-3)
+    prio = priority_ranks(SPECIES, hp.PRIORITY_ORDER)
+    xp = x.pin_memory()
+    pred, best, ok_h, mu_h = engine3s.encode_detect_host(xp, cent_o, rk_o, prio, pcm16=True, want_mu=True)
+    assert np.array_equal(ok_h, oko)
+    assert np.max(np.abs(mu_h - Zo)) / np.max(np.abs(Zo)) < 1e-3
+    # decisions identical except chunks within 1e-3 of a threshold
+    near = np.any(np.abs(radii_o - rk_o[None]) / rk_o[None] <= 1e-3, axis=1)
+    assert np.array_equal(pred[~near], pred_o[~near]), (pred, pred_o)
+    assert near.sum() < n // 4
+    assert np.allclose(best, best_o, rtol=1e-3)
+    assert len(set(pred_o.tolist())) >= 3          # detections of several species and NO_DETECT all occur
