@@ -12,7 +12,7 @@ a q_out grid (run_qout_grid.sh:13 refits per grid point; the radii do not depend
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -31,6 +31,7 @@ class RadialFit:
     q_in: float
     q_out: Tuple[float, ...]
     summaries: Dict[str, np.ndarray]   # 'in' / 'out' -> [K, 4] = (min, p50, p90, max), summarize_dist 08:115-123
+    radii_local: Optional[torch.Tensor] = None   # [n_local, K] radii of this rank's rows to the fitted centroids
 
 
 def all_gather_rows(radii: torch.Tensor, label: torch.Tensor, group) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -82,6 +83,7 @@ def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 
     counts = cnts.cpu().numpy()
     cent = (sums / cnts.clamp_min(1).to(torch.float64)[:, None]).to(torch.float32)   # mean(...).astype(f32), 08:316
     radii = ops.radii(Z, cent)
+    radii_local = radii
     lab = label
     if distributed:
         radii, lab = all_gather_rows(radii, label, group)
@@ -125,4 +127,4 @@ def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 
     rk = np.minimum(rk_in[None, :], rk_out)
     cent_np = cent.cpu().numpy().copy()
     cent_np[counts == 0] = np.nan
-    return RadialFit(cent_np, counts, rk_in, rk_out, rk, float(q_in), q_outs, summ)
+    return RadialFit(cent_np, counts, rk_in, rk_out, rk, float(q_in), q_outs, summ, radii_local)

@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: end-to-end encode+detect chunks/s (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm on the host cores
+
+Workload (BASELINE.json configs[1], weak-scaled for N > 1): per GPU `--chunks` (default 100 000) synthetic mono
+3 s chunks (48 kHz, 144 000 samples), random-init stand-in encoder (seed 123).
+One *step* = one pass of the whole hot path over the rank's resident chunks:
+  RMS normalise (+PCM_16 round trip) -> STFT/mel/log/z-score -> encoder mu        [avld_encode]
+  -> per-species centroid sums (+ all-reduce) -> radii (+ all-gather) -> exact q_in / q_out-grid quantiles
+  -> accept / priority decision -> per-class decision histogram read back         [fit_radial + avld_decide]
+`value` times that with inputs resident in HBM; `e2e` times the host-buffer C-ABI call
+(avld_encode_detect_host: pinned host audio in, decisions out, H2D/D2H inside the timed region).
+Inputs (57.6 GB per GPU) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+SPECIES = ["Batrachyla_leptopus", "Batrachyla_taeniata", "Calyptocephalella_gayi", "Pleurodema_thaul"]
+PRIORITY_ORDER = SPECIES                      # 09_evaluate_wav_detection.py:61-66
+MEL_KW = dict(sr=48000, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048, target_frames=192)
+CHUNK_LEN = 144000
+Q_IN, Q_OUT_GRID = 0.95, (0.10, 0.15, 0.20, 0.25)          # run_qout_grid.sh:6, :13
+DFT_FLOP_PER_CHUNK = 2.0 * 376 * 2048 * (2 * 634)          # 1.953 GFLOP (algorithmic, 1 pass)
+METRIC = "encode+detect chunks/sec"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chunks", type=int, default=100000, help="resident chunks per GPU (one step processes all)")
+    ap.add_argument("--e2e-chunks", type=int, default=8192, help="host-resident chunks per e2e step")
+    ap.add_argument("--max-batch", type=int, default=1024, help="chunks per internal kernel pass")
+    ap.add_argument("--cpu-chunks", type=int, default=192, help="chunks of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), tflops_burst=float(d["bf16_tflops"]),
+                    tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle = numpy/torch restatement of the reference algorithm; oracle/ is test infrastructure and is
+# only *timed* here, never used by the CUDA path)
+# ------------------------------------------------------------------------------------------------------------
+def _cpu_fit_detect(Z, labels, hp):
+    cent, rk, _, _ = hp.fit_radial(Z, labels, 4, Q_IN, Q_OUT_GRID[0])
+    for q in Q_OUT_GRID[1:]:
+        hp.fit_radial(Z, labels, 4, Q_IN, q)
+    pred, best, _ = hp.decide_batch(Z, SPECIES, cent, rk)
+    return pred
+
+
+def cpu_reference_loop(x: np.ndarray, labels: np.ndarray):
+    """The reference's execution model: one chunk at a time, batch 1 (08:488-506, 10:395-418)."""
+    from oracle import hotpath as hp
+    from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
+    enc = build_standin_encoder(seed=123)
+    t0 = time.perf_counter()
+    y, ok, _ = hp.rms_normalize_batch(x, pcm16=True)
+    Z = hp.encode_batch(enc, y, **MEL_KW)
+    _cpu_fit_detect(Z, labels, hp)
+    return time.perf_counter() - t0
+
+
+def _pool_worker(args):
+    seed, n = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import hotpath as hp
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
+    global _ENC
+    try:
+        enc = _ENC
+    except NameError:
+        enc = _ENC = build_standin_encoder(seed=123)
+    x, _ = synth.make_chunks(n, CHUNK_LEN, seed=123, first_index=seed)
+    t0 = time.perf_counter()
+    y, ok, _ = hp.rms_normalize_batch(x.numpy(), pcm16=True)
+    Z = hp.encode_batch(enc, y, **MEL_KW)
+    return Z, time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm on all host cores (process pool, one chunk at a time
+    inside each worker); rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import hotpath as hp
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    per_worker = 4
+    n_step = workers * per_worker
+    ctx = mp.get_context("spawn")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for it in range(args.warmup + args.steps):
+            jobs = [(it * n_step + w * per_worker, per_worker) for w in range(workers)]
+            t0 = time.perf_counter()
+            res = pool.map(_pool_worker, jobs)
+            Z = np.concatenate([r[0] for r in res])
+            labels = (np.arange(n_step) % 4).astype(np.int32)
+            _cpu_fit_detect(Z, labels, hp)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = n_step * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 FFT)",
+            "data": "synthetic",
+            "config": {"workload": "synthetic 3 s mono chunks, encode+radial fit/detect, stand-in encoder",
+                       "chunk_len": CHUNK_LEN, "chunks_per_step": n_step, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": workers, "kind": "port",
+                             "sample": f"{n_step} chunks per step, process pool of {workers} single-thread workers "
+                                       f"running the numpy/torch oracle of the reference algorithm"},
+            "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
+    from amphibian_vae_latent_detector_b200.engine import Engine, priority_ranks
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group=group, device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    # ---------------- setup (untimed)
+    n = args.chunks
+    eng = Engine(local_rank, chunk_len=CHUNK_LEN, max_batch=args.max_batch)
+    eng.load_encoder(build_standin_encoder(seed=123))
+    X = torch.empty(n, CHUNK_LEN, dtype=torch.float32, device=dev)
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    slab = 1024
+    for i in range(0, n, slab):
+        m = min(slab, n - i)
+        xs, ls = synth.make_chunks(m, CHUNK_LEN, seed=123, first_index=rank * n + i, device=dev)
+        X[i:i + m], labels[i:i + m] = xs, ls
+    del xs, ls
+    torch.cuda.empty_cache()
+    prio = priority_ranks(SPECIES, PRIORITY_ORDER)
+    prio_d = torch.from_numpy(prio).to(dev)
+    state = {}
+
+    def step():
+        Z, ok = eng.encode(X, pcm16=True)
+        fit = eng.fit_radial(Z, labels, 4, Q_IN, Q_OUT_GRID, group=group)
+        thr = torch.from_numpy(fit.rk[0]).to(dev)
+        pred, best = eng.decide(fit.radii_local, thr, prio_d)
+        hist = torch.bincount((pred + 1).long(), minlength=5).cpu()        # D2H read of the step's result
+        state.update(fit=fit, hist=hist, ok=ok)
+        return hist
+
+    for _ in range(args.warmup):
+        step()
+    eng.collect(reset=True)
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    eng.profile(False)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+    total_ms = float(ms.item())
+    value = world * n * args.steps / (total_ms / 1e3)
+    stages = eng.collect(reset=True)
+    launches = sum(v["launches"] for v in stages.values())
+
+    # ---------------- e2e through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_chunks, n)
+        fit = state["fit"]
+        xh = torch.empty(ne, CHUNK_LEN, dtype=torch.float32, pin_memory=True)
+        xh.copy_(X[:ne])
+        torch.cuda.synchronize()
+        cent, thr = np.nan_to_num(fit.centroids), fit.rk[0]
+        for _ in range(2):
+            eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pred_h, best_h, ok_h, _ = eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=group)
+        e2e = {"value": world * ne * args.steps / float(dt.item()), "unit": "chunks/s",
+               "h2d_bytes_per_step": int(ne) * CHUNK_LEN * 4, "d2h_bytes_per_step": int(ne) * (4 + 4 + 1),
+               "chunks_per_step": int(ne), "api": "avld_encode_detect_host (pinned host float32 audio -> decisions)"}
+        eng.collect(reset=True)
+        del xh
+
+    if rank == 0:
+        peaks = measured_peaks()
+        dft = stages["gemm3_kernel<DFT>"]
+        chunks_timed = n * args.steps
+        dft_tflops = DFT_FLOP_PER_CHUNK * chunks_timed / (dft["ms"] / 1e3) / 1e12 if dft["ms"] > 0 else None
+        stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in stages.items() if v["timed_launches"]}
+        kernel_ms = sum(stage_ms.values())
+        hbm = {}
+        prep = stages["prep_kernel"]
+        if prep["ms"] > 0:   # reads 4L, writes fp16 hi+lo operand rows incl. reflect padding: 4 * 381 * 384 bytes
+            hbm["prep_kernel"] = round((4 * CHUNK_LEN + 4 * 381 * 384) * chunks_timed / (prep["ms"] / 1e3) / 1e9, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16x2 split operands, fp32 accumulate (TMEM)", "data": "synthetic",
+            "config": {"workload": "100k synthetic 3 s mono chunks per GPU (configs[1]): RMS-normalise + log-mel + "
+                                   "encoder mu + radial fit (q_in 0.95, q_out grid) + decision; stand-in encoder, random init",
+                       "chunk_len": CHUNK_LEN, "chunks_per_gpu": n, "max_batch": args.max_batch,
+                       "l2": "inputs (57.6 GB/GPU at 100k chunks) exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}"},
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm3_kernel<256,128,EPI_DFT> (windowed DFT as GEMM + |X|^2 + mel)",
+                         "achieved": dft_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (dft_tflops / peaks["tflops_sustained"]) if dft_tflops else None,
+                         "peak_source": f"bf16 dense sustained, {peaks['source']}",
+                         "issued_over_algorithmic": 3.0 * (2 * 768) / (2 * 634) * 381 / 376,
+                         "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": None,
+                         "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None},
+            "stage_ms_per_step": stage_ms,
+            "stage_hbm_gbs": hbm,
+            "decision_hist": state["hist"].tolist(),
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            nc = args.cpu_chunks
+            xc, lc = synth.make_chunks(nc, CHUNK_LEN, seed=123, first_index=0)
+            dt = cpu_reference_loop(xc.numpy(), lc.numpy())
+            line["cpu_baseline"] = {"value": nc / dt, "unit": "chunks/s", "cores": int(torch.get_num_threads()),
+                                    "kind": "port",
+                                    "sample": f"{nc} chunks of the same workload, one chunk at a time (batch 1) as the "
+                                              f"reference runs it: numpy float64 FFT + torch CPU encoder, "
+                                              f"{dt:.1f} s wall, host has {os.cpu_count()} logical cores"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

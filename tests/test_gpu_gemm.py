@@ -23,8 +23,9 @@ def test_gemm3_matches_fp64(engine3s, M, N, K, mode):
     C = engine3s.dbg_gemm(A, B, mode)
     ref = A.double() @ B.double().T
     err = _rel(C, ref)
-    # hi*hi + lo*hi + hi*lo leaves ~2^-16..2^-18 relative operand error; fp32 accumulation over K
-    assert err < 2e-5, (M, N, K, mode, err)
+    # hi*hi + lo*hi + hi*lo: bf16 pairs carry 16 mantissa bits (~2^-16 relative per operand), fp16 pairs 22;
+    # fp32 accumulation over K
+    assert err < (6e-5 if mode == 1 else 5e-6), (M, N, K, mode, err)
     # and it is much better than a single 16-bit pass, i.e. the lo terms are really applied
     one_pass = _rel((A.bfloat16().float() @ B.bfloat16().float().T), ref)
     assert err < one_pass / 20 or one_pass < 1e-6
