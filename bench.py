@@ -333,7 +333,7 @@ def main():
                          "achieved": dft_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dft_tflops / peaks["tflops_sustained"]) if dft_tflops else None,
                          "peak_source": f"bf16 dense sustained, {peaks['source']}",
-                         "issued_over_algorithmic": 3.0 * (2 * 768) / (2 * 634) * 381 / 376,
+                         "issued_over_algorithmic": 3.0 * (2 * 640) / (2 * 634) * 381 / 376,
                          "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": None,
                          "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None},
             "stage_ms_per_step": stage_ms,
