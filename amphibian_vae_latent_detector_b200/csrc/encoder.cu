@@ -123,6 +123,77 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectConvParams
   }
 }
 
+// Fast path for the usual first layer: C_in == 1, 3x3, stride 1, 'same', C_out % 8 == 0.
+// thread = (pooled output pixel, group of 8 output channels); the 72 filter taps of the group live in
+// registers for the whole kernel, the fp32 input strip (+ halo, zero padded) in shared memory; four
+// consecutive threads cover 32 channels of one pixel, so a warp stores 512 contiguous bytes of the NHWC
+// hi and lo planes.
+template <int POOL>
+__global__ void __launch_bounds__(256) conv1_kernel(const DirectConvParams P) {
+  extern __shared__ float s_in[];                               // [in_rows][in_cols]
+  const int in_rows = P.rows_per_block * POOL + 2;
+  const int in_cols = P.W + 2;
+  const int img = blockIdx.y;
+  const int orow0 = blockIdx.x * P.rows_per_block;
+  const int irow0 = orow0 * POOL - 1;
+  const float* __restrict__ src = P.in + static_cast<size_t>(img) * P.H * P.W;
+  for (int i = threadIdx.x; i < in_rows * in_cols; i += blockDim.x) {
+    const int rr = i / in_cols, cc = i - rr * in_cols;
+    const int h = irow0 + rr, w = cc - 1;
+    s_in[i] = (h >= 0 && h < P.H && w >= 0 && w < P.W) ? src[static_cast<size_t>(h) * P.W + w] : 0.f;
+  }
+  const int groups = P.Cout >> 3;
+  const int cg = threadIdx.x % groups;
+  const int co0 = cg * 8;
+  float wreg[8][9], breg[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    breg[q] = P.bias[co0 + q];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wreg[q][t] = P.w[(co0 + q) * 9 + t];
+  }
+  __syncthreads();
+  const int npix = P.rows_per_block * P.OW;
+  for (int pix = threadIdx.x / groups; pix < npix; pix += blockDim.x / groups) {
+    const int orl = pix / P.OW, oc = pix - orl * P.OW;
+    const int orow = orow0 + orl;
+    if (orow >= P.OH) break;
+    float patch[POOL + 2][POOL + 2];
+#pragma unroll
+    for (int r = 0; r < POOL + 2; ++r)
+#pragma unroll
+      for (int cc = 0; cc < POOL + 2; ++cc) patch[r][cc] = s_in[(orl * POOL + r) * in_cols + oc * POOL + cc];
+    float best[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) best[q] = -INFINITY;
+#pragma unroll
+    for (int ph = 0; ph < POOL; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < POOL; ++pw)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float a = breg[q];
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) a = fmaf(patch[ph + kh][pw + kw], wreg[q][kh * 3 + kw], a);
+          best[q] = fmaxf(best[q], a);
+        }
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float t = best[q];
+      if (P.relu) t = fmaxf(t, 0.f);
+      hi[q] = __float2bfloat16_rn(t);
+      lo[q] = __float2bfloat16_rn(t - __bfloat162float(hi[q]));
+    }
+    const size_t obase = ((static_cast<size_t>(img) * P.OH + orow) * P.OW + oc) * P.Cout + co0;
+    *reinterpret_cast<uint4*>(P.out_hi + obase) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(P.out_lo + obase) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 static int pick_bn(int cout) { return cout <= 64 ? 64 : (cout <= 128 ? 128 : 256); }
 
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st) {
@@ -142,12 +213,25 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       P.out_lo = out_lo;
       P.H = L.in_h; P.W = L.in_w; P.Cin = L.c_in; P.Cout = L.c_out; P.k = L.ksize; P.pad = L.pad;
       P.relu = L.relu; P.pool = L.pool; P.OH = L.out_h; P.OW = L.out_w;
-      P.rows_per_block = std::max(1, 256 / L.out_w);
-      const int in_rows = P.rows_per_block * P.pool + P.k - 1, in_cols = P.W + P.k - 1;
-      const size_t smem = (static_cast<size_t>(in_rows) * in_cols * P.Cin + static_cast<size_t>(P.Cout) * P.k * P.k * P.Cin + P.Cout) * sizeof(float);
-      AVLD_CHECK(smem <= 48 * 1024, AVLD_ERR_UNSUPPORTED, "first-layer direct convolution tile does not fit shared memory");
-      dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
-      { LaunchScope ls(c, ST_CONV_DIRECT, st); conv_direct_kernel<<<grid, 256, smem, st>>>(P); }
+      const int groups = P.Cout / 8;
+      const bool fast = P.Cin == 1 && P.k == 3 && P.pad == 1 && P.Cout % 8 == 0 && groups >= 1 && 256 % groups == 0 &&
+                        static_cast<size_t>(16 * P.pool + 2) * (P.W + 2) * sizeof(float) <= 48 * 1024;
+      if (fast) {
+        P.rows_per_block = 16;
+        const size_t smem = static_cast<size_t>(P.rows_per_block * P.pool + 2) * (P.W + 2) * sizeof(float);
+        dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
+        LaunchScope ls(c, ST_CONV_DIRECT, st);
+        if (P.pool == 2) conv1_kernel<2><<<grid, 256, smem, st>>>(P);
+        else conv1_kernel<1><<<grid, 256, smem, st>>>(P);
+      } else {
+        P.rows_per_block = std::max(1, 256 / L.out_w);
+        const int in_rows = P.rows_per_block * P.pool + P.k - 1, in_cols = P.W + P.k - 1;
+        const size_t smem = (static_cast<size_t>(in_rows) * in_cols * P.Cin + static_cast<size_t>(P.Cout) * P.k * P.k * P.Cin + P.Cout) * sizeof(float);
+        AVLD_CHECK(smem <= 48 * 1024, AVLD_ERR_UNSUPPORTED, "first-layer direct convolution tile does not fit shared memory");
+        dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
+        LaunchScope ls(c, ST_CONV_DIRECT, st);
+        conv_direct_kernel<<<grid, 256, smem, st>>>(P);
+      }
       AVLD_CUDA(cudaGetLastError());
     } else if (L.kind == 0) {
       Gemm3Params P{};
@@ -172,6 +256,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       Gemm3Params P{};
       P.num_m_tiles = (n + 127) / 128;
       P.num_n_tiles = (L.c_out + L.bn - 1) / L.bn;
+      P.split_n = 1;   // few m tiles (128 chunks each): spread (m, n) pairs over the SMs
       P.num_k_blocks = static_cast<int>(L.K / 64);
       P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(1, 1, 128, L.bn);
       P.a_mode = 0;
@@ -233,7 +318,7 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
         AVLD_CHECK(i > 0, AVLD_ERR_UNSUPPORTED, "layer 0 must have <= 4 input channels");
         AVLD_CHECK(s.c_in == 32 || s.c_in % 64 == 0, AVLD_ERR_UNSUPPORTED,
                    "layer %d: C_in must be 32 or a multiple of 64 for the tensor-core path (got %d)", i, s.c_in);
-        AVLD_CHECK(s.c_out % 16 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: C_out must be a multiple of 16", i);
+        AVLD_CHECK(s.c_out % 16 == 0 && s.c_out <= 2048, AVLD_ERR_UNSUPPORTED, "layer %d: C_out must be a multiple of 16, <= 2048", i);
         L.kind = 0;
         L.cblk = s.c_in == 32 ? 32 : 64;
         L.swz = L.cblk * 2;
@@ -257,10 +342,10 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
       AVLD_CHECK(i > 0, AVLD_ERR_UNSUPPORTED, "the first layer must be a convolution");
       AVLD_CHECK(s.c_in == in_features, AVLD_ERR_INVALID, "layer %d: linear expects %d inputs, previous layer gives %d", i, s.c_in, in_features);
       AVLD_CHECK(s.c_in % 64 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: linear in_features must be a multiple of 64", i);
-      AVLD_CHECK(s.c_out % 16 == 0, AVLD_ERR_UNSUPPORTED, "layer %d: linear out_features must be a multiple of 16", i);
+      AVLD_CHECK(s.c_out % 16 == 0 && s.c_out <= 2048, AVLD_ERR_UNSUPPORTED, "layer %d: linear out_features must be a multiple of 16, <= 2048", i);
       L.kind = 1;
       L.K = s.c_in;
-      L.bn = pick_bn(s.c_out);
+      L.bn = s.c_out % 64 == 0 ? 64 : (s.c_out <= 64 ? 64 : (s.c_out <= 128 ? 128 : 256));   // narrow tiles: more CTAs
       L.swz = 128;
       const size_t wcount = static_cast<size_t>(s.c_out) * s.c_in;
       AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&L.bias), s.c_out * sizeof(float)));

@@ -28,6 +28,7 @@ enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2 };
 
 struct Gemm3Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
+  int split_n;  // 1: a work item is one (m tile, n tile) pair (dense layers with few m tiles); 0: one m tile, all n tiles
   uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
   int a_mode;
   int hpb;  // a_mode 1: 64-sample blocks per hop
@@ -90,6 +91,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint64_t* tmem_empty = tmem_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);            // EPI_DFT only (<= 12 KB)
+  float* s_bias = reinterpret_cast<float*>(tail + 512);              // other epilogues: bias[N_total], zero padded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +115,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   if (EPI == EPI_DFT) {
     for (int i = threadIdx.x; i < P.nbins_pad; i += blockDim.x) s_taps[i] = P.taps[i];
+  } else {
+    const int nb = P.num_n_tiles * BN;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bias[i] = (P.bias != nullptr && i < P.N_total) ? P.bias[i] : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -120,13 +125,17 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int nkb = P.num_k_blocks;
+  const int n_items = P.split_n ? P.num_m_tiles * P.num_n_tiles : P.num_m_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mt = P.split_n ? item / P.num_n_tiles : item;
+        const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
+        const int nt_end = P.split_n ? nt_begin + 1 : P.num_n_tiles;
         int img = 0, h0 = 0, w0 = 0;
         if (P.a_mode == 2) {
           const int per_img = P.tiles_w * P.tiles_h;
@@ -135,7 +144,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           h0 = (r / P.tiles_w) * P.th;
           w0 = (r % P.tiles_w) * P.tw;
         }
-        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+        for (int nt = nt_begin; nt < nt_end; ++nt) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
             uint8_t* sa_hi = smem + stage * Cfg::STAGE_BYTES;
@@ -172,8 +181,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int n_sub = P.split_n ? 1 : P.num_n_tiles;
+        for (int sub = 0; sub < n_sub; ++sub) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -208,7 +218,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int mt = blockIdx.x; mt < P.num_m_tiles; mt += gridDim.x) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int mt = P.split_n ? item / P.num_n_tiles : item;
+      const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
+      const int nt_end = P.split_n ? nt_begin + 1 : P.num_n_tiles;
       // ---- per M-tile state
       [[maybe_unused]] int cur = 0;
       [[maybe_unused]] float acc0 = 0.f, acc1 = 0.f, s2 = 0.f;
@@ -221,7 +234,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         valid = (g < P.M_total) && (f < P.F);
         s2 = valid ? P.inv2[c] : 0.f;
       }
-      for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+      for (int nt = nt_begin; nt < nt_end; ++nt) {
         mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
@@ -238,8 +251,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               float o[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float t = __uint_as_float(v[j]);
-                if (P.bias != nullptr && n0 + j < P.N_total) t += P.bias[n0 + j];
+                float t = __uint_as_float(v[j]) + s_bias[n0 + j];
                 if (P.relu) t = fmaxf(t, 0.f);
                 o[j] = t;
               }
@@ -313,15 +325,27 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const int n0 = nt * BN + c0;
             float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float t = __uint_as_float(v[j]);
-              if (n0 + j < P.Cout) t += P.bias[n0 + j];
-              if (P.relu) t = fmaxf(t, 0.f);
-              if (P.pool == 2) {
-                t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 1));
-                t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, P.tw));
-              }
-              o[j] = t;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+              o[j] = __uint_as_float(v[j]) + b4.x;
+              o[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            if (P.pool == 2) {   // 16 independent shuffles in flight per stage
+              float u[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], 1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], P.tw);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
             }
             if (writer && n0 < P.Cout) {
               __align__(16) __nv_bfloat16 hi[16];
@@ -368,7 +392,8 @@ int launch_gemm3(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUt
     AVLD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  int grid = P.num_m_tiles < sm_count ? P.num_m_tiles : sm_count;
+  const int items = P.split_n ? P.num_m_tiles * P.num_n_tiles : P.num_m_tiles;
+  int grid = items < sm_count ? items : sm_count;
   if (grid < 1) return AVLD_OK;
   kfn<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, P);
   AVLD_CUDA(cudaGetLastError());
