@@ -63,6 +63,7 @@ _SIGNATURES = {
                                    C.POINTER(C.c_float), _P]),
     "avld_decide": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "avld_encode_detect_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
+    "avld_encode_detect_host_pcm16": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "avld_pairwise_plan": (C.c_int64, [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64]),
     "avld_mel_taps": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "avld_dbg_gemm": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -8,9 +8,10 @@
 
 using namespace avld;
 
-static int encode_pass(avld_ctx* c, const float* x, float* mu, uint8_t* ok, int m, float target_rms, float rms_min,
-                       float eps, int quantize, cudaStream_t st) {
-  AVLD_TRY(launch_prep(c, x, nullptr, true, true, ok, nullptr, m, target_rms, rms_min, eps, quantize, st));
+static int encode_pass(avld_ctx* c, const float* x, const int16_t* x16, float* mu, uint8_t* ok, int m, float target_rms,
+                       float rms_min, float eps, int quantize, cudaStream_t st) {
+  AVLD_CHECK(c->features_ok, AVLD_ERR_UNSUPPORTED, "chunk_len %d is outside the feature kernels' range", c->L);
+  AVLD_TRY(launch_prep(c, x, x16, nullptr, true, true, ok, nullptr, m, target_rms, rms_min, eps, quantize, st));
   AVLD_TRY(launch_stft_mel(c, m, st));
   AVLD_TRY(launch_logmel_post(c, c->d_feat, m, st));
   AVLD_TRY(launch_encoder(c, c->d_feat, mu, m, st));
@@ -25,16 +26,15 @@ extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t i = 0; i < n; i += c->max_batch) {
     const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
-    AVLD_TRY(encode_pass(c, x + i * c->L, mu + i * c->latent_dim, ok ? ok + i : nullptr, m, target_rms, rms_min, eps,
-                         quantize_pcm16, st));
+    AVLD_TRY(encode_pass(c, x + i * c->L, nullptr, mu + i * c->latent_dim, ok ? ok + i : nullptr, m, target_rms, rms_min,
+                         eps, quantize_pcm16, st));
   }
   return AVLD_OK;
 }
 
-extern "C" int avld_encode_detect_host(avld_ctx* c, const float* x_host, int64_t n, int quantize_pcm16,
-                                       const float* centroid, const double* thr, const int32_t* priority_rank,
-                                       int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
-                                       uint8_t* ok_host) {
+static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_bytes, int64_t n, int quantize_pcm16,
+                                   const float* centroid, const double* thr, const int32_t* priority_rank, int32_t K,
+                                   int32_t* pred_host, float* best_host, float* mu_host, uint8_t* ok_host) {
   AVLD_CHECK(c && x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0 && K >= 1 && K <= 64, AVLD_ERR_INVALID, "bad n / K");
   AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
@@ -61,11 +61,13 @@ extern "C" int avld_encode_detect_host(avld_ctx* c, const float* x_host, int64_t
     const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
     const int b = static_cast<int>(slab & 1);
     if (slab >= 2) AVLD_CUDA(cudaStreamWaitEvent(sx, c->ev_done[b], 0));   // buffer b free again
-    AVLD_CUDA(cudaMemcpyAsync(c->d_xbuf[b], x_host + i * c->L, static_cast<size_t>(m) * c->L * sizeof(float),
-                              cudaMemcpyHostToDevice, sx));
+    AVLD_CUDA(cudaMemcpyAsync(c->d_xbuf[b], static_cast<const char*>(x_host) + static_cast<size_t>(i) * c->L * sample_bytes,
+                              static_cast<size_t>(m) * c->L * sample_bytes, cudaMemcpyHostToDevice, sx));
     AVLD_CUDA(cudaEventRecord(c->ev_h2d[b], sx));
     AVLD_CUDA(cudaStreamWaitEvent(sc, c->ev_h2d[b], 0));
-    AVLD_TRY(encode_pass(c, c->d_xbuf[b], c->d_mu, c->d_ok, m, 0.05f, 1e-4f, 1e-8f, quantize_pcm16, sc));
+    AVLD_TRY(encode_pass(c, sample_bytes == 4 ? c->d_xbuf[b] : nullptr,
+                         sample_bytes == 2 ? reinterpret_cast<const int16_t*>(c->d_xbuf[b]) : nullptr, c->d_mu, c->d_ok, m,
+                         0.05f, 1e-4f, 1e-8f, quantize_pcm16, sc));
     AVLD_CUDA(cudaEventRecord(c->ev_done[b], sc));                         // x buffer consumed by the prep kernel
     AVLD_TRY(avld_radii(c, c->d_mu, c->d_cent, c->d_radii, m, K, D, sc));
     AVLD_TRY(avld_decide(c, c->d_radii, c->d_thr, c->d_prio, c->d_pred, c->d_best, m, K, sc));
@@ -79,6 +81,22 @@ extern "C" int avld_encode_detect_host(avld_ctx* c, const float* x_host, int64_t
   AVLD_CUDA(cudaStreamSynchronize(sc));
   AVLD_CUDA(cudaStreamSynchronize(sx));
   return AVLD_OK;
+}
+
+extern "C" int avld_encode_detect_host(avld_ctx* c, const float* x_host, int64_t n, int quantize_pcm16,
+                                       const float* centroid, const double* thr, const int32_t* priority_rank,
+                                       int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
+                                       uint8_t* ok_host) {
+  return encode_detect_host_impl(c, x_host, 4, n, quantize_pcm16, centroid, thr, priority_rank, K, pred_host, best_host,
+                                 mu_host, ok_host);
+}
+
+extern "C" int avld_encode_detect_host_pcm16(avld_ctx* c, const int16_t* pcm_host, int64_t n, int quantize_pcm16,
+                                             const float* centroid, const double* thr, const int32_t* priority_rank,
+                                             int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
+                                             uint8_t* ok_host) {
+  return encode_detect_host_impl(c, pcm_host, 2, n, quantize_pcm16, centroid, thr, priority_rank, K, pred_host, best_host,
+                                 mu_host, ok_host);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -82,6 +82,7 @@ struct avld_ctx {
   int bin_lo = 0, nbins_pad = 0, ncols = 0, n_tiles_n = 0;
   int T = 0, M = 0;            // target_frames, n_mels
   int crop_start = 0, pad_left = 0, frames_copy = 0;
+  bool features_ok = true;     // false: chunk too short / long for the feature kernels (RMS normalisation still works)
 
   // numpy pairwise-sum plan
   int n_leaves = 0, n_nodes = 0, n_levels = 0;
@@ -164,7 +165,7 @@ struct LaunchScope {
 };
 
 // stage launchers (each in its own translation unit)
-int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
+int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);

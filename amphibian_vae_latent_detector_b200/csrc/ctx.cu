@@ -267,7 +267,6 @@ static int build_ctx(avld_ctx* c) {
              AVLD_ERR_INVALID, "non-positive feature parameter");
   AVLD_CHECK(p.n_fft % 64 == 0, AVLD_ERR_UNSUPPORTED, "n_fft must be a multiple of 64 (got %d)", p.n_fft);
   AVLD_CHECK(p.hop % 64 == 0, AVLD_ERR_UNSUPPORTED, "hop_length must be a multiple of 64 (got %d)", p.hop);
-  AVLD_CHECK(p.chunk_len > p.n_fft / 2, AVLD_ERR_UNSUPPORTED, "chunk_len must exceed n_fft/2 (reflect padding)");
   AVLD_CHECK(p.n_mels <= 256, AVLD_ERR_UNSUPPORTED, "n_mels > 256");
   AVLD_CHECK(p.amin > 0.f && p.top_db >= 0.f, AVLD_ERR_INVALID, "amin must be > 0 and top_db >= 0");
   AVLD_CHECK(p.max_batch >= 1, AVLD_ERR_INVALID, "max_batch must be >= 1");
@@ -288,8 +287,8 @@ static int build_ctx(avld_ctx* c) {
     c->pad_left = (c->T - c->F) / 2;
     c->frames_copy = c->F;
   }
-  AVLD_CHECK(static_cast<size_t>(c->F) * c->M * sizeof(float) <= 200 * 1024, AVLD_ERR_UNSUPPORTED,
-             "chunk too long: %d frames x %d mels do not fit the log-mel kernel's shared memory", c->F, c->M);
+  // reflect padding needs L > n_fft/2 (as librosa does); the log-mel kernel keeps a whole chunk's [F, M] in shared memory
+  c->features_ok = p.chunk_len > p.n_fft / 2 && static_cast<size_t>(c->F) * c->M * sizeof(float) <= 200 * 1024;
 
   // ---- pairwise plan
   std::vector<int64_t> off, len;

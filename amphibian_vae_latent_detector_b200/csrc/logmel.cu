@@ -139,9 +139,11 @@ using namespace avld;
 
 static int features_pass(avld_ctx* c, const float* x, float* feat, uint8_t* ok, float* rms, int64_t n, bool normalize,
                          float target_rms, float rms_min, float eps, int quantize, cudaStream_t st) {
+  AVLD_CHECK(c->features_ok, AVLD_ERR_UNSUPPORTED,
+             "chunk_len %d: features need n_fft/2 < chunk_len and frames x mels x 4 <= 200 KB (got %d frames)", c->L, c->F);
   for (int64_t i = 0; i < n; i += c->max_batch) {
     const int m = static_cast<int>(n - i < c->max_batch ? n - i : c->max_batch);
-    AVLD_TRY(launch_prep(c, x + i * c->L, nullptr, true, normalize, ok ? ok + i : nullptr, rms ? rms + i : nullptr, m,
+    AVLD_TRY(launch_prep(c, x + i * c->L, nullptr, nullptr, true, normalize, ok ? ok + i : nullptr, rms ? rms + i : nullptr, m,
                          target_rms, rms_min, eps, quantize, st));
     AVLD_TRY(launch_stft_mel(c, m, st));
     AVLD_TRY(launch_logmel_post(c, feat + i * c->T * c->M, m, st));

@@ -17,6 +17,7 @@ namespace avld {
 
 struct PrepParams {
   const float* x;
+  const int16_t* x16;     // alternative input: PCM_16 samples, decoded as s / 32768 (librosa.load of a 16-bit WAV)
   float* y;               // nullable
   __half* a_hi;           // nullable (operand mode)
   __half* a_lo;
@@ -47,14 +48,33 @@ __device__ __forceinline__ float finish_sample(float v, float scale, int scaled,
   return v;
 }
 
+// sample loaders: float32 chunk or PCM_16 chunk (exact: |s| < 2^15, scale 2^-15)
+struct LoadF32 {
+  const float* p;
+  __device__ __forceinline__ float operator()(int i) const { return p[i]; }
+};
+struct LoadPcm16 {
+  const int16_t* p;
+  __device__ __forceinline__ float operator()(int i) const { return static_cast<float>(p[i]) * (1.0f / 32768.0f); }
+};
+
+template <typename Load>
+__device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, float* s_val);
+
 __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
   extern __shared__ float s_val[];            // [n_leaves + n_nodes]
+  const size_t base = static_cast<size_t>(blockIdx.x) * P.L;
+  if (P.x16 != nullptr) prep_body(P, LoadPcm16{P.x16 + base}, s_val);
+  else prep_body(P, LoadF32{P.x + base}, s_val);
+}
+
+template <typename Load>
+__device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, float* s_val) {
   __shared__ float s_red[16];
   __shared__ float s_scale, s_pow2;
   __shared__ int s_scaled;
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
-  const float* __restrict__ xc = P.x + static_cast<size_t>(c) * P.L;
 
   // ---------------------------------------------------------------- phase 1: leaves
   float mx = 0.f;
@@ -67,19 +87,19 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
       r = 0.f;
       if (j == 0) {
         for (int i = 0; i < len; ++i) {
-          const float v = xc[off + i];
+          const float v = xc(off + i);
           mx = fmaxf(mx, fabsf(v));
           r = __fadd_rn(r, __fmul_rn(v, v));
         }
       }
     } else {
       const int n8 = len & ~7;
-      float v = xc[off + j];
+      float v = xc(off + j);
       mx = fmaxf(mx, fabsf(v));
       r = __fmul_rn(v, v);
 #pragma unroll 4
       for (int i = 8; i < n8; i += 8) {
-        v = xc[off + i + j];
+        v = xc(off + i + j);
         mx = fmaxf(mx, fabsf(v));
         r = __fadd_rn(r, __fmul_rn(v, v));
       }
@@ -89,7 +109,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
       r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4, 8));
       if (j == 0) {
         for (int i = n8; i < len; ++i) {
-          v = xc[off + i];
+          v = xc(off + i);
           mx = fmaxf(mx, fabsf(v));
           r = __fadd_rn(r, __fmul_rn(v, v));
         }
@@ -143,8 +163,8 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
   // ---------------------------------------------------------------- phase 2a: y (float32)
   if (P.y != nullptr) {
     float* __restrict__ yc = P.y + static_cast<size_t>(c) * P.L;
-    if ((P.L & 3) == 0) {
-      const float4* x4 = reinterpret_cast<const float4*>(xc);
+    if ((P.L & 3) == 0 && P.x16 == nullptr) {
+      const float4* x4 = reinterpret_cast<const float4*>(P.x + static_cast<size_t>(c) * P.L);
       float4* y4 = reinterpret_cast<float4*>(yc);
       for (int i = tid; i < (P.L >> 2); i += blockDim.x) {
         float4 v = x4[i];
@@ -155,7 +175,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
         y4[i] = v;
       }
     } else {
-      for (int i = tid; i < P.L; i += blockDim.x) yc[i] = finish_sample(xc[i], scale, scaled, P.quantize);
+      for (int i = tid; i < P.L; i += blockDim.x) yc[i] = finish_sample(xc(i), scale, scaled, P.quantize);
     }
   }
 
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
         if (src < 0) src = -src;
         if (src >= P.L) src = 2 * (P.L - 1) - src;
         float v = 0.f;
-        if (p < P.L + P.n_fft) v = finish_sample(xc[src], scale, scaled, P.quantize) * pow2;
+        if (p < P.L + P.n_fft) v = finish_sample(xc(src), scale, scaled, P.quantize) * pow2;
         const __half h = __float2half_rn(v);
         hi[q] = h;
         lo[q] = __float2half_rn(v - __half2float(h));
@@ -188,11 +208,12 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
   }
 }
 
-int launch_prep(avld_ctx* c, const float* x, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
+int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
   PrepParams P{};
   P.x = x;
+  P.x16 = x16;
   P.y = y_out;
   P.a_hi = write_operand ? c->d_Ahi : nullptr;
   P.a_lo = write_operand ? c->d_Alo : nullptr;
@@ -239,7 +260,7 @@ extern "C" int avld_rms_normalize(avld_ctx* c, const float* x, float* y, uint8_t
   const int64_t step = 1 << 20;   // grid size limit is far above this; chunk the launch only for int safety
   for (int64_t i = 0; i < n; i += step) {
     const int m = static_cast<int>(n - i < step ? n - i : step);
-    AVLD_TRY(launch_prep(c, x + i * c->L, y + i * c->L, false, true, ok ? ok + i : nullptr, rms ? rms + i : nullptr, m,
+    AVLD_TRY(launch_prep(c, x + i * c->L, nullptr, y + i * c->L, false, true, ok ? ok + i : nullptr, rms ? rms + i : nullptr, m,
                          target_rms, rms_min, eps, quantize_pcm16, st));
   }
   return AVLD_OK;

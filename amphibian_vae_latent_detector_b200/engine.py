@@ -233,11 +233,14 @@ class Engine:
     def encode_detect_host(self, x_host, centroid: np.ndarray, thr: np.ndarray, priority_rank: np.ndarray, *,
                            pcm16: bool = True, want_mu: bool = False):
         """HOST buffers in / out (the call the drop-in layer makes per batch of decoded files):
-        ``x_host [n, L]`` float32 (numpy or CPU tensor, pinned for full copy/compute overlap) ->
+        ``x_host [n, L]`` float32, or int16 PCM_16 samples as stored in the WAV files (half the PCIe bytes;
+        decoded on the GPU as s / 32768), numpy or CPU tensor, pinned for full copy/compute overlap ->
         ``(pred [n] int32, best_d [n] f32, ok [n] uint8, mu [n, D] f32 | None)`` as numpy arrays."""
-        xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host, np.float32))
-        if xt.device.type != "cpu" or xt.dtype != torch.float32 or xt.ndim != 2 or xt.shape[1] != self.chunk_len:
-            raise ValueError(f"x_host must be a CPU float32 [n, {self.chunk_len}] array")
+        xt = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_host))
+        if xt.device.type != "cpu" or xt.dtype not in (torch.float32, torch.int16) or xt.ndim != 2 \
+                or xt.shape[1] != self.chunk_len:
+            raise ValueError(f"x_host must be a CPU float32 or int16 (PCM_16) [n, {self.chunk_len}] array")
+        fn = self.lib.avld_encode_detect_host if xt.dtype == torch.float32 else self.lib.avld_encode_detect_host_pcm16
         xt = xt.contiguous()
         n = xt.shape[0]
         centroid = np.ascontiguousarray(centroid, dtype=np.float32)
@@ -248,7 +251,7 @@ class Engine:
         best = np.empty(n, dtype=np.float32)
         ok = np.empty(n, dtype=np.uint8)
         mu = np.empty((n, self.latent_dim), dtype=np.float32) if want_mu else None
-        _lib.check(self.lib.avld_encode_detect_host(
+        _lib.check(fn(
             self._h, xt.data_ptr(), n, int(pcm16), centroid.ctypes.data, thr.ctypes.data, priority_rank.ctypes.data, K,
             pred.ctypes.data, best.ctypes.data, None if mu is None else mu.ctypes.data, ok.ctypes.data))
         return pred, best, ok, mu

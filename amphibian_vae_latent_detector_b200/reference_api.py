@@ -1,0 +1,463 @@
+"""The reference's own function surface for the hot path -- same names, arguments, return types and
+error behaviour -- executed by the CUDA library.  Paths relative to
+``latent_space_exploration/`` in the reference:
+
+    rms_normalize, process_folder                       00_normalize_dataset_rms.py:29-57
+    crop_or_pad_time, wav_to_mel, encode_wav_to_latent  map_detector_core.py:185-300 (= 07/08/09 copies)
+    load_encoder (+ helpers)                            map_detector_core.py:104-179
+    l2_norm_rows, quantile_safe, summarize_dist,
+    fit_species_with_fp_control                         08_fit_radial_detector.py:105-123, :310-333
+    get_detector_from_config, l2, detect_species,
+    PRIORITY_ORDER                                      09_evaluate_wav_detection.py:61-66, :113-149, :354-436
+    DetectorSession                                     10_benchmark_folder_detection.py:113-199
+
+plus batched additions (``*_batch`` / ``predict_many``) that feed many files per GPU pass.  File I/O is
+PCM WAV via the standard library (the reference's librosa.load / soundfile.write on 16-bit mono/stereo
+files); resampling is not implemented (the reference's datasets are already 48 kHz) and raises.
+Everything numeric runs on the GPU: ``device`` arguments are accepted for signature compatibility, and
+"cpu" is mapped to ``cuda:0`` -- there is no CPU implementation to fall back to.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import sys
+import wave
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .engine import Engine, priority_ranks
+
+PRIORITY_ORDER = [
+    "Batrachyla_leptopus",
+    "Batrachyla_taeniata",
+    "Calyptocephalella_gayi",
+    "Pleurodema_thaul",
+]
+
+_ENGINES: Dict[tuple, Engine] = {}
+_LOADED: Dict[tuple, int] = {}
+
+
+def _cuda_index(device) -> int:
+    dev = torch.device(device) if not isinstance(device, torch.device) else device
+    return (dev.index or 0) if dev.type == "cuda" else 0
+
+
+def _engine(chunk_len: int, device=0, *, sr=48000, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048,
+            target_frames=192, max_batch: int = 64) -> Engine:
+    key = (_cuda_index(device), int(chunk_len), sr, n_mels, float(fmin), float(fmax), hop_length, n_fft, target_frames)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=max_batch, sr=sr, n_fft=n_fft, hop_length=hop_length,
+                     n_mels=n_mels, fmin=fmin, fmax=fmax, target_frames=target_frames)
+        _ENGINES[key] = eng
+    return eng
+
+
+def _engine_with_encoder(encoder, chunk_len, device, **mel_kw) -> Engine:
+    """One engine per (geometry, encoder object); the layer program is exported and uploaded once."""
+    key = (_cuda_index(device), int(chunk_len), tuple(sorted(mel_kw.items())), id(encoder))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=64, **mel_kw)
+        eng.load_encoder(encoder)
+        _ENGINES[key] = eng
+    return eng
+
+
+# ----------------------------------------------------------------------------------------------------------
+# WAV I/O (librosa.load(sr=sr, mono=True) on PCM files; soundfile.write(float data) = PCM_16)
+# ----------------------------------------------------------------------------------------------------------
+def load_wav(path, sr: int = 48000) -> np.ndarray:
+    with wave.open(str(path), "rb") as w:
+        nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+        raw = w.readframes(n)
+    if rate != sr:
+        raise RuntimeError(f"{path}: sample rate {rate} != {sr}; resampling is not implemented on this path")
+    if width == 2:
+        x = np.frombuffer(raw, dtype="<i2").astype(np.float32) * np.float32(1.0 / 32768.0)
+    elif width == 4:
+        x = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    else:
+        raise RuntimeError(f"{path}: unsupported sample width {width}")
+    if nch > 1:
+        x = x.reshape(-1, nch).mean(axis=1).astype(np.float32)     # librosa to_mono
+    return np.ascontiguousarray(x)
+
+
+def write_wav_pcm16(path, y: np.ndarray, sr: int) -> None:
+    """``sf.write(path, y, sr)`` for float data on a .wav path: PCM_16, ``lrintf(x * 0x7FFF)``."""
+    pcm = np.clip(np.rint(np.asarray(y, dtype=np.float32) * np.float32(32767.0)), -32768, 32767).astype("<i2")
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(int(sr))
+        w.writeframes(pcm.tobytes())
+
+
+def _fix_length(y: np.ndarray, sr: int, duration: float) -> np.ndarray:
+    if duration > 0:                                               # core:212-217
+        target_len = int(sr * duration)
+        if y.shape[0] < target_len:
+            y = np.pad(y, (0, target_len - y.shape[0]), mode="constant")
+        else:
+            y = y[:target_len]
+    return y
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 00_normalize_dataset_rms.py
+# ----------------------------------------------------------------------------------------------------------
+def rms_normalize(y, target_rms=0.05, rms_min=1e-4, eps=1e-8):
+    """00:29-38.  -> ``(y_norm float32 ndarray, ok bool)``; silent input is returned unchanged."""
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    if y.ndim != 1 or y.size == 0:
+        raise ValueError("rms_normalize expects a non-empty 1-D signal")
+    eng = _engine(y.shape[0], 0, max_batch=8)
+    out, ok, _ = eng.rms_normalize(torch.from_numpy(y[None]).to(eng.device), target_rms, rms_min, eps)
+    return out[0].cpu().numpy(), bool(ok[0].item())
+
+
+def rms_normalize_batch(x: np.ndarray, target_rms=0.05, rms_min=1e-4, eps=1e-8):
+    """rows of ``x [n, L]`` -> ``(y [n, L], ok [n] bool)``."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    eng = _engine(x.shape[1], 0, max_batch=64)
+    out, ok, _ = eng.rms_normalize(torch.from_numpy(x).to(eng.device), target_rms, rms_min, eps)
+    return out.cpu().numpy(), ok.cpu().numpy().astype(bool)
+
+
+def process_folder(src_root: Path, dst_root: Path, sr=48000):
+    """00:41-57: every ``<species>/*.wav`` -> normalised PCM_16 WAV under ``dst_root`` (written even when
+    the file is silent).  Files of equal length are normalised in one GPU batch."""
+    src_root, dst_root = Path(src_root), Path(dst_root)
+    for species_dir in sorted(src_root.iterdir()):
+        if not species_dir.is_dir():
+            continue
+        out_dir = dst_root / species_dir.name
+        out_dir.mkdir(parents=True, exist_ok=True)
+        by_len: Dict[int, List[Tuple[Path, np.ndarray]]] = {}
+        for wav in sorted(species_dir.glob("*.wav")):
+            y = load_wav(wav, sr)
+            by_len.setdefault(y.shape[0], []).append((wav, y))
+        for length, items in by_len.items():
+            ys, _ = rms_normalize_batch(np.stack([y for _, y in items]))
+            for (wav, _), yn in zip(items, ys):
+                write_wav_pcm16(out_dir / wav.name, yn, sr)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# map_detector_core.py: features and encoding
+# ----------------------------------------------------------------------------------------------------------
+def crop_or_pad_time(mel: np.ndarray, target_frames: int) -> np.ndarray:
+    """core:185-195 (host-side helper kept for API compatibility; the GPU path crops inside the kernel)."""
+    _, T = mel.shape
+    if T == target_frames:
+        return mel
+    if T > target_frames:
+        start = (T - target_frames) // 2
+        return mel[:, start:start + target_frames]
+    pad_total = target_frames - T
+    pad_left = pad_total // 2
+    return np.pad(mel, ((0, 0), (pad_left, pad_total - pad_left)), mode="constant")
+
+
+def wav_to_mel(wav_path: Path, *, sr: int = 48000, duration: float = 5.0, n_mels: int = 64, fmin: float = 150.0,
+               fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048, target_frames: int = 192) -> torch.Tensor:
+    """core:198-237 -> ``torch.float32 [n_mels, target_frames]`` (on the CPU, like the reference)."""
+    y = _fix_length(load_wav(wav_path, sr), sr, duration)
+    eng = _engine(y.shape[0], 0, sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length, n_fft=n_fft,
+                  target_frames=target_frames)
+    feat = eng.logmel(torch.from_numpy(y[None]).to(eng.device))[0]              # [T, M]
+    return feat.T.contiguous().cpu()
+
+
+def encode_wavs_to_latents(encoder: torch.nn.Module, wav_paths: Sequence[Path], device=None, *, sr: int = 48000,
+                           duration: float = 5.0, n_mels: int = 64, fmin: float = 150.0, fmax: float = 15000.0,
+                           hop_length: int = 384, n_fft: int = 2048, target_frames: int = 192,
+                           return_failed: bool = False):
+    """Batched ``encode_wav_to_latent``: many files per GPU pass.  Unreadable files are skipped and counted
+    (the reference's per-file try/except, 08:489-506)."""
+    mel_kw = dict(sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length, n_fft=n_fft,
+                  target_frames=target_frames)
+    chunk_len = int(sr * duration)
+    eng = _engine_with_encoder(encoder, chunk_len, device if device is not None else 0, **mel_kw)
+    rows, failed = [], []
+    for p in wav_paths:
+        try:
+            rows.append(_fix_length(load_wav(p, sr), sr, duration))
+        except Exception:
+            failed.append(p)
+    if not rows:
+        Z = np.zeros((0, eng.latent_dim), dtype=np.float32)
+    else:
+        x = torch.from_numpy(np.stack(rows)).to(eng.device)
+        feat = eng.logmel(x)                       # files on disk are already normalised (00) -> no RMS stage here
+        Z = eng.encoder_forward(feat).cpu().numpy()
+    return (Z, failed) if return_failed else Z
+
+
+@torch.no_grad()
+def encode_wav_to_latent(encoder: torch.nn.Module, wav_path: Path, device=None, *, sr: int = 48000,
+                         duration: float = 5.0, n_mels: int = 64, fmin: float = 150.0, fmax: float = 15000.0,
+                         hop_length: int = 384, n_fft: int = 2048, target_frames: int = 192) -> np.ndarray:
+    """core:241-300 -> ``np.float32 [D]``."""
+    Z = encode_wavs_to_latents(encoder, [wav_path], device, sr=sr, duration=duration, n_mels=n_mels, fmin=fmin,
+                               fmax=fmax, hop_length=hop_length, n_fft=n_fft, target_frames=target_frames,
+                               return_failed=True)
+    if Z[1]:
+        load_wav(wav_path, sr)                     # re-raise the file's own error, as the reference would
+    return Z[0][0].astype(np.float32)
+
+
+# ---- encoder loading: host-only logic, restated from core:104-179 -------------------------------------------
+def load_yaml_cfg(cfg_path: Path) -> Dict[str, Any]:
+    import yaml
+    with open(cfg_path, "r", encoding="utf-8") as f:
+        cfg = yaml.safe_load(f)                    # == OmegaConf.to_container(resolve=False) for plain YAML
+    if not isinstance(cfg, dict):
+        raise ValueError("YAML no es dict tras to_container.")
+    return cfg
+
+
+def pick_encoder_cfg(cfg: Dict[str, Any]) -> Dict[str, Any]:
+    enc = cfg.get("encoder")
+    if not isinstance(enc, dict) or "_target_" not in enc:
+        raise KeyError("No pude encontrar cfg['encoder'] con _target_ en el YAML.")
+    return enc
+
+
+def split_model_and_state(ckpt: Any):
+    if isinstance(ckpt, torch.nn.Module):
+        return ckpt, None
+    if isinstance(ckpt, dict):
+        for key in ("state_dict", "model_state_dict"):
+            if key in ckpt and isinstance(ckpt[key], dict):
+                return None, ckpt[key]
+        if ckpt and all(isinstance(v, torch.Tensor) for v in ckpt.values()):
+            return None, ckpt
+    raise RuntimeError("Checkpoint no reconocido (ni nn.Module ni state_dict).")
+
+
+def build_nn_module(obj: Any) -> torch.nn.Module:
+    if isinstance(obj, torch.nn.Module):
+        return obj
+    if callable(obj):
+        out = obj()
+        if isinstance(out, torch.nn.Module):
+            return out
+    raise RuntimeError(f"instantiate devolvió {type(obj)}; no pude obtener nn.Module.")
+
+
+def _instantiate(cfg: Dict[str, Any]):
+    cfg = dict(cfg)
+    target = cfg.pop("_target_")
+    mod_name, _, attr = target.rpartition(".")
+    return getattr(importlib.import_module(mod_name), attr)(**cfg)
+
+
+def load_encoder(encoder_pt: Path, encoder_yaml: Path, project_root: Path, device=None) -> torch.nn.Module:
+    """core:150-179.  Returns the ``nn.Module`` (eval mode, on the CPU: it is only walked by
+    ``export_program``; the forward itself runs in the CUDA library)."""
+    if str(project_root) not in sys.path:
+        sys.path.insert(0, str(project_root))
+    encoder_pt = Path(encoder_pt)
+    if not encoder_pt.exists():
+        raise FileNotFoundError(f"No existe encoder .pt: {encoder_pt}")
+    ckpt = torch.load(str(encoder_pt), map_location="cpu", weights_only=True)
+    model, state = split_model_and_state(ckpt)
+    if model is None:
+        encoder_yaml = Path(encoder_yaml)
+        if not encoder_yaml.exists():
+            raise FileNotFoundError(f"No existe YAML: {encoder_yaml}")
+        model = build_nn_module(_instantiate(pick_encoder_cfg(load_yaml_cfg(encoder_yaml))))
+        model.load_state_dict(state, strict=False)
+    return model.eval()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 08_fit_radial_detector.py
+# ----------------------------------------------------------------------------------------------------------
+def _dev_rows(x: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to("cuda:0")
+
+
+def l2_norm_rows(x: np.ndarray) -> np.ndarray:
+    """08:105-106 via the radii kernel against a zero centroid."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.shape[0] == 0:
+        return np.zeros(0, dtype=np.float32)
+    eng = _engine(144000, 0)
+    zero = torch.zeros(1, x.shape[1], dtype=torch.float32, device=eng.device)
+    return eng.radii(_dev_rows(x), zero)[:, 0].cpu().numpy()
+
+
+def _quantiles(x: np.ndarray, qs: Sequence[float]) -> List[float]:
+    from . import quantile as _q
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    eng = _engine(144000, 0)
+    r = _dev_rows(x[:, None])
+    lab = torch.zeros(x.shape[0], dtype=torch.int32, device=eng.device)
+    queries, plan = [], []
+    for q in qs:
+        prev, nxt, gamma = _q.neighbour_ranks(x.shape[0], q)
+        queries += [(0, 0, prev), (0, 0, nxt)]
+        plan.append(gamma)
+    vals = eng.order_stats(r, lab, queries)
+    return [_q.lerp(float(vals[2 * i]), float(vals[2 * i + 1]), g) for i, g in enumerate(plan)]
+
+
+def quantile_safe(x: np.ndarray, q: float) -> float:
+    """08:109-112: 0.0 on empty input, else ``float(np.quantile(x, q))`` (exact selection on the GPU)."""
+    if np.asarray(x).size == 0:
+        return 0.0
+    return _quantiles(x, [q])[0]
+
+
+def summarize_dist(x: np.ndarray) -> Dict[str, float]:
+    """08:115-123."""
+    if np.asarray(x).size == 0:
+        return {"min": float("nan"), "p50": float("nan"), "p90": float("nan"), "max": float("nan")}
+    v = _quantiles(x, [0.0, 0.5, 0.9, 1.0])
+    return {"min": v[0], "p50": v[1], "p90": v[2], "max": v[3]}
+
+
+def fit_species_with_fp_control(Z_in: np.ndarray, Z_out: Optional[np.ndarray], q_in: float, q_out: float):
+    """08:310-333 -> ``(mu float32[D], rk, rk_in, rk_out, extra)``."""
+    Z_in = np.ascontiguousarray(Z_in, dtype=np.float32)
+    has_out = Z_out is not None and np.asarray(Z_out).size > 0
+    Z = np.concatenate([Z_in, np.ascontiguousarray(Z_out, dtype=np.float32)]) if has_out else Z_in
+    lab = np.zeros(Z.shape[0], dtype=np.int32)
+    lab[Z_in.shape[0]:] = 1
+    eng = _engine(144000, 0)
+    fit = eng.fit_radial(_dev_rows(Z), torch.from_numpy(lab).to(eng.device), 2 if has_out else 1, q_in, q_out)
+    names = ("min", "p50", "p90", "max")
+    nan4 = {k: float("nan") for k in names}
+    extra = {"rho_in_summary": dict(zip(names, map(float, fit.summaries["in"][0]))),
+             "rho_out_summary": dict(zip(names, map(float, fit.summaries["out"][0]))) if has_out else nan4}
+    rk_in = float(fit.rk_in[0])
+    rk_out = float(fit.rk_out[0, 0]) if has_out else float("inf")
+    return fit.centroids[0].astype(np.float32), float(min(rk_in, rk_out)), rk_in, rk_out, extra
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 09_evaluate_wav_detection.py / 10_benchmark_folder_detection.py
+# ----------------------------------------------------------------------------------------------------------
+def load_json(path: Path) -> Dict[str, Any]:
+    path = Path(path)
+    if not path.exists():
+        raise FileNotFoundError(f"No existe: {path}")
+    with open(path, "r", encoding="utf-8") as f:
+        return json.load(f)
+
+
+def get_detector_from_config(cfg: Dict[str, Any]) -> Tuple[Dict[str, np.ndarray], Dict[str, float], float]:
+    """09:113-149."""
+    rd = cfg.get("radial_detector", None)
+    if not isinstance(rd, dict):
+        raise ValueError("config.json no contiene radial_detector (dict). Ejecuta antes 08_fit_radial_detector.py")
+    cent, thr = rd.get("centroids", None), rd.get("thresholds", None)
+    if not isinstance(cent, dict) or not isinstance(thr, dict):
+        raise ValueError("radial_detector debe contener 'centroids' y 'thresholds' como dicts.")
+    centroids = {sp: np.array(vec, dtype=np.float32) for sp, vec in cent.items()
+                 if isinstance(sp, str) and isinstance(vec, list) and len(vec) > 0}
+    thresholds = {sp: float(v) for sp, v in thr.items() if isinstance(sp, str)}
+    if not centroids or not thresholds:
+        raise ValueError("centroids/thresholds vacíos o mal formateados en config.json.")
+    try:
+        chunk_seconds = float(cfg.get("chunk_seconds", 5.0))
+    except Exception:
+        chunk_seconds = 5.0
+    return centroids, thresholds, chunk_seconds
+
+
+def l2(a: np.ndarray) -> float:
+    """09:354-355."""
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(1, -1)
+    return float(l2_norm_rows(a)[0])
+
+
+def _decide_many(Z: np.ndarray, centroids: Dict[str, np.ndarray], thresholds: Dict[str, float]):
+    """D2 for rows of ``Z``: ``-> [(detected, species | None, best_d)]`` (09:416-436, 10:175-199)."""
+    D = Z.shape[1]
+    species = [sp for sp, mu in centroids.items() if sp in thresholds and mu.shape[0] == D]
+    if not species or Z.shape[0] == 0:
+        return [(False, None, float("inf"))] * Z.shape[0]
+    eng = _engine(144000, 0)
+    cent = torch.from_numpy(np.stack([centroids[sp] for sp in species]).astype(np.float32)).to(eng.device)
+    thr = torch.tensor([thresholds[sp] for sp in species], dtype=torch.float64, device=eng.device)
+    prio = torch.from_numpy(priority_ranks(species, PRIORITY_ORDER)).to(eng.device)
+    radii = eng.radii(_dev_rows(Z), cent)
+    pred, best = eng.decide(radii, thr, prio)
+    pred, best = pred.cpu().numpy(), best.cpu().numpy()
+    return [(bool(p >= 0), species[p] if p >= 0 else None, float(b)) for p, b in zip(pred, best)]
+
+
+class DetectorSession:
+    """10:113-199: load config + encoder once, then ``predict_one`` per file (or ``predict_many``)."""
+
+    def __init__(self, module=None, project_root: Path = Path("."), config_path: Path = Path("config.json"),
+                 encoder_pt: Path = Path("model.pt"), encoder_yaml: Path = Path("model.yaml"), device: str = "cpu",
+                 sr: int = 48000, n_mels: int = 64, target_frames: int = 192, fmin: float = 150.0,
+                 fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048):
+        self.m = module
+        self.project_root, self.config_path = Path(project_root), Path(config_path)
+        self.encoder_pt, self.encoder_yaml, self.device = Path(encoder_pt), Path(encoder_yaml), device
+        self.sr, self.n_mels, self.target_frames = sr, n_mels, target_frames
+        self.fmin, self.fmax, self.hop_length, self.n_fft = fmin, fmax, hop_length, n_fft
+        self.centroids: Dict[str, np.ndarray] = {}
+        self.thresholds: Dict[str, float] = {}
+        self.duration = 5.0
+        self.encoder: Optional[torch.nn.Module] = None
+
+    def load(self) -> None:
+        cfg = load_json(self.config_path)
+        self.centroids, self.thresholds, self.duration = get_detector_from_config(cfg)
+        self.encoder = load_encoder(self.encoder_pt, self.encoder_yaml, self.project_root, self.device)
+
+    def _mel_kw(self):
+        return dict(sr=self.sr, duration=self.duration, n_mels=self.n_mels, fmin=self.fmin, fmax=self.fmax,
+                    hop_length=self.hop_length, n_fft=self.n_fft, target_frames=self.target_frames)
+
+    def predict_one(self, wav_path: Path) -> Tuple[bool, Optional[str], float]:
+        if self.encoder is None:
+            raise RuntimeError("Session no cargada. Llama load().")
+        z = encode_wav_to_latent(self.encoder, wav_path, self.device, **self._mel_kw())
+        return _decide_many(z[None], self.centroids, self.thresholds)[0]
+
+    def predict_many(self, wav_paths: Sequence[Path]) -> List[Tuple[bool, Optional[str], float]]:
+        """Batched ``predict_one``; an unreadable file yields ``(False, "ERROR", nan)`` (10:409-418)."""
+        if self.encoder is None:
+            raise RuntimeError("Session no cargada. Llama load().")
+        Z, failed = encode_wavs_to_latents(self.encoder, wav_paths, self.device, return_failed=True, **self._mel_kw())
+        good = iter(_decide_many(Z, self.centroids, self.thresholds))
+        bad = set(map(str, failed))
+        return [(False, "ERROR", float("nan")) if str(p) in bad else next(good) for p in wav_paths]
+
+
+def detect_species(wav_path, *, config_path=None, encoder_pt=None, encoder_yaml=None, device: str = "cpu",
+                   sr: int = 48000, n_mels: int = 64, target_frames: int = 192, fmin: float = 150.0,
+                   fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048,
+                   encoder: Optional[torch.nn.Module] = None) -> Tuple[bool, Optional[str]]:
+    """09:358-436 -> ``(True, species)`` / ``(False, None)``.  ``config_path`` / ``encoder_pt`` / ``encoder_yaml``
+    default to ``<cwd>/config.json``, ``downloaded_models/model.pt`` and ``downloaded_models/model.yaml``.
+    ``encoder=`` (addition) passes an already loaded module, avoiding the checkpoint reload per call (09:400)."""
+    wav_p = Path(wav_path).expanduser()
+    if not wav_p.is_absolute():
+        wav_p = (Path.cwd() / wav_p).resolve()
+    if not wav_p.exists():
+        raise FileNotFoundError(f"No existe WAV: {wav_p}")
+    root = Path.cwd()
+    cfg = load_json(Path(config_path).expanduser().resolve() if config_path else root / "config.json")
+    centroids, thresholds, duration = get_detector_from_config(cfg)
+    if encoder is None:
+        encoder = load_encoder(Path(encoder_pt) if encoder_pt else root / "downloaded_models" / "model.pt",
+                               Path(encoder_yaml) if encoder_yaml else root / "downloaded_models" / "model.yaml",
+                               root, device)
+    z = encode_wav_to_latent(encoder, wav_p, device, sr=sr, duration=duration, n_mels=n_mels, fmin=fmin, fmax=fmax,
+                             hop_length=hop_length, n_fft=n_fft, target_frames=target_frames)
+    det, sp, _ = _decide_many(z[None], centroids, thresholds)[0]
+    return det, sp

@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chunks", type=int, default=100000, help="resident chunks per GPU (one step processes all)")
-    ap.add_argument("--e2e-chunks", type=int, default=8192, help="host-resident chunks per e2e step")
+    ap.add_argument("--e2e-chunks", type=int, default=16384, help="host-resident chunks per e2e step")
     ap.add_argument("--max-batch", type=int, default=1024, help="chunks per internal kernel pass")
     ap.add_argument("--cpu-chunks", type=int, default=192, help="chunks of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -285,30 +285,49 @@ def main():
     stages = eng.collect(reset=True)
     launches = sum(v["launches"] for v in stages.values())
 
-    # ---------------- e2e through the host-buffer C-ABI call
+    # ---------------- e2e through the host-buffer C-ABI calls (pinned host audio in, decisions out)
     e2e = None
+    e2e_f32 = None
     if not args.no_e2e:
         ne = min(args.e2e_chunks, n)
         fit = state["fit"]
-        xh = torch.empty(ne, CHUNK_LEN, dtype=torch.float32, pin_memory=True)
-        xh.copy_(X[:ne])
-        torch.cuda.synchronize()
         cent, thr = np.nan_to_num(fit.centroids), fit.rk[0]
-        for _ in range(2):
-            eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pred_h, best_h, ok_h, _ = eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
+
+        def run_e2e(xh, bytes_per_sample, api):
+            for _ in range(2):
+                eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pred_h, best_h, ok_h, _ = eng.encode_detect_host(xh, cent, thr, prio, pcm16=True)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=group)
+            sec = float(dt.item())
+            h2d = int(ne) * CHUNK_LEN * bytes_per_sample
+            return {"value": world * ne * args.steps / sec, "unit": "chunks/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(ne) * (4 + 4 + 1), "chunks_per_step": int(ne),
+                    "h2d_gbs_per_gpu": h2d * args.steps / sec / 1e9, "api": api}
+
+        # (a) PCM_16 samples, the format of the reference's WAV datasets (00:57 writes PCM_16, core:210 reads it)
+        xh16 = torch.empty(ne, CHUNK_LEN, dtype=torch.int16, pin_memory=True)
+        for i in range(0, ne, 2048):
+            m = min(2048, ne - i)
+            xh16[i:i + m].copy_(torch.clamp(torch.round(X[i:i + m] * 32767.0), -32768, 32767).to(torch.int16))
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=group)
-        e2e = {"value": world * ne * args.steps / float(dt.item()), "unit": "chunks/s",
-               "h2d_bytes_per_step": int(ne) * CHUNK_LEN * 4, "d2h_bytes_per_step": int(ne) * (4 + 4 + 1),
-               "chunks_per_step": int(ne), "api": "avld_encode_detect_host (pinned host float32 audio -> decisions)"}
-        eng.collect(reset=True)
+        e2e = run_e2e(xh16, 2, "avld_encode_detect_host_pcm16 (pinned host PCM_16 audio -> decisions)")
+        del xh16
+        # (b) float32 samples (twice the PCIe bytes)
+        nf = min(ne, 8192)
+        xh = torch.empty(nf, CHUNK_LEN, dtype=torch.float32, pin_memory=True)
+        xh.copy_(X[:nf])
+        torch.cuda.synchronize()
+        ne_save, ne = ne, nf
+        e2e_f32 = run_e2e(xh, 4, "avld_encode_detect_host (pinned host float32 audio -> decisions)")
+        ne = ne_save
         del xh
+        eng.collect(reset=True)
 
     if rank == 0:
         peaks = measured_peaks()
@@ -342,6 +361,7 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+            line["e2e_f32_host"] = e2e_f32
         if world == 1 and not args.no_cpu_baseline:
             nc = args.cpu_chunks
             xc, lc = synth.make_chunks(nc, CHUNK_LEN, seed=123, first_index=0)

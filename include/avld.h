@@ -159,6 +159,14 @@ int avld_encode_detect_host(avld_ctx* ctx, const float* x_host, int64_t n, int q
                             int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
                             uint8_t* ok_host);
 
+/* Same, with the audio as PCM_16 samples (what the reference's WAV files hold; librosa.load decodes them as
+ * s / 32768, 00:51 / core:210): pcm_host int16 [n, chunk_len].  Halves the bytes crossing PCIe; the decode is
+ * fused into the normalisation kernel and is exact. */
+int avld_encode_detect_host_pcm16(avld_ctx* ctx, const int16_t* pcm_host, int64_t n, int quantize_pcm16,
+                                  const float* centroid, const double* thr, const int32_t* priority_rank,
+                                  int32_t K, int32_t* pred_host, float* best_host, float* mu_host,
+                                  uint8_t* ok_host);
+
 /* ---- host-side helpers (no device work; used by tests and by the Python layer) -----------------*/
 /* numpy's float32 pairwise-summation plan for a length-n reduction: writes up to cap leaves
  * (offset, length) in in-order traversal; returns the number of leaves (or a negative error). */

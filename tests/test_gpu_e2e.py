@@ -42,3 +42,18 @@ def test_encode_fit_detect_vs_oracle(engine3s, standin_encoder):
     assert near.sum() < n // 4
     assert np.allclose(best, best_o, rtol=1e-3)
     assert len(set(pred_o.tolist())) >= 3          # detections of several species and NO_DETECT all occur
+
+
+def test_pcm16_host_input_equals_float_input(engine3s):
+    """int16 PCM in (decoded on the GPU as s/32768, librosa.load semantics) == the same samples passed as float32."""
+    x, label = synth.make_chunks(70, 144000, seed=5, special_every=9)
+    pcm = torch.clamp(torch.round(x * 20000.0), -32768, 32767).to(torch.int16)
+    xf = pcm.to(torch.float32) * (1.0 / 32768.0)
+    rng = np.random.default_rng(0)
+    cent = rng.standard_normal((4, 128)).astype(np.float32)
+    thr = np.array([30.0, 40.0, 50.0, 60.0])
+    prio = priority_ranks(SPECIES, hp.PRIORITY_ORDER)
+    a = engine3s.encode_detect_host(pcm.pin_memory(), cent, thr, prio, pcm16=True, want_mu=True)
+    b = engine3s.encode_detect_host(xf.pin_memory(), cent, thr, prio, pcm16=True, want_mu=True)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
