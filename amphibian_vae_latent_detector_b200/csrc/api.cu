@@ -49,6 +49,22 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_prio), 64 * sizeof(int32_t)));
   }
   AVLD_CHECK(static_cast<size_t>(K) * D <= 64 * 4096, AVLD_ERR_UNSUPPORTED, "K*D too large");
+  // pinned staging: pred | best | mu | ok
+  const size_t n_sz = static_cast<size_t>(n);
+  const size_t off_best = n_sz * 4, off_mu = off_best + n_sz * 4, off_ok = off_mu + (mu_host ? n_sz * D * 4 : 0);
+  const size_t need = off_ok + n_sz + 64;
+  if (need > c->h_stage_bytes) {
+    if (c->h_stage) AVLD_CUDA(cudaFreeHost(c->h_stage));
+    c->h_stage = nullptr;
+    c->h_stage_bytes = 0;
+    AVLD_CUDA(cudaHostAlloc(&c->h_stage, need, cudaHostAllocDefault));
+    c->h_stage_bytes = need;
+  }
+  char* hs = static_cast<char*>(c->h_stage);
+  int32_t* s_pred = reinterpret_cast<int32_t*>(hs);
+  float* s_best = reinterpret_cast<float*>(hs + off_best);
+  float* s_mu = reinterpret_cast<float*>(hs + off_mu);
+  uint8_t* s_ok = reinterpret_cast<uint8_t*>(hs + off_ok);
   cudaStream_t sc = c->s_compute, sx = c->s_copy;
   AVLD_CUDA(cudaMemcpyAsync(c->d_cent, centroid, static_cast<size_t>(K) * D * sizeof(float), cudaMemcpyHostToDevice, sc));
   AVLD_CUDA(cudaMemcpyAsync(c->d_thr, thr, K * sizeof(double), cudaMemcpyHostToDevice, sc));
@@ -71,15 +87,19 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     AVLD_CUDA(cudaEventRecord(c->ev_done[b], sc));                         // x buffer consumed by the prep kernel
     AVLD_TRY(avld_radii(c, c->d_mu, c->d_cent, c->d_radii, m, K, D, sc));
     AVLD_TRY(avld_decide(c, c->d_radii, c->d_thr, c->d_prio, c->d_pred, c->d_best, m, K, sc));
-    AVLD_CUDA(cudaMemcpyAsync(pred_host + i, c->d_pred, static_cast<size_t>(m) * sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
-    AVLD_CUDA(cudaMemcpyAsync(best_host + i, c->d_best, static_cast<size_t>(m) * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    AVLD_CUDA(cudaMemcpyAsync(s_pred + i, c->d_pred, static_cast<size_t>(m) * sizeof(int32_t), cudaMemcpyDeviceToHost, sc));
+    AVLD_CUDA(cudaMemcpyAsync(s_best + i, c->d_best, static_cast<size_t>(m) * sizeof(float), cudaMemcpyDeviceToHost, sc));
     if (mu_host)
-      AVLD_CUDA(cudaMemcpyAsync(mu_host + i * D, c->d_mu, static_cast<size_t>(m) * D * sizeof(float), cudaMemcpyDeviceToHost, sc));
+      AVLD_CUDA(cudaMemcpyAsync(s_mu + i * D, c->d_mu, static_cast<size_t>(m) * D * sizeof(float), cudaMemcpyDeviceToHost, sc));
     if (ok_host)
-      AVLD_CUDA(cudaMemcpyAsync(ok_host + i, c->d_ok, static_cast<size_t>(m), cudaMemcpyDeviceToHost, sc));
+      AVLD_CUDA(cudaMemcpyAsync(s_ok + i, c->d_ok, static_cast<size_t>(m), cudaMemcpyDeviceToHost, sc));
   }
   AVLD_CUDA(cudaStreamSynchronize(sc));
   AVLD_CUDA(cudaStreamSynchronize(sx));
+  memcpy(pred_host, s_pred, n_sz * sizeof(int32_t));
+  memcpy(best_host, s_best, n_sz * sizeof(float));
+  if (mu_host) memcpy(mu_host, s_mu, n_sz * D * sizeof(float));
+  if (ok_host) memcpy(ok_host, s_ok, n_sz);
   return AVLD_OK;
 }
 

@@ -127,6 +127,8 @@ struct avld_ctx {
   int32_t* d_prio = nullptr;
   int32_t* d_pred = nullptr;
   float* d_best = nullptr;
+  void* h_stage = nullptr;         // pinned staging for results (a D2H into pageable memory would block the host
+  size_t h_stage_bytes = 0;        // thread until the slab's kernels finish and serialise copy against compute)
 
   // order-statistics scratch
   unsigned int* d_hist = nullptr;

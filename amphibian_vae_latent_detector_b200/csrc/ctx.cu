@@ -443,6 +443,7 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
     if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
   }
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (auto& t : c->timed) {
     cudaEventDestroy(t.start);
     cudaEventDestroy(t.stop);

@@ -1,0 +1,97 @@
+"""GPU: the reference-named Python surface (reference_api.py) on files and arrays, against the fixtures the
+reference's own functions produced (tests/golden) and the oracle."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_pcm_case
+from oracle import hotpath as hp
+from oracle import librosa_port as lp
+
+pytestmark = pytest.mark.gpu
+MEL_KW = dict(sr=48000, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048, target_frames=192)
+SPECIES = ["Batrachyla_leptopus", "Batrachyla_taeniata", "Calyptocephalella_gayi", "Pleurodema_thaul"]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_rms_normalize_all_golden_lengths(golden_meta):
+    """every reference-made RMS case incl. L = 7, 100, 1000, 4097 (n < 8 loop, tail loop, odd splits of the pairwise tree)."""
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    for key, info in golden_meta["rms_cases"].items():
+        x, _ = load_pcm_case(GOLDEN / f"rms_{key}.npz")
+        y, ok = api.rms_normalize(x)
+        assert ok == info["ok"], key
+        assert y.dtype == np.float32 and sha(y) == info["sha"], key
+
+
+def test_process_folder_and_wav_to_mel_and_session(tmp_path, standin_encoder, golden_meta):
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    keys = ["noise_3s", "tonal_3s", "pulsed_3s", "burst0_3s", "silent_3s"]
+    src = tmp_path / "train_chunks" / "Pleurodema_thaul"
+    src.mkdir(parents=True)
+    for k in keys:
+        x, _ = load_pcm_case(GOLDEN / f"feat_{k}.npz")
+        pcm = np.load(GOLDEN / f"feat_{k}.npz")
+        # raw chunk files: the fixture inputs are exactly int16/32768 * gain; write those with gain 1 as PCM_16
+        if float(pcm["gain"]) != 1.0:
+            continue
+        lp.write_wav(src / f"{k}.wav", pcm["pcm"], 48000)
+    api.process_folder(tmp_path / "train_chunks", tmp_path / "train_chunks_norm", sr=48000)         # 00:41-57
+    out = tmp_path / "train_chunks_norm" / "Pleurodema_thaul"
+    done = sorted(p.stem for p in out.glob("*.wav"))
+    assert len(done) >= 4
+    for k in done:
+        d = np.load(GOLDEN / f"feat_{k}.npz")
+        mel = api.wav_to_mel(out / f"{k}.wav", duration=3.0, **MEL_KW)                              # core:198-237
+        assert isinstance(mel, torch.Tensor) and mel.shape == (64, 192) and mel.dtype == torch.float32
+        assert float(np.max(np.abs(mel.numpy() - d["feat"])) / np.max(np.abs(d["feat"]))) < 2e-4, k
+        z = api.encode_wav_to_latent(standin_encoder, out / f"{k}.wav", "cuda", duration=3.0, **MEL_KW)
+        assert z.shape == (128,) and z.dtype == np.float32
+        assert float(np.max(np.abs(z - d["z"])) / np.max(np.abs(d["z"]))) < 1e-3, k
+
+    # DetectorSession (10:113-199) with the decision fixture
+    dec = np.load(GOLDEN / "decision.npz")
+    cfg = {"species": SPECIES, "chunk_seconds": 3.0,
+           "radial_detector": {"centroids": {sp: dec["centroids"][i].tolist() for i, sp in enumerate(SPECIES)},
+                               "thresholds": {sp: float(dec["thresholds"][i]) for i, sp in enumerate(SPECIES)}}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    sess = api.DetectorSession(None, tmp_path, tmp_path / "config.json", tmp_path / "x.pt", tmp_path / "x.yaml", "cuda")
+    sess.centroids, sess.thresholds, sess.duration = api.get_detector_from_config(cfg)
+    sess.encoder = standin_encoder
+    wavs = [out / f"{k}.wav" for k in done] + [tmp_path / "missing.wav"]
+    many = sess.predict_many(wavs)
+    assert many[-1][1] == "ERROR"
+    for k, (det, sp, best) in zip(done, many):
+        g = golden_meta["decision"][k]
+        assert (det, sp) == (g["detected"], g["species"]), k
+        assert best == pytest.approx(g["best_d"], rel=1e-3)
+        assert sess.predict_one(out / f"{k}.wav")[:2] == (det, sp)
+
+
+def test_fit_species_and_helpers_vs_oracle():
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    rng = np.random.default_rng(31)
+    cents = 3.0 * rng.standard_normal((4, 128))
+    labels = np.arange(400) % 4
+    Z = (cents[labels] + rng.standard_normal((400, 128))).astype(np.float32)
+    mu, rk, rk_in, rk_out, extra = api.fit_species_with_fp_control(Z[labels == 1], Z[labels != 1], 0.95, 0.10)
+    mo, ro, rio, roo, eo = hp.fit_species_with_fp_control(Z[labels == 1], Z[labels != 1], 0.95, 0.10)
+    assert np.allclose(mu, mo, rtol=1e-5, atol=1e-6) and mu.dtype == np.float32
+    assert (rk, rk_in, rk_out) == pytest.approx((ro, rio, roo), rel=1e-5)
+    for part in ("rho_in_summary", "rho_out_summary"):
+        for k in ("min", "p50", "p90", "max"):
+            assert extra[part][k] == pytest.approx(eo[part][k], rel=1e-5)
+    _, rk2, _, rk_out2, _ = api.fit_species_with_fp_control(Z[labels == 1], None, 0.95, 0.10)
+    assert rk_out2 == float("inf") and rk2 == pytest.approx(rio, rel=1e-5)
+    rho = hp.l2_norm_rows(Z)
+    assert np.allclose(api.l2_norm_rows(Z), rho, rtol=1e-6)
+    assert api.quantile_safe(rho, 0.95) == hp.quantile_safe(rho, 0.95)        # exact selection + numpy's lerp
+    assert api.quantile_safe(np.array([], dtype=np.float32), 0.5) == 0.0
+    assert api.summarize_dist(rho) == hp.summarize_dist(rho)
+    assert api.l2(Z[0]) == pytest.approx(hp.l2(Z[0]), rel=1e-6)
