@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...);
 // kernel families, for the launch counter and the optional per-stage CUDA-event timing
 enum Stage {
   ST_PREP = 0, ST_STFT_MEL, ST_LOGMEL_POST, ST_CONV_DIRECT, ST_CONV_GEMM, ST_DENSE_GEMM, ST_RADII, ST_DECIDE,
-  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_COUNT
+  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_FOLD, ST_COUNT
 };
 
 #define AVLD_CUDA(expr)                                                                       \
@@ -97,6 +97,20 @@ struct avld_ctx {
   int dft_scale_log2 = 10;
   CUtensorMap tm_B_hi, tm_B_lo;
 
+  // folded STFT (default): the Hann window is symmetric (w[k] = w[N-k], w[0] = 0), so
+  //   Re X[b] =  sum_{k=1..N/2} (x[k] + x[N-k]) w[k] cos(2 pi k b / N)      (k = N/2: x[N/2] alone)
+  //   Im X[b] = -sum_{k=1..N/2-1} (x[k] - x[N-k]) w[k] sin(2 pi k b / N)
+  // i.e. two GEMMs with K = N/2 instead of one with K = N: half the tensor-core work.  The folded frames
+  // E | O are materialised per pass by fold_kernel as fp16 hi/lo rows [frame][N/2 + N/2].
+  int dft_fold = 1;
+  int n_tiles2 = 0, last_tile_bins = 0;   // 256-bin N tiles; the last one may hold only 128
+  float* d_xs = nullptr;           // [max_batch][R * hop] normalised, quantised, reflect-padded, pow2-scaled audio (fp32)
+  __half* d_A2hi = nullptr;        // [max_batch * F + 128][n_fft] folded frames, E in columns [0, N/2), O in [N/2, N)
+  __half* d_A2lo = nullptr;
+  __half* d_B2hi = nullptr;        // [n_tiles2 * 512][N/2]: per tile 256 cos rows then 256 (-sin) rows
+  __half* d_B2lo = nullptr;
+  CUtensorMap tm_A2_hi, tm_A2_lo, tm_B2_hi, tm_B2_lo;
+
   // per-pass scratch (max_batch chunks)
   int max_batch = 0;
   __half* d_Ahi = nullptr;         // padded, pow2-scaled audio rows [max_batch * R + 128][hop]
@@ -170,6 +184,7 @@ struct LaunchScope {
 int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
+int launch_fold(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);

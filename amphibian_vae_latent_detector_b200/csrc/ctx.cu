@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -316,7 +317,13 @@ static int build_ctx(avld_ctx* c) {
   AVLD_TRY(mel_taps_host(p, first, w0, w1, &bin_lo, &bin_hi));
   c->bin_lo = bin_lo;
   const int nbins = bin_hi - bin_lo + 1;
-  c->nbins_pad = (nbins + 127) / 128 * 128;
+  {
+    const char* mode = getenv("AVLD_DFT_MODE");          // "direct" selects the un-folded K = n_fft GEMM (A/B comparisons)
+    c->dft_fold = !(mode != nullptr && strcmp(mode, "direct") == 0) && (p.n_fft % 128 == 0);
+  }
+  c->n_tiles2 = (nbins + 255) / 256;
+  c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;
+  c->nbins_pad = c->dft_fold ? c->n_tiles2 * 256 : (nbins + 127) / 128 * 128;
   c->n_tiles_n = c->nbins_pad / 128;
   c->ncols = 2 * c->nbins_pad;
   AVLD_CHECK(static_cast<size_t>(c->nbins_pad) * sizeof(MelTap) <= 14000, AVLD_ERR_UNSUPPORTED, "too many FFT bins");
@@ -335,7 +342,43 @@ static int build_ctx(avld_ctx* c) {
   AVLD_CUDA(cudaMemcpy(c->d_taps, taps.data(), taps.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
 
   // ---- windowed DFT matrix B[col][k]; N tile t holds Re of bins [128t, 128t+128) then Im of the same bins
-  {
+  if (c->dft_fold) {
+    const int nf = p.n_fft, half = nf / 2;
+    const double bscale = std::ldexp(1.0, c->dft_scale_log2);
+    const size_t rows2 = static_cast<size_t>(c->n_tiles2) * 512;
+    std::vector<__half> hi(rows2 * half), lo(rows2 * half);
+    for (size_t r = 0; r < rows2; ++r) {
+      const int tile = static_cast<int>(r / 512), part = static_cast<int>((r % 512) / 256), j = static_cast<int>(r % 256);
+      const int bin = bin_lo + tile * 256 + j;
+      for (int col = 0; col < half; ++col) {
+        const int k = col + 1;                                   // taps 1 .. N/2
+        double v = 0.0;
+        if (bin <= bin_hi) {
+          const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf);   // scipy get_window('hann', n, fftbins=True)
+          const long long ph = (static_cast<long long>(k) * bin) % nf;
+          const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
+          v = bscale * w * (part == 0 ? std::cos(ang) : -std::sin(ang));
+        }
+        const __half h = __float2half_rn(static_cast<float>(v));
+        hi[r * half + col] = h;
+        lo[r * half + col] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+      }
+    }
+    AVLD_TRY(dev_alloc(&c->d_B2hi, hi.size()));
+    AVLD_TRY(dev_alloc(&c->d_B2lo, lo.size()));
+    AVLD_CUDA(cudaMemcpy(c->d_B2hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    AVLD_CUDA(cudaMemcpy(c->d_B2lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 256, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 256, 128));
+    const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 128;
+    AVLD_TRY(dev_alloc(&c->d_A2hi, frames * nf));
+    AVLD_TRY(dev_alloc(&c->d_A2lo, frames * nf));
+    AVLD_CUDA(cudaMemset(c->d_A2hi, 0, frames * nf * 2));
+    AVLD_CUDA(cudaMemset(c->d_A2lo, 0, frames * nf * 2));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
+    AVLD_TRY(dev_alloc(&c->d_xs, static_cast<size_t>(c->max_batch) * c->R * p.hop));
+  } else {
     const int nf = p.n_fft;
     std::vector<double> win(nf), ct(nf), stab(nf);
     for (int k = 0; k < nf; ++k) {
@@ -370,13 +413,15 @@ static int build_ctx(avld_ctx* c) {
   }
 
   // ---- per-pass scratch
-  const size_t rows = static_cast<size_t>(c->max_batch) * c->R + 136;
-  AVLD_TRY(dev_alloc(&c->d_Ahi, rows * p.hop));
-  AVLD_TRY(dev_alloc(&c->d_Alo, rows * p.hop));
-  AVLD_CUDA(cudaMemset(c->d_Ahi, 0, rows * p.hop * 2));
-  AVLD_CUDA(cudaMemset(c->d_Alo, 0, rows * p.hop * 2));
-  AVLD_TRY(encode_tmap_2d(&c->tm_A_hi, c->d_Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
-  AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+  if (!c->dft_fold) {
+    const size_t rows = static_cast<size_t>(c->max_batch) * c->R + 136;
+    AVLD_TRY(dev_alloc(&c->d_Ahi, rows * p.hop));
+    AVLD_TRY(dev_alloc(&c->d_Alo, rows * p.hop));
+    AVLD_CUDA(cudaMemset(c->d_Ahi, 0, rows * p.hop * 2));
+    AVLD_CUDA(cudaMemset(c->d_Alo, 0, rows * p.hop * 2));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A_hi, c->d_Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
+  }
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->max_batch) * c->R * c->M));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
@@ -426,7 +471,7 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
-                  c->d_Alo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
+                  c->d_Alo, c->d_xs, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
                   c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
                   c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)
@@ -485,7 +530,7 @@ extern "C" int avld_stage_count(void) { return ST_COUNT; }
 extern "C" const char* avld_stage_name(int stage) {
   static const char* names[ST_COUNT] = {"prep_kernel", "gemm3_kernel<DFT>", "logmel_post_kernel", "conv_direct_kernel",
                                         "gemm3_kernel<CONV>", "gemm3_kernel<PLAIN>", "radii_kernel", "decide_kernel",
-                                        "centroid_kernel", "select_hist_kernel", "split_kernel"};
+                                        "centroid_kernel", "select_hist_kernel", "split_kernel", "fold_kernel"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 

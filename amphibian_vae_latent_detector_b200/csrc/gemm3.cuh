@@ -24,12 +24,17 @@
 
 namespace avld {
 
-enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2 };
+enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2, EPI_DFTF = 3 };
+// EPI_DFTF = folded STFT: per 256-bin N tile the first half of the K blocks (E | cos) accumulates the real parts
+// into TMEM columns [0, 256), the second half (O | -sin) the imaginary parts into [256, 512): one 512-column
+// accumulator, single buffered (the epilogue of a tile is not overlapped with the next tile's MMAs).
 
 struct Gemm3Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int split_n;  // 1: a work item is one (m tile, n tile) pair (dense layers with few m tiles); 0: one m tile, all n tiles
   uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
+  uint32_t idesc_last;                    // EPI_DFTF: descriptor of the last N tile when it holds only last_bins bins
+  int last_bins;
   int a_mode;
   int hpb;  // a_mode 1: 64-sample blocks per hop
   // a_mode 2 geometry
@@ -69,6 +74,7 @@ struct Gemm3Cfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_DFTF = 2 * STAGE_BYTES + EXTRA;   // same stage size; TMEM: 2 x BN columns, one buffer
   static_assert(STAGES >= 2, "tile too large for shared memory");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -81,6 +87,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
   using Cfg = Gemm3Cfg<BN, SWZ>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool FOLD = (EPI == EPI_DFTF);
+  constexpr int NACC = FOLD ? 1 : 2;            // TMEM accumulator buffers
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -113,7 +121,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if (EPI == EPI_DFT) {
+  if (EPI == EPI_DFT || EPI == EPI_DFTF) {
     for (int i = threadIdx.x; i < P.nbins_pad; i += blockDim.x) s_taps[i] = P.taps[i];
   } else {
     const int nb = P.num_n_tiles * BN;
@@ -167,8 +175,15 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               tma_load_4d(sa_hi, &tmA_hi, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
               tma_load_4d(sa_lo, &tmA_lo, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
             }
-            tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
-            tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
+            if (FOLD) {   // B2 rows: tile nt holds BN cos rows then BN (-sin) rows, each K/2 wide
+              const int hk = nkb >> 1;
+              const int bx = (kb < hk ? kb : kb - hk) * Cfg::BK, by = nt * 2 * BN + (kb < hk ? 0 : BN);
+              tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
+              tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
+            } else {
+              tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
+              tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -186,8 +201,15 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int sub = 0; sub < n_sub; ++sub) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
           tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          const uint32_t d_tmem0 = tmem_base + static_cast<uint32_t>(acc * BN);
+          [[maybe_unused]] const bool last_tile = FOLD && (sub == n_sub - 1) && P.last_bins != BN;
+          const uint32_t id_hh = last_tile ? P.idesc_last : P.idesc_hh;
+          const uint32_t id_lh = last_tile ? P.idesc_last : P.idesc_lh;
+          const uint32_t id_hl = last_tile ? P.idesc_last : P.idesc_hl;
           for (int kb = 0; kb < nkb; ++kb) {
+            const int hk = nkb >> 1;
+            const uint32_t d_tmem = FOLD ? d_tmem0 + (kb < hk ? 0u : static_cast<uint32_t>(BN)) : d_tmem0;
+            const int kb_acc = FOLD ? (kb < hk ? kb : kb - hk) : kb;
             mbar_wait(&full_bar[stage], phase, 300 + stage);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -199,15 +221,15 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < Cfg::BK / 16; ++k) {
               const uint64_t koff = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B, in 16 B units
-              umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc_hh, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc_lh, 1u);
-              umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc_hl, 1u);
+              umma_f16(d_tmem, da_hi + koff, db_hi + koff, id_hh, (kb_acc | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da_lo + koff, db_hi + koff, id_lh, 1u);
+              umma_f16(d_tmem, da_hi + koff, db_lo + koff, id_hl, 1u);
             }
             umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
             if (kb == nkb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
         }
       }
     }
@@ -227,9 +249,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       [[maybe_unused]] float acc0 = 0.f, acc1 = 0.f, s2 = 0.f;
       [[maybe_unused]] bool valid = false;
       [[maybe_unused]] long long g = 0;
-      if (EPI == EPI_DFT) {
+      if (EPI == EPI_DFT || EPI == EPI_DFTF) {
         g = static_cast<long long>(mt) * Cfg::BM + row;
-        const long long c = g / P.R;
+        const long long c = g / P.R;                    // R = rows per chunk (direct: R incl. junk frames; folded: F)
         const int f = static_cast<int>(g - c * P.R);
         valid = (g < P.M_total) && (f < P.F);
         s2 = valid ? P.inv2[c] : 0.f;
@@ -273,11 +295,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               }
             }
           }
-        } else if (EPI == EPI_DFT) {
-          // columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins
-          constexpr int HB = BN / 2;
+        } else if (EPI == EPI_DFT || EPI == EPI_DFTF) {
+          // direct: columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins; folded: [0, BN) = Re, [BN, 2 BN) = Im
+          constexpr int HB = FOLD ? BN : BN / 2;
+          const int nb_tile = (FOLD && nt == P.num_n_tiles - 1) ? P.last_bins : HB;
 #pragma unroll 1
-          for (int c0 = 0; c0 < HB; c0 += 16) {
+          for (int c0 = 0; c0 < nb_tile; c0 += 16) {
             uint32_t re[16], im[16];
             tmem_ld16(t_acc + c0, re);
             tmem_ld16(t_acc + HB + c0, im);
@@ -370,7 +393,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         tcgen05_fence_before();
         mbar_arrive(&tmem_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   }

@@ -12,7 +12,34 @@
 
 namespace avld {
 
+static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
+  Gemm3Params P{};
+  const long long rows = static_cast<long long>(n) * c->F;          // only real frames: no junk rows between chunks
+  P.num_m_tiles = static_cast<int>((rows + 127) / 128);
+  P.num_n_tiles = c->n_tiles2;
+  P.num_k_blocks = c->p.n_fft / 64;                                 // n_fft/128 blocks of E|cos, then n_fft/128 of O|-sin
+  P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(0, 0, 128, 256);
+  P.idesc_last = avld_make_idesc(0, 0, 128, c->last_tile_bins);
+  P.last_bins = c->last_tile_bins;
+  P.a_mode = 0;
+  P.M_total = rows;
+  P.N_total = c->ncols;
+  P.inv2 = c->d_inv2;
+  P.taps = c->d_taps;
+  P.melpow = c->d_melpow;
+  P.R = c->F;
+  P.F = c->F;
+  P.n_mels = c->M;
+  P.nbins_pad = c->nbins_pad;
+  LaunchScope ls(c, ST_STFT_MEL, st);
+  return run_gemm3(256, 128, EPI_DFTF, c->tm_A2_hi, c->tm_A2_lo, c->tm_B2_hi, c->tm_B2_lo, P, c->sm_count, st);
+}
+
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
+  if (c->dft_fold) {
+    AVLD_TRY(launch_fold(c, n, st));
+    return launch_stft_mel_folded(c, n, st);
+  }
   Gemm3Params P{};
   const long long rows = static_cast<long long>(n) * c->R;
   P.num_m_tiles = static_cast<int>((rows + 127) / 128);
@@ -121,7 +148,7 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
 
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
-  PostParams P{c->d_melpow, feat, c->R, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
+  PostParams P{c->d_melpow, feat, c->dft_fold ? c->F : c->R, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
   const size_t smem = static_cast<size_t>(c->F) * c->M * sizeof(float);
   static bool configured = false;
   if (!configured) {

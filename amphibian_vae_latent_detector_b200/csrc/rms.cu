@@ -21,6 +21,7 @@ struct PrepParams {
   float* y;               // nullable
   __half* a_hi;           // nullable (operand mode)
   __half* a_lo;
+  float* xs;              // nullable (folded STFT): fp32 padded, scaled samples [n][R * hop]
   float* inv2;
   uint8_t* ok;            // nullable
   float* rms;             // nullable
@@ -179,6 +180,22 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     }
   }
 
+  // ---------------------------------------------------------------- phase 2b': padded fp32 samples for fold_kernel
+  if (P.xs != nullptr) {
+    const float pow2 = s_pow2;
+    const int half = P.n_fft / 2;
+    const int total = P.R * P.hop;
+    float* __restrict__ dst = P.xs + static_cast<size_t>(c) * total;
+    for (int p = tid; p < total; p += blockDim.x) {
+      int src = p - half;                                // np.pad(y, n_fft//2, mode="reflect")
+      if (src < 0) src = -src;
+      if (src >= P.L) src = 2 * (P.L - 1) - src;
+      float v = 0.f;
+      if (p < P.L + P.n_fft) v = finish_sample(xc(src), scale, scaled, P.quantize) * pow2;
+      dst[p] = v;
+    }
+  }
+
   // ---------------------------------------------------------------- phase 2b: GEMM operand rows
   if (P.a_hi != nullptr) {
     const float pow2 = s_pow2;
@@ -208,6 +225,72 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fold_kernel: frames -> even/odd folded fp16 hi/lo operand rows (see common.cuh, "folded STFT")
+//   E[f][j] = xs[f*hop + k] + xs[f*hop + N - k],  O[f][j] = xs[f*hop + k] - xs[f*hop + N - k],  k = j + 1
+//   (k = N/2: E = xs[f*hop + N/2], O = 0).  One thread = 8 consecutive taps of one frame; a warp reads
+//   two runs of 256 contiguous floats and stores 4 x 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+struct FoldParams {
+  const float* xs;      // [n][R*hop]
+  __half* a_hi;         // [n*F][n_fft]
+  __half* a_lo;
+  int F, hop, n_fft, chunk_stride;
+  long long total;      // n * F * (n_fft/2/8) threads
+};
+
+__global__ void __launch_bounds__(256) fold_kernel(const FoldParams P) {
+  const int half = P.n_fft >> 1, per_frame = half >> 3;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < P.total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = t / per_frame;                 // global frame index = chunk * F + f
+    const int j0 = static_cast<int>(t - row * per_frame) << 3;
+    const long long chunk = row / P.F;
+    const int f = static_cast<int>(row - chunk * P.F);
+    const float* __restrict__ x = P.xs + chunk * P.chunk_stride + static_cast<long long>(f) * P.hop;
+    float a[8], b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a[q] = x[j0 + 1 + q];
+      b[q] = x[P.n_fft - 1 - j0 - q];
+    }
+    __align__(16) __half eh[8], el[8], oh[8], ol[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const bool mid = (j0 + q == half - 1);             // k = N/2 pairs with itself
+      const float e = mid ? a[q] : a[q] + b[q];
+      const float o = mid ? 0.f : a[q] - b[q];
+      eh[q] = __float2half_rn(e);
+      el[q] = __float2half_rn(e - __half2float(eh[q]));
+      oh[q] = __float2half_rn(o);
+      ol[q] = __float2half_rn(o - __half2float(oh[q]));
+    }
+    const size_t base = static_cast<size_t>(row) * P.n_fft + j0;
+    *reinterpret_cast<uint4*>(P.a_hi + base) = *reinterpret_cast<const uint4*>(eh);
+    *reinterpret_cast<uint4*>(P.a_lo + base) = *reinterpret_cast<const uint4*>(el);
+    *reinterpret_cast<uint4*>(P.a_hi + base + half) = *reinterpret_cast<const uint4*>(oh);
+    *reinterpret_cast<uint4*>(P.a_lo + base + half) = *reinterpret_cast<const uint4*>(ol);
+  }
+}
+
+int launch_fold(avld_ctx* c, int n, cudaStream_t st) {
+  if (n <= 0) return AVLD_OK;
+  FoldParams P{};
+  P.xs = c->d_xs;
+  P.a_hi = c->d_A2hi;
+  P.a_lo = c->d_A2lo;
+  P.F = c->F;
+  P.hop = c->p.hop;
+  P.n_fft = c->p.n_fft;
+  P.chunk_stride = c->R * c->p.hop;
+  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / 16);
+  const long long blocks = (P.total + 255) / 256;
+  const int grid = static_cast<int>(blocks < static_cast<long long>(c->sm_count) * 32 ? blocks : static_cast<long long>(c->sm_count) * 32);
+  { LaunchScope ls(c, ST_FOLD, st); fold_kernel<<<grid, 256, 0, st>>>(P); }
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+
 int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
@@ -215,8 +298,9 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.x = x;
   P.x16 = x16;
   P.y = y_out;
-  P.a_hi = write_operand ? c->d_Ahi : nullptr;
-  P.a_lo = write_operand ? c->d_Alo : nullptr;
+  P.a_hi = (write_operand && !c->dft_fold) ? c->d_Ahi : nullptr;
+  P.a_lo = (write_operand && !c->dft_fold) ? c->d_Alo : nullptr;
+  P.xs = (write_operand && c->dft_fold) ? c->d_xs : nullptr;
   P.inv2 = write_operand ? c->d_inv2 : nullptr;
   P.ok = ok;
   P.rms = rms;

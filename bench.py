@@ -340,6 +340,9 @@ def main():
         prep = stages["prep_kernel"]
         if prep["ms"] > 0:   # reads 4L, writes fp16 hi+lo operand rows incl. reflect padding: 4 * 381 * 384 bytes
             hbm["prep_kernel"] = round((4 * CHUNK_LEN + 4 * 381 * 384) * chunks_timed / (prep["ms"] / 1e3) / 1e9, 1)
+        fold = stages.get("fold_kernel")
+        if fold and fold["ms"] > 0:   # reads the padded fp32 samples (L2-resident re-reads not counted), writes E|O hi+lo
+            hbm["fold_kernel"] = round((4 * 381 * 384 + 4 * 376 * 2048) * chunks_timed / (fold["ms"] / 1e3) / 1e9, 1)
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -352,7 +355,9 @@ def main():
                          "achieved": dft_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (dft_tflops / peaks["tflops_sustained"]) if dft_tflops else None,
                          "peak_source": f"bf16 dense sustained, {peaks['source']}",
-                         "issued_over_algorithmic": 3.0 * (2 * 640) / (2 * 634) * 381 / 376,
+                         "issued_over_algorithmic": (3.0 * 640 / 634 / 2) if os.environ.get("AVLD_DFT_MODE", "fold") != "direct"
+                         else 3.0 * 640 / 634 * 381 / 376,
+                         "dft_mode": os.environ.get("AVLD_DFT_MODE", "fold"),
                          "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": None,
                          "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None},
             "stage_ms_per_step": stage_ms,
