@@ -140,6 +140,23 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // FOLD: the A operand (folded frames) streams from HBM and is re-read once per N tile; a second iterator runs
+      // PF K blocks ahead of the loads and prefetches those boxes into L2
+      constexpr int PF = 8;
+      [[maybe_unused]] int pf_item = blockIdx.x, pf_nt = 0, pf_kb = 0;
+      [[maybe_unused]] auto pf_step = [&]() {
+        if (pf_item < n_items) {
+          tma_prefetch_2d(&tmA_hi, pf_kb * Cfg::BK, pf_item * Cfg::BM);
+          tma_prefetch_2d(&tmA_lo, pf_kb * Cfg::BK, pf_item * Cfg::BM);
+          if (++pf_kb == nkb) {
+            pf_kb = 0;
+            if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_item += gridDim.x; }
+          }
+        }
+      };
+      if (FOLD) {
+        for (int i = 0; i < PF; ++i) pf_step();
+      }
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = P.split_n ? item / P.num_n_tiles : item;
         const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
@@ -154,6 +171,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         for (int nt = nt_begin; nt < nt_end; ++nt) {
           for (int kb = 0; kb < nkb; ++kb) {
+            if (FOLD) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
             uint8_t* sa_hi = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sa_lo = sa_hi + Cfg::A_BYTES;
