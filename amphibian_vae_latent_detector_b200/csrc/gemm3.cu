@@ -26,6 +26,7 @@ int run_gemm3(int bn, int swz, int epi, const CUtensorMap& a_hi, const CUtensorM
   if (epi == EPI_CONV) return by_shape<EPI_CONV>(bn, swz, a_hi, a_lo, b_hi, b_lo, P, sms, st);
   if (epi == EPI_DFT && bn == 256 && swz == 128) return launch_gemm3<256, 128, EPI_DFT>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
   if (epi == EPI_DFTF && bn == 256 && swz == 128) return launch_gemm3<256, 128, EPI_DFTF>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
+  if (epi == EPI_DFTF && bn == 256 && swz == 64) return launch_gemm3<256, 64, EPI_DFTF>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
   set_error("run_gemm3: no kernel for BN=%d swizzle=%d epilogue=%d", bn, swz, epi);
   return AVLD_ERR_UNSUPPORTED;
 }

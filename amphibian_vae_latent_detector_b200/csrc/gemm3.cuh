@@ -74,7 +74,6 @@ struct Gemm3Cfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_DFTF = 2 * STAGE_BYTES + EXTRA;   // same stage size; TMEM: 2 x BN columns, one buffer
   static_assert(STAGES >= 2, "tile too large for shared memory");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -142,7 +141,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       uint32_t phase = 0;
       // FOLD: the A operand (folded frames) streams from HBM and is re-read once per N tile; a second iterator runs
       // PF K blocks ahead of the loads and prefetches those boxes into L2
-      constexpr int PF = 8;
+      constexpr int PF = 512 / Cfg::BK;   // 8 blocks of 64 / 16 blocks of 32 taps ahead
       [[maybe_unused]] int pf_item = blockIdx.x, pf_nt = 0, pf_kb = 0;
       [[maybe_unused]] auto pf_step = [&]() {
         if (pf_item < n_items) {

@@ -17,7 +17,7 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
   const long long rows = static_cast<long long>(n) * c->F;          // only real frames: no junk rows between chunks
   P.num_m_tiles = static_cast<int>((rows + 127) / 128);
   P.num_n_tiles = c->n_tiles2;
-  P.num_k_blocks = c->p.n_fft / 64;                                 // n_fft/128 blocks of E|cos, then n_fft/128 of O|-sin
+  P.num_k_blocks = c->p.n_fft / c->fold_bk;                         // first half: E | cos blocks, second half: O | -sin blocks
   P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(0, 0, 128, 256);
   P.idesc_last = avld_make_idesc(0, 0, 128, c->last_tile_bins);
   P.last_bins = c->last_tile_bins;
@@ -32,7 +32,7 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
   P.n_mels = c->M;
   P.nbins_pad = c->nbins_pad;
   LaunchScope ls(c, ST_STFT_MEL, st);
-  return run_gemm3(256, 128, EPI_DFTF, c->tm_A2_hi, c->tm_A2_lo, c->tm_B2_hi, c->tm_B2_lo, P, c->sm_count, st);
+  return run_gemm3(256, c->fold_bk * 2, EPI_DFTF, c->tm_A2_hi, c->tm_A2_lo, c->tm_B2_hi, c->tm_B2_lo, P, c->sm_count, st);
 }
 
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
