@@ -45,9 +45,10 @@ enum Stage {
   } while (0)
 
 // mel filterbank tap of one FFT bin: feeds filter `first` with w0 and `first + 1` with w1
-struct MelTap {
+struct __align__(16) MelTap {
   int32_t first;
   float w0, w1;
+  int32_t pad;
 };
 
 struct PairNode {
@@ -104,7 +105,7 @@ struct avld_ctx {
   // E | O are materialised per pass by fold_kernel as fp16 hi/lo rows [frame][N/2 + N/2].
   int dft_fold = 1;
   int n_tiles2 = 0, last_tile_bins = 0;   // 256-bin N tiles; the last one may hold only 128
-  int fold_bk = 32;                       // K elements per pipeline stage of the folded GEMM (32: 4 x 48 KB stages, 64: 2 x 96 KB)
+  int fold_bk = 64;                       // K elements per pipeline stage of the folded GEMM (64: 2 x 96 KB stages, 32: 4 x 48 KB)
   float* d_xs = nullptr;           // [max_batch][R * hop] normalised, quantised, reflect-padded, pow2-scaled audio (fp32)
   __half* d_A2hi = nullptr;        // [max_batch * F + 128][n_fft] folded frames, E in columns [0, N/2), O in [N/2, N)
   __half* d_A2lo = nullptr;

@@ -333,9 +333,9 @@ static int build_ctx(avld_ctx* c) {
     const int b = bin_lo + i;
     if (b <= bin_hi && first[b] >= 0) {
       run_first = first[b];
-      taps[i] = {first[b], w0[b], w1[b]};
+      taps[i] = {first[b], w0[b], w1[b], 0};
     } else {
-      taps[i] = {run_first, 0.f, 0.f};
+      taps[i] = {run_first, 0.f, 0.f, 0};
     }
   }
   AVLD_TRY(dev_alloc(&c->d_taps, taps.size()));
@@ -370,7 +370,7 @@ static int build_ctx(avld_ctx* c) {
     AVLD_CUDA(cudaMemcpy(c->d_B2lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
     {
       const char* bk = getenv("AVLD_FOLD_BK");
-      c->fold_bk = (bk != nullptr && atoi(bk) == 64) ? 64 : 32;
+      c->fold_bk = (bk != nullptr && atoi(bk) == 32) ? 32 : 64;
     }
     const uint32_t fbk = static_cast<uint32_t>(c->fold_bk), fsw = fbk * 2;
     AVLD_TRY(encode_tmap_2d(&c->tm_B2_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));

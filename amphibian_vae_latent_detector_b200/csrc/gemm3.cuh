@@ -78,8 +78,12 @@ struct Gemm3Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
 
+// threads per CTA: TMA warp + MMA warp + 4 epilogue warps (8 for the folded STFT, whose epilogue is not overlapped)
+template <int EPI>
+struct Gemm3Threads { static constexpr int value = (EPI == EPI_DFTF) ? 320 : 192; };
+
 template <int BN, int SWZ, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(Gemm3Threads<EPI>::value, 1)
 gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
              const Gemm3Params P) {
@@ -114,7 +118,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], FOLD ? 256 : 128);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -278,7 +282,49 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
 
-        if (EPI == EPI_PLAIN) {
+        if (EPI == EPI_DFTF) {
+          // Folded STFT: [0, BN) = Re, [BN, 2 BN) = Im of the tile's BN bins.  Two warps per TMEM lane quarter, each
+          // taking half of the tile's bins; every mel output is accumulated with atomicAdd onto a zeroed buffer (a
+          // filter is narrower than half a tile, so it receives at most two partial sums: 0 + a + b is order independent).
+          const int half_id = (warp - 2) >> 2;
+          const int nb_tile = (nt == P.num_n_tiles - 1) ? P.last_bins : BN;
+          const int hbins = nb_tile >> 1;
+          const int b0 = half_id * hbins;
+          const MelTap* tile_taps = s_taps + nt * BN;
+          float* mrow = P.melpow + g * P.n_mels;
+          int mcur = tile_taps[b0].first;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+          for (int c0 = b0; c0 < b0 + hbins; c0 += 16) {
+            uint32_t re[16], im[16];
+            tmem_ld16(t_acc + c0, re);
+            tmem_ld16(t_acc + BN + c0, im);
+            tmem_ld_wait();
+            float pw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+              pw[j] = (a * a + b * b) * s2;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const MelTap tp = tile_taps[c0 + j];
+              if (mcur < tp.first) {                 // warp-uniform (taps do not depend on the row), rare: 64 times per row
+#pragma unroll 1
+                while (mcur < tp.first) {
+                  if (valid && a0 != 0.f) atomicAdd(mrow + mcur, a0);
+                  a0 = a1;
+                  a1 = 0.f;
+                  ++mcur;
+                }
+              }
+              a0 = fmaf(tp.w0, pw[j], a0);
+              a1 = fmaf(tp.w1, pw[j], a1);
+            }
+          }
+          if (valid && a0 != 0.f && mcur < P.n_mels) atomicAdd(mrow + mcur, a0);
+          if (valid && a1 != 0.f && mcur + 1 < P.n_mels) atomicAdd(mrow + mcur + 1, a1);
+        } else if (EPI == EPI_PLAIN) {
           const long long m = static_cast<long long>(mt) * Cfg::BM + row;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -312,12 +358,11 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               }
             }
           }
-        } else if (EPI == EPI_DFT || EPI == EPI_DFTF) {
-          // direct: columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins; folded: [0, BN) = Re, [BN, 2 BN) = Im
-          constexpr int HB = FOLD ? BN : BN / 2;
-          const int nb_tile = (FOLD && nt == P.num_n_tiles - 1) ? P.last_bins : HB;
+        } else if (EPI == EPI_DFT) {
+          // columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins
+          constexpr int HB = BN / 2;
 #pragma unroll 1
-          for (int c0 = 0; c0 < nb_tile; c0 += 16) {
+          for (int c0 = 0; c0 < HB; c0 += 16) {
             uint32_t re[16], im[16];
             tmem_ld16(t_acc + c0, re);
             tmem_ld16(t_acc + HB + c0, im);
@@ -435,7 +480,7 @@ int launch_gemm3(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUt
   const int items = P.split_n ? P.num_m_tiles * P.num_n_tiles : P.num_m_tiles;
   int grid = items < sm_count ? items : sm_count;
   if (grid < 1) return AVLD_OK;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, P);
+  kfn<<<grid, Gemm3Threads<EPI>::value, Cfg::SMEM_BYTES, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, P);
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }

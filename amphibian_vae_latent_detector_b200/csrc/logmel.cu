@@ -31,6 +31,8 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
   P.F = c->F;
   P.n_mels = c->M;
   P.nbins_pad = c->nbins_pad;
+  // the epilogue accumulates mel outputs with atomicAdd
+  AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
   LaunchScope ls(c, ST_STFT_MEL, st);
   return run_gemm3(256, c->fold_bk * 2, EPI_DFTF, c->tm_A2_hi, c->tm_A2_lo, c->tm_B2_hi, c->tm_B2_lo, P, c->sm_count, st);
 }
