@@ -112,6 +112,8 @@ struct avld_ctx {
   __half* d_B2hi = nullptr;        // [n_tiles2 * 512][N/2]: per tile 256 cos rows then 256 (-sin) rows
   __half* d_B2lo = nullptr;
   CUtensorMap tm_A2_hi, tm_A2_lo, tm_B2_hi, tm_B2_lo;
+  CUtensorMap tm_B2h_hi, tm_B2h_lo;   // 128-row boxes of B2 for the CTA-pair kernel
+  int dft_pair = 1;                   // folded GEMM on CTA pairs (cta_group::2); AVLD_DFT_MODE=fold1 selects the 1-CTA kernel
 
   // per-pass scratch (max_batch chunks)
   int max_batch = 0;
@@ -187,6 +189,7 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold(avld_ctx* c, int n, cudaStream_t st);
+int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);

@@ -320,6 +320,7 @@ static int build_ctx(avld_ctx* c) {
   {
     const char* mode = getenv("AVLD_DFT_MODE");          // "direct" selects the un-folded K = n_fft GEMM (A/B comparisons)
     c->dft_fold = !(mode != nullptr && strcmp(mode, "direct") == 0) && (p.n_fft % 128 == 0);
+    c->dft_pair = !(mode != nullptr && strcmp(mode, "fold1") == 0);
   }
   c->n_tiles2 = (nbins + 255) / 256;
   c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;
@@ -375,7 +376,9 @@ static int build_ctx(avld_ctx* c) {
     const uint32_t fbk = static_cast<uint32_t>(c->fold_bk), fsw = fbk * 2;
     AVLD_TRY(encode_tmap_2d(&c->tm_B2_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
     AVLD_TRY(encode_tmap_2d(&c->tm_B2_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
-    const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 128;
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 128, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 128, 128));
+    const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 256;
     AVLD_TRY(dev_alloc(&c->d_A2hi, frames * nf));
     AVLD_TRY(dev_alloc(&c->d_A2lo, frames * nf));
     AVLD_CUDA(cudaMemset(c->d_A2hi, 0, frames * nf * 2));

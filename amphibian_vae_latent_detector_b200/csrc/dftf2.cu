@@ -1,0 +1,257 @@
+// dftf2.cu -- folded STFT GEMM on CTA pairs (tcgen05 cta_group::2).
+//
+// Same mathematics as gemm3_kernel<256,128,EPI_DFTF> (see common.cuh "folded STFT"), but two CTAs of a cluster share
+// one 256-frame x 256-bin MMA: each CTA stages its own 128 frames of A and only HALF of the B rows, so a pipeline
+// stage is 64 KB instead of 96 KB (three stages instead of two), and each SM pulls a third less from L2.
+//   warp 0 lane 0 (both CTAs)   TMA producer: own A rows, own half of the B rows, bytes counted on the leader's barrier
+//   warp 1 lane 0 (leader only) MMA issuer: tcgen05.mma.cta_group::2, commits multicast to both CTAs
+//   warps 2..9    (both CTAs)   epilogue on the CTA's own TMEM: |X|^2, un-scale, sparse slaney mel, atomicAdd
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace avld {
+
+struct Dftf2Params {
+  int num_pairs, num_n_tiles, num_k_blocks;   // pairs of 128-frame tiles; 256-bin tiles; 64-tap blocks (E half then O half)
+  uint32_t idesc_full, idesc_last;
+  int last_bins;
+  long long M_total;
+  const float* inv2;
+  const MelTap* taps;
+  float* melpow;
+  int F, n_mels, nbins_pad;
+};
+
+namespace {
+constexpr int kStages = 3;
+constexpr int kBM = 128, kBK = 64, kBN = 256;
+constexpr int kABytes = kBM * 128;              // one of hi / lo: 128 rows x 128 B
+constexpr int kBBytes = (kBN / 2) * 128;        // this CTA's half of the N rows
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 64 KB
+constexpr int kExtra = 16384;
+constexpr int kSmemBytes = kStages * kStageBytes + kExtra + 1024;
+constexpr int kThreads = 320;
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Dftf2Params P) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* tail = smem + kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [kStages]  (used in the leader)
+  uint64_t* empty_bar = full_bar + kStages;                   // [kStages]  (per CTA)
+  uint64_t* tmem_full = empty_bar + kStages;                  // [1]        (per CTA)
+  uint64_t* tmem_empty = tmem_full + 1;                       // [1]        (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_clusters = static_cast<int>(ncluster_id_x());
+  const int cluster = static_cast<int>(cluster_id_x());
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 2);          // leader's expect_tx arrive + the peer producer's arrive
+      mbar_init(&empty_bar[s], 1);         // one multicast commit
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_empty[0], 16);         // lane 0 of the 8 epilogue warps of both CTAs
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  for (int i = threadIdx.x; i < P.nbins_pad; i += blockDim.x) s_taps[i] = P.taps[i];
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer's barriers exist before anything can signal them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = P.num_k_blocks, hk = nkb >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      constexpr int PF = 8;
+      int pf_pair = cluster, pf_nt = 0, pf_kb = 0;
+      auto pf_step = [&]() {
+        if (pf_pair < P.num_pairs) {
+          const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
+          tma_prefetch_2d(&tmA_hi, pf_kb * kBK, y);
+          tma_prefetch_2d(&tmA_lo, pf_kb * kBK, y);
+          if (++pf_kb == nkb) {
+            pf_kb = 0;
+            if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_pair += n_clusters; }
+          }
+        }
+      };
+      for (int i = 0; i < PF; ++i) pf_step();
+      for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+        const int ay = pair * 2 * kBM + static_cast<int>(rank) * kBM;
+        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+          const int nb = (nt == P.num_n_tiles - 1) ? P.last_bins : kBN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            pf_step();
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+            uint8_t* sa_hi = smem + stage * kStageBytes;
+            uint8_t* sa_lo = sa_hi + kABytes;
+            uint8_t* sb_hi = sa_lo + kABytes;
+            uint8_t* sb_lo = sb_hi + kBBytes;
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+            const int bx = (kb < hk ? kb : kb - hk) * kBK;
+            const int by = nt * 2 * kBN + (kb < hk ? 0 : kBN) + static_cast<int>(rank) * (nb >> 1);
+            tma_load_2d_pair(sa_hi, &tmA_hi, &full_bar[stage], kb * kBK, ay);
+            tma_load_2d_pair(sa_lo, &tmA_lo, &full_bar[stage], kb * kBK, ay);
+            tma_load_2d_pair(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
+            tma_load_2d_pair(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+        for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+          const uint32_t idesc = (nt == P.num_n_tiles - 1) ? P.idesc_last : P.idesc_full;
+          mbar_wait(&tmem_empty[0], acc_phase ^ 1u, 200);
+          tcgen05_fence_after();
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase, 300 + stage);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (kb < hk ? 0u : static_cast<uint32_t>(kBN));
+            const int kb_acc = kb < hk ? kb : kb - hk;
+            const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
+            const uint32_t a_lo = a_hi + kABytes, b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
+            const uint64_t da_hi = make_smem_desc(a_hi, 128), da_lo = make_smem_desc(a_lo, 128);
+            const uint64_t db_hi = make_smem_desc(b_hi, 128), db_lo = make_smem_desc(b_lo, 128);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t koff = static_cast<uint64_t>(k * 2);
+              umma_f16_pair(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+              umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
+              umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+            }
+            umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
+            if (kb == nkb - 1) umma_commit_pair(&tmem_full[0], 0x3);     // accumulators complete in both CTAs
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int quarter = warp & 3, half_id = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t acc_phase = 0;
+    for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+      const long long g = static_cast<long long>(pair) * 2 * kBM + static_cast<long long>(rank) * kBM + row;
+      const bool valid = g < P.M_total;
+      const float s2 = valid ? P.inv2[g / P.F] : 0.f;
+      float* mrow = P.melpow + g * P.n_mels;
+      for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+        mbar_wait(&tmem_full[0], acc_phase, 400);
+        tcgen05_fence_after();
+        const int nb_tile = (nt == P.num_n_tiles - 1) ? P.last_bins : kBN;
+        const int hbins = nb_tile >> 1, b0 = half_id * hbins;
+        const MelTap* tile_taps = s_taps + nt * kBN;
+        int mcur = tile_taps[b0].first;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+        for (int c0 = b0; c0 < b0 + hbins; c0 += 16) {
+          uint32_t re[16], im[16];
+          tmem_ld16(t_acc + c0, re);
+          tmem_ld16(t_acc + kBN + c0, im);
+          tmem_ld_wait();
+          float pw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
+            pw[j] = (a * a + b * b) * s2;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const MelTap tp = tile_taps[c0 + j];
+            if (mcur < tp.first) {
+#pragma unroll 1
+              while (mcur < tp.first) {
+                if (valid && a0 != 0.f) atomicAdd(mrow + mcur, a0);
+                a0 = a1;
+                a1 = 0.f;
+                ++mcur;
+              }
+            }
+            a0 = fmaf(tp.w0, pw[j], a0);
+            a1 = fmaf(tp.w1, pw[j], a1);
+          }
+        }
+        if (valid && a0 != 0.f && mcur < P.n_mels) atomicAdd(mrow + mcur, a0);
+        if (valid && a1 != 0.f && mcur + 1 < P.n_mels) atomicAdd(mrow + mcur + 1, a1);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tmem_empty[0]);
+          else mbar_arrive_cluster(&tmem_empty[0], 0);
+        }
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer may still be reading operands / signalling our barriers
+  tcgen05_fence_after();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+#endif
+}
+
+int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st) {
+  Dftf2Params P{};
+  const long long rows = static_cast<long long>(n) * c->F;
+  const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
+  P.num_pairs = (m_tiles + 1) / 2;
+  P.num_n_tiles = c->n_tiles2;
+  P.num_k_blocks = c->p.n_fft / kBK;
+  P.idesc_full = avld_make_idesc(0, 0, 256, 256);
+  P.idesc_last = avld_make_idesc(0, 0, 256, c->last_tile_bins);
+  P.last_bins = c->last_tile_bins;
+  P.M_total = rows;
+  P.inv2 = c->d_inv2;
+  P.taps = c->d_taps;
+  P.melpow = c->d_melpow;
+  P.F = c->F;
+  P.n_mels = c->M;
+  P.nbins_pad = c->nbins_pad;
+  static bool configured = false;
+  if (!configured) {
+    AVLD_CUDA(cudaFuncSetAttribute(dftf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
+  int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
+  if (grid < 2) return AVLD_OK;
+  LaunchScope ls(c, ST_STFT_MEL, st);
+  dftf2_kernel<<<grid, kThreads, kSmemBytes, st>>>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B2h_hi, c->tm_B2h_lo, P);
+  AVLD_CUDA(cudaGetLastError());
+  return AVLD_OK;
+}
+
+}  // namespace avld
