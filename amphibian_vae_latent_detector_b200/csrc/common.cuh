@@ -113,6 +113,7 @@ struct avld_ctx {
   __half* d_B2lo = nullptr;
   CUtensorMap tm_A2_hi, tm_A2_lo, tm_B2_hi, tm_B2_lo;
   CUtensorMap tm_B2h_hi, tm_B2h_lo;   // 128-row boxes of B2 for the CTA-pair kernel
+  CUtensorMap tm_A2pf_hi, tm_A2pf_lo; // un-swizzled 256-tap x 128-row boxes of A2, used only for L2 prefetch (4x fewer TMA rows)
   int dft_pair = 1;                   // folded GEMM on CTA pairs (cta_group::2); AVLD_DFT_MODE=fold1 selects the 1-CTA kernel
 
   // per-pass scratch (max_batch chunks)

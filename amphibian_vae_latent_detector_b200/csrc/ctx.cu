@@ -376,8 +376,8 @@ static int build_ctx(avld_ctx* c) {
     const uint32_t fbk = static_cast<uint32_t>(c->fold_bk), fsw = fbk * 2;
     AVLD_TRY(encode_tmap_2d(&c->tm_B2_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
     AVLD_TRY(encode_tmap_2d(&c->tm_B2_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 128, 128));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, 64, 128, 128));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 128, fsw));
+    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 128, fsw));
     const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 256;
     AVLD_TRY(dev_alloc(&c->d_A2hi, frames * nf));
     AVLD_TRY(dev_alloc(&c->d_A2lo, frames * nf));
@@ -385,6 +385,8 @@ static int build_ctx(avld_ctx* c) {
     AVLD_CUDA(cudaMemset(c->d_A2lo, 0, frames * nf * 2));
     AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, fbk, 128, fsw));
     AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, fbk, 128, fsw));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
+    AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
     AVLD_TRY(dev_alloc(&c->d_xs, static_cast<size_t>(c->max_batch) * c->R * p.hop));
   } else {
     const int nf = p.n_fft;

@@ -7,6 +7,9 @@
 //   warp 1 lane 0 (leader only) MMA issuer: tcgen05.mma.cta_group::2, commits multicast to both CTAs
 //   warps 2..9    (both CTAs)   epilogue on the CTA's own TMEM: |X|^2, un-scale, sparse slaney mel, atomicAdd
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -22,29 +25,41 @@ struct Dftf2Params {
   const MelTap* taps;
   float* melpow;
   int F, n_mels, nbins_pad;
+  long long* trace;   // bring-up: clock64 timestamps of cluster 0 (4 event kinds x 2 ranks x 256 K blocks), or NULL
+  int dbg;   // bring-up: 1 = skip the epilogue math, 2 = skip the A/B loads after the first fill (MMA-only timing)
 };
 
 namespace {
-constexpr int kStages = 3;
-constexpr int kBM = 128, kBK = 64, kBN = 256;
-constexpr int kABytes = kBM * 128;              // one of hi / lo: 128 rows x 128 B
-constexpr int kBBytes = (kBN / 2) * 128;        // this CTA's half of the N rows
-constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 64 KB
+constexpr int kBM = 128, kBN = 256;
 constexpr int kExtra = 16384;
-constexpr int kSmemBytes = kStages * kStageBytes + kExtra + 1024;
 constexpr int kThreads = 320;
+// KBK taps per pipeline stage: 64 (128-byte swizzled rows, 3 stages of 64 KB) or 32 (64-byte rows, 6 stages of 32 KB)
+template <int KBK>
+struct PairCfg {
+  static constexpr int kSwz = KBK * 2;
+  static constexpr int kABytes = kBM * kSwz;            // one of hi / lo
+  static constexpr int kBBytes = (kBN / 2) * kSwz;      // this CTA's half of the N rows
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kExtra + 1024;
+};
 }  // namespace
 
+template <int kBK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Dftf2Params P) {
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+             const __grid_constant__ CUtensorMap tmPf_hi, const __grid_constant__ CUtensorMap tmPf_lo, const Dftf2Params P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
+  using Cfg = PairCfg<kBK>;
+  constexpr int kStages = Cfg::kStages, kStageBytes = Cfg::kStageBytes, kABytes = Cfg::kABytes, kBBytes = Cfg::kBBytes;
+  constexpr int kSwz = Cfg::kSwz;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* tail = smem + kStages * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [kStages]  (used in the leader)
-  uint64_t* empty_bar = full_bar + kStages;                   // [kStages]  (per CTA)
-  uint64_t* tmem_full = empty_bar + kStages;                  // [1]        (per CTA)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [8]  (used in the leader)
+  uint64_t* empty_bar = full_bar + 8;                         // [8]  (per CTA)
+  uint64_t* tmem_full = empty_bar + 8;                        // [1]  (per CTA)
   uint64_t* tmem_empty = tmem_full + 1;                       // [1]        (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);
@@ -60,6 +75,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
+    tma_prefetch_desc(&tmPf_hi);
+    tma_prefetch_desc(&tmPf_lo);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 2);          // leader's expect_tx arrive + the peer producer's arrive
       mbar_init(&empty_bar[s], 1);         // one multicast commit
@@ -83,13 +100,17 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      constexpr int PF = 8;
+      // L2 prefetch of this CTA's A rows, PF K blocks ahead of the loads (a wider un-swizzled prefetch box, 256 taps per
+      // instruction via tmPf_*, measured slower: 3.55 ms vs 2.83 ms per 1024-chunk launch)
+      constexpr int PF = 512 / kBK;
       int pf_pair = cluster, pf_nt = 0, pf_kb = 0;
       auto pf_step = [&]() {
         if (pf_pair < P.num_pairs) {
-          const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
-          tma_prefetch_2d(&tmA_hi, pf_kb * kBK, y);
-          tma_prefetch_2d(&tmA_lo, pf_kb * kBK, y);
+          {
+            const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
+            tma_prefetch_2d(&tmA_hi, pf_kb * kBK, y);
+            tma_prefetch_2d(&tmA_lo, pf_kb * kBK, y);
+          }
           if (++pf_kb == nkb) {
             pf_kb = 0;
             if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_pair += n_clusters; }
@@ -97,13 +118,16 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
       };
       for (int i = 0; i < PF; ++i) pf_step();
+      int tk = 0;
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
-        const int ay = pair * 2 * kBM + static_cast<int>(rank) * kBM;
+        const int ay = (P.dbg & 2) ? (cluster * 2 * kBM + static_cast<int>(rank) * kBM)      // bring-up: A always L2 resident
+                                   : pair * 2 * kBM + static_cast<int>(rank) * kBM;
         for (int nt = 0; nt < P.num_n_tiles; ++nt) {
           const int nb = (nt == P.num_n_tiles - 1) ? P.last_bins : kBN;
           for (int kb = 0; kb < nkb; ++kb) {
-            pf_step();
+            if (!(P.dbg & 2)) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
+            if (P.trace && cluster == 0 && tk < 256) P.trace[(0 * 2 + rank) * 256 + tk] = clock64();
             uint8_t* sa_hi = smem + stage * kStageBytes;
             uint8_t* sa_lo = sa_hi + kABytes;
             uint8_t* sb_hi = sa_lo + kABytes;
@@ -116,6 +140,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             tma_load_2d_pair(sa_lo, &tmA_lo, &full_bar[stage], kb * kBK, ay);
             tma_load_2d_pair(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
             tma_load_2d_pair(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
+            if (P.trace && cluster == 0 && tk < 256) P.trace[(1 * 2 + rank) * 256 + tk] = clock64();
+            ++tk;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -126,6 +152,7 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (leader && lane == 0) {
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
+      int tk = 0;
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
         for (int nt = 0; nt < P.num_n_tiles; ++nt) {
           const uint32_t idesc = (nt == P.num_n_tiles - 1) ? P.idesc_last : P.idesc_full;
@@ -133,13 +160,14 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           tcgen05_fence_after();
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full_bar[stage], phase, 300 + stage);
+            if (P.trace && cluster == 0 && tk < 256) P.trace[(2 * 2 + 0) * 256 + tk] = clock64();
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (kb < hk ? 0u : static_cast<uint32_t>(kBN));
             const int kb_acc = kb < hk ? kb : kb - hk;
             const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
             const uint32_t a_lo = a_hi + kABytes, b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
-            const uint64_t da_hi = make_smem_desc(a_hi, 128), da_lo = make_smem_desc(a_lo, 128);
-            const uint64_t db_hi = make_smem_desc(b_hi, 128), db_lo = make_smem_desc(b_lo, 128);
+            const uint64_t da_hi = make_smem_desc(a_hi, kSwz), da_lo = make_smem_desc(a_lo, kSwz);
+            const uint64_t db_hi = make_smem_desc(b_hi, kSwz), db_lo = make_smem_desc(b_lo, kSwz);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t koff = static_cast<uint64_t>(k * 2);
@@ -149,6 +177,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
             umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
             if (kb == nkb - 1) umma_commit_pair(&tmem_full[0], 0x3);     // accumulators complete in both CTAs
+            if (P.trace && cluster == 0 && tk < 256) P.trace[(3 * 2 + 0) * 256 + tk] = clock64();
+            ++tk;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
           acc_phase ^= 1u;
@@ -175,7 +205,7 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         int mcur = tile_taps[b0].first;
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll 1
-        for (int c0 = b0; c0 < b0 + hbins; c0 += 16) {
+        for (int c0 = b0; c0 < b0 + ((P.dbg & 1) ? 0 : hbins); c0 += 16) {
           uint32_t re[16], im[16];
           tmem_ld16(t_acc + c0, re);
           tmem_ld16(t_acc + kBN + c0, im);
@@ -229,7 +259,7 @@ int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st) {
   const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
   P.num_pairs = (m_tiles + 1) / 2;
   P.num_n_tiles = c->n_tiles2;
-  P.num_k_blocks = c->p.n_fft / kBK;
+  P.num_k_blocks = c->p.n_fft / c->fold_bk;
   P.idesc_full = avld_make_idesc(0, 0, 256, 256);
   P.idesc_last = avld_make_idesc(0, 0, 256, c->last_tile_bins);
   P.last_bins = c->last_tile_bins;
@@ -240,17 +270,48 @@ int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st) {
   P.F = c->F;
   P.n_mels = c->M;
   P.nbins_pad = c->nbins_pad;
+  {
+    const char* d = getenv("AVLD_DBG");
+    P.dbg = d ? atoi(d) : 0;
+    static long long* trace_buf = nullptr;
+    if (getenv("AVLD_TRACE") != nullptr) {
+      if (!trace_buf) AVLD_CUDA(cudaMalloc(reinterpret_cast<void**>(&trace_buf), 8 * 256 * sizeof(long long)));
+      P.trace = trace_buf;
+    }
+  }
   static bool configured = false;
   if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(dftf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AVLD_CUDA(cudaFuncSetAttribute(dftf2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<64>::kSmemBytes));
+    AVLD_CUDA(cudaFuncSetAttribute(dftf2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<32>::kSmemBytes));
     configured = true;
   }
   AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
   int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
   if (grid < 2) return AVLD_OK;
   LaunchScope ls(c, ST_STFT_MEL, st);
-  dftf2_kernel<<<grid, kThreads, kSmemBytes, st>>>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B2h_hi, c->tm_B2h_lo, P);
+  if (c->fold_bk == 64)
+    dftf2_kernel<64><<<grid, kThreads, PairCfg<64>::kSmemBytes, st>>>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B2h_hi, c->tm_B2h_lo,
+                                                                      c->tm_A2pf_hi, c->tm_A2pf_lo, P);
+  else
+    dftf2_kernel<32><<<grid, kThreads, PairCfg<32>::kSmemBytes, st>>>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B2h_hi, c->tm_B2h_lo,
+                                                                      c->tm_A2pf_hi, c->tm_A2pf_lo, P);
   AVLD_CUDA(cudaGetLastError());
+  if (P.trace != nullptr) {   // bring-up only: dump the timestamps of this launch
+    std::vector<long long> h(8 * 256);
+    AVLD_CUDA(cudaStreamSynchronize(st));
+    AVLD_CUDA(cudaMemcpy(h.data(), P.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(getenv("AVLD_TRACE"), "w");
+    if (f) {
+      const char* names[4] = {"prod_empty_done", "prod_issued", "mma_full_done", "mma_issued"};
+      for (int e = 0; e < 4; ++e)
+        for (int r = 0; r < 2; ++r) {
+          fprintf(f, "%s r%d", names[e], r);
+          for (int i = 0; i < 256; ++i) fprintf(f, " %lld", h[(e * 2 + r) * 256 + i] - h[0]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
   return AVLD_OK;
 }
 

@@ -40,7 +40,7 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
   if (c->dft_fold) {
     AVLD_TRY(launch_fold(c, n, st));
-    if (c->dft_pair && c->fold_bk == 64 && c->sm_count % 2 == 0) return launch_stft_mel_pair(c, n, st);
+    if (c->dft_pair && c->sm_count % 2 == 0) return launch_stft_mel_pair(c, n, st);
     return launch_stft_mel_folded(c, n, st);
   }
   Gemm3Params P{};
