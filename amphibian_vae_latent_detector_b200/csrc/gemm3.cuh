@@ -49,6 +49,9 @@ struct Gemm3Params {
   __nv_bfloat16* out_hi;    // PLAIN/CONV: split output for the next tensor-core layer
   __nv_bfloat16* out_lo;
   // DFT epilogue
+  const void* a_hi_ptr;     // EPI_DFTF: base pointers / row pitch (bytes) of the A operand, for the L2-prefetch warp
+  const void* a_lo_ptr;
+  long long a_pitch;
   const float* inv2;        // per chunk 2^(-2 s)
   const MelTap* taps;       // [nbins_pad]
   float* melpow;            // [rows][n_mels]
@@ -80,7 +83,7 @@ struct Gemm3Cfg {
 
 // threads per CTA: TMA warp + MMA warp + 4 epilogue warps (8 for the folded STFT, whose epilogue is not overlapped)
 template <int EPI>
-struct Gemm3Threads { static constexpr int value = (EPI == EPI_DFTF) ? 320 : 192; };
+struct Gemm3Threads { static constexpr int value = (EPI == EPI_DFTF) ? 352 : 192; };   // DFTF: + 4 epilogue warps + 1 L2-prefetch warp
 
 template <int BN, int SWZ, int EPI>
 __global__ void __launch_bounds__(Gemm3Threads<EPI>::value, 1)
@@ -157,9 +160,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           }
         }
       };
-      if (FOLD) {
-        for (int i = 0; i < PF; ++i) pf_step();
-      }
+      (void)pf_step;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = P.split_n ? item / P.num_n_tiles : item;
         const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
@@ -174,7 +175,6 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         for (int nt = nt_begin; nt < nt_end; ++nt) {
           for (int kb = 0; kb < nkb; ++kb) {
-            if (FOLD) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
             uint8_t* sa_hi = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sa_lo = sa_hi + Cfg::A_BYTES;
@@ -254,8 +254,45 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
       }
     }
+  } else if (FOLD && warp == 10) {
+    // ------------------------------------------------------------------ L2 prefetch warp (folded STFT only)
+    // The A operand (folded frames) streams from HBM and is re-read once per N tile.  This warp walks the producer's
+    // K-block sequence PFD blocks ahead, paced by the same "stage free" barriers, and pulls the rows of that block into
+    // L2 with plain prefetch instructions (LSU path): the TMA unit's row rate is the scarce resource of this kernel.
+    constexpr int PFD = 6;
+    int stage = 0;
+    uint32_t phase = 0;
+    int pf_item = blockIdx.x, pf_nt = 0, pf_kb = 0;
+    auto issue = [&]() {
+      if (pf_item < n_items) {
+        const long long row0 = static_cast<long long>(pf_item) * Cfg::BM;
+        const char* ph = static_cast<const char*>(P.a_hi_ptr) + row0 * P.a_pitch + static_cast<long long>(pf_kb) * SWZ;
+        const char* pl = static_cast<const char*>(P.a_lo_ptr) + row0 * P.a_pitch + static_cast<long long>(pf_kb) * SWZ;
+#pragma unroll
+        for (int q = 0; q < Cfg::BM / 32; ++q) {
+          const long long off = static_cast<long long>(lane + 32 * q) * P.a_pitch;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + off));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + off));
+        }
+        if (++pf_kb == nkb) {
+          pf_kb = 0;
+          if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_item += gridDim.x; }
+        }
+      }
+    };
+    for (int i = 0; i < PFD; ++i) issue();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1u, 500 + stage);
+          __syncwarp();
+          issue();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..5; 2..9 for the folded STFT)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;

@@ -22,6 +22,9 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
   P.idesc_last = avld_make_idesc(0, 0, 128, c->last_tile_bins);
   P.last_bins = c->last_tile_bins;
   P.a_mode = 0;
+  P.a_hi_ptr = c->d_A2hi;
+  P.a_lo_ptr = c->d_A2lo;
+  P.a_pitch = static_cast<long long>(c->p.n_fft) * 2;
   P.M_total = rows;
   P.N_total = c->ncols;
   P.inv2 = c->d_inv2;
