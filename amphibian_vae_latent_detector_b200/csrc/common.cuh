@@ -106,7 +106,10 @@ struct avld_ctx {
   int dft_fold = 1;
   int n_tiles2 = 0, last_tile_bins = 0;   // 256-bin N tiles; the last one may hold only 128
   int fold_bk = 64;                       // K elements per pipeline stage of the folded GEMM (64: 2 x 96 KB stages, 32: 4 x 48 KB)
-  float* d_xs = nullptr;           // [max_batch][R * hop] normalised, quantised, reflect-padded, pow2-scaled audio (fp32)
+  float4* d_chunk_par = nullptr;   // [max_batch] (scale, pow2, scaled, -) written by prep_kernel, read by fold_kernel
+  const float* cur_x = nullptr;    // operand source of the current pass (set by launch_prep, read by launch_fold)
+  const int16_t* cur_x16 = nullptr;
+  int cur_quantize = 0;
   __half* d_A2hi = nullptr;        // [max_batch * F + 128][n_fft] folded frames, E in columns [0, N/2), O in [N/2, N)
   __half* d_A2lo = nullptr;
   __half* d_B2hi = nullptr;        // [n_tiles2 * 512][N/2]: per tile 256 cos rows then 256 (-sin) rows

@@ -387,7 +387,7 @@ static int build_ctx(avld_ctx* c) {
     AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, fbk, 128, fsw));
     AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
     AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
-    AVLD_TRY(dev_alloc(&c->d_xs, static_cast<size_t>(c->max_batch) * c->R * p.hop));
+    AVLD_TRY(dev_alloc(&c->d_chunk_par, c->max_batch));
   } else {
     const int nf = p.n_fft;
     std::vector<double> win(nf), ct(nf), stab(nf);
@@ -481,7 +481,7 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
-                  c->d_Alo, c->d_xs, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
+                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
                   c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
                   c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)

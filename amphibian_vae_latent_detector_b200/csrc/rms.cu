@@ -21,7 +21,8 @@ struct PrepParams {
   float* y;               // nullable
   __half* a_hi;           // nullable (operand mode)
   __half* a_lo;
-  float* xs;              // nullable (folded STFT): fp32 padded, scaled samples [n][R * hop]
+  float4* chunk_par;      // nullable (folded STFT): per chunk (scale, pow2, scaled flag, -) for fold_kernel, which
+                          // re-applies the normalisation on the fly instead of reading a materialised copy
   float* inv2;
   uint8_t* ok;            // nullable
   float* rms;             // nullable
@@ -63,16 +64,14 @@ struct LoadPcm16 {
 template <typename Load>
 __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, float* s_val, int c);
 
-// Persistent: one 1024-thread CTA per SM walks the chunks.  Each chunk is read twice (sum of squares, then scale);
-// with at most sm_count chunks in flight (148 x 576 KB = 85 MB < 126 MB L2) the second read is an L2 hit.
-__global__ void __launch_bounds__(1024, 1) prep_kernel(const PrepParams P) {
+// One CTA per chunk (a persistent one-CTA-per-SM variant that keeps the second read in L2 measured slower: 89 vs 60 ms
+// per 100k chunks -- too little memory parallelism per SM).
+__global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
   extern __shared__ float s_val[];            // [n_leaves + n_nodes]
-  for (int c = blockIdx.x; c < P.n; c += gridDim.x) {
-    const size_t base = static_cast<size_t>(c) * P.L;
-    if (P.x16 != nullptr) prep_body(P, LoadPcm16{P.x16 + base}, s_val, c);
-    else prep_body(P, LoadF32{P.x + base}, s_val, c);
-    __syncthreads();
-  }
+  const int c = blockIdx.x;
+  const size_t base = static_cast<size_t>(c) * P.L;
+  if (P.x16 != nullptr) prep_body(P, LoadPcm16{P.x16 + base}, s_val, c);
+  else prep_body(P, LoadF32{P.x + base}, s_val, c);
 }
 
 template <typename Load>
@@ -159,6 +158,7 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     s_scaled = scaled;
     s_pow2 = ldexpf(1.0f, s);
     if (P.inv2) P.inv2[c] = ldexpf(1.0f, -2 * (s + P.dft_scale_log2));
+    if (P.chunk_par) P.chunk_par[c] = make_float4(scale, ldexpf(1.0f, s), scaled ? 1.0f : 0.0f, 0.0f);
     if (P.ok) P.ok[c] = P.normalize ? static_cast<uint8_t>(scaled) : static_cast<uint8_t>(1);
     if (P.rms) P.rms[c] = rms;
   }
@@ -182,22 +182,6 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
       }
     } else {
       for (int i = tid; i < P.L; i += blockDim.x) yc[i] = finish_sample(xc(i), scale, scaled, P.quantize);
-    }
-  }
-
-  // ---------------------------------------------------------------- phase 2b': padded fp32 samples for fold_kernel
-  if (P.xs != nullptr) {
-    const float pow2 = s_pow2;
-    const int half = P.n_fft / 2;
-    const int total = P.R * P.hop;
-    float* __restrict__ dst = P.xs + static_cast<size_t>(c) * total;
-    for (int p = tid; p < total; p += blockDim.x) {
-      int src = p - half;                                // np.pad(y, n_fft//2, mode="reflect")
-      if (src < 0) src = -src;
-      if (src >= P.L) src = 2 * (P.L - 1) - src;
-      float v = 0.f;
-      if (p < P.L + P.n_fft) v = finish_sample(xc(src), scale, scaled, P.quantize) * pow2;
-      dst[p] = v;
     }
   }
 
@@ -231,19 +215,34 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
 }
 
 // ------------------------------------------------------------------------------------------------
-// fold_kernel: frames -> even/odd folded fp16 hi/lo operand rows (see common.cuh, "folded STFT")
+// fold_kernel: raw chunk -> even/odd folded fp16 hi/lo operand rows (see common.cuh, "folded STFT").
+//   xs[p] = finish(x[reflect(p - N/2)]) * pow2        (normalise, clip, PCM_16 round trip, power-of-two scale)
 //   E[f][j] = xs[f*hop + k] + xs[f*hop + N - k],  O[f][j] = xs[f*hop + k] - xs[f*hop + N - k],  k = j + 1
-//   (k = N/2: E = xs[f*hop + N/2], O = 0).  One thread = 8 consecutive taps of one frame; a warp reads
-//   two runs of 256 contiguous floats and stores 4 x 512 contiguous bytes.
+//   (k = N/2: E = xs[f*hop + N/2], O = 0).  One thread = 8 consecutive taps of one frame.  The normalisation is
+//   re-applied on the fly (each sample ~10x, from L1/L2) instead of materialising xs: 1.2 MB less HBM traffic per chunk.
 // ------------------------------------------------------------------------------------------------
 struct FoldParams {
-  const float* xs;      // [n][R*hop]
+  const float* x;       // [n][L] or NULL
+  const int16_t* x16;   // [n][L] PCM_16 or NULL
+  const float4* chunk_par;
   __half* a_hi;         // [n*F][n_fft]
   __half* a_lo;
-  int F, hop, n_fft, chunk_stride;
+  int F, hop, n_fft, L, quantize;
+  int vec_ok;           // chunk rows are 16-byte aligned: interior frames may use vector loads
   long long total;      // n * F * (n_fft/2/8) threads
 };
 
+template <bool PCM>
+__device__ __forceinline__ float fold_sample(const FoldParams& P, const float* xf, const int16_t* xi, int p, float scale,
+                                             int scaled, float pow2) {
+  int src = p - (P.n_fft >> 1);                         // np.pad(y, n_fft//2, mode="reflect")
+  if (src < 0) src = -src;
+  if (src >= P.L) src = 2 * (P.L - 1) - src;
+  const float v = PCM ? static_cast<float>(xi[src]) * (1.0f / 32768.0f) : xf[src];
+  return finish_sample(v, scale, scaled, P.quantize) * pow2;
+}
+
+template <bool PCM>
 __global__ void __launch_bounds__(256) fold_kernel(const FoldParams P) {
   const int half = P.n_fft >> 1, per_frame = half >> 3;
   for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < P.total;
@@ -252,16 +251,55 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams P) {
     const int j0 = static_cast<int>(t - row * per_frame) << 3;
     const long long chunk = row / P.F;
     const int f = static_cast<int>(row - chunk * P.F);
-    const float* __restrict__ x = P.xs + chunk * P.chunk_stride + static_cast<long long>(f) * P.hop;
-    // a[q] = x[j0 + 1 + q]: three aligned float4 (j0 .. j0+11), shifted by one; b[q] = x[N - 1 - j0 - q]: two aligned float4
+    const float4 par = P.chunk_par[chunk];
+    const float scale = par.x, pow2 = par.y;
+    const int scaled = par.z != 0.f;
+    const float* xf = PCM ? nullptr : P.x + chunk * P.L;
+    const int16_t* xi = PCM ? P.x16 + chunk * P.L : nullptr;
+    const int pa = f * P.hop + j0;                        // padded index of tap j0 (a[q] is tap j0 + 1 + q)
+    const int pb = f * P.hop + P.n_fft - 8 - j0;          // b[q] is padded index pb + 7 - q
     float a[8], b[8];
-    {
-      const float4* xa = reinterpret_cast<const float4*>(x + j0);
-      const float4 v0 = xa[0], v1 = xa[1], v2 = xa[2];
-      a[0] = v0.y; a[1] = v0.z; a[2] = v0.w; a[3] = v1.x; a[4] = v1.y; a[5] = v1.z; a[6] = v1.w; a[7] = v2.x;
-      const float4* xb = reinterpret_cast<const float4*>(x + (P.n_fft - 8 - j0));
-      const float4 w0 = xb[0], w1 = xb[1];
-      b[7] = w0.x; b[6] = w0.y; b[5] = w0.z; b[4] = w0.w; b[3] = w1.x; b[2] = w1.y; b[1] = w1.z; b[0] = w1.w;
+    const int sa = pa - half, sb = pb - half;             // un-reflected source indices of the two runs
+    if (P.vec_ok && sa >= 0 && sa + 12 <= P.L && sb >= 0 && sb + 8 <= P.L) {
+      // interior: both runs are contiguous in the chunk and 16-byte aligned (hop % 64 == 0, j0 % 8 == 0)
+      float ra[12], rb[8];
+      if (PCM) {
+        const uint4 u0 = *reinterpret_cast<const uint4*>(xi + sa);                 // 8 samples
+        const uint2 u1 = *reinterpret_cast<const uint2*>(xi + sa + 8);             // 4 samples
+        const uint4 w0 = *reinterpret_cast<const uint4*>(xi + sb);
+        const uint32_t wa[6] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y};
+        const uint32_t wb[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          ra[2 * i] = static_cast<float>(static_cast<int16_t>(wa[i] & 0xffffu)) * (1.0f / 32768.0f);
+          ra[2 * i + 1] = static_cast<float>(static_cast<int16_t>(wa[i] >> 16)) * (1.0f / 32768.0f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rb[2 * i] = static_cast<float>(static_cast<int16_t>(wb[i] & 0xffffu)) * (1.0f / 32768.0f);
+          rb[2 * i + 1] = static_cast<float>(static_cast<int16_t>(wb[i] >> 16)) * (1.0f / 32768.0f);
+        }
+      } else {
+        const float4* xa = reinterpret_cast<const float4*>(xf + sa);
+        const float4 v0 = xa[0], v1 = xa[1], v2 = xa[2];
+        ra[0] = v0.x; ra[1] = v0.y; ra[2] = v0.z; ra[3] = v0.w; ra[4] = v1.x; ra[5] = v1.y; ra[6] = v1.z; ra[7] = v1.w;
+        ra[8] = v2.x; ra[9] = v2.y; ra[10] = v2.z; ra[11] = v2.w;
+        const float4* xb = reinterpret_cast<const float4*>(xf + sb);
+        const float4 w0 = xb[0], w1 = xb[1];
+        rb[0] = w0.x; rb[1] = w0.y; rb[2] = w0.z; rb[3] = w0.w; rb[4] = w1.x; rb[5] = w1.y; rb[6] = w1.z; rb[7] = w1.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        a[q] = finish_sample(ra[q + 1], scale, scaled, P.quantize) * pow2;
+        b[q] = finish_sample(rb[7 - q], scale, scaled, P.quantize) * pow2;
+      }
+    } else {
+      // the first / last frames touch the reflect padding
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        a[q] = fold_sample<PCM>(P, xf, xi, pa + 1 + q, scale, scaled, pow2);
+        b[q] = fold_sample<PCM>(P, xf, xi, pb + 7 - q, scale, scaled, pow2);
+      }
     }
     __align__(16) __half eh[8], el[8], oh[8], ol[8];
 #pragma unroll
@@ -285,17 +323,25 @@ __global__ void __launch_bounds__(256) fold_kernel(const FoldParams P) {
 int launch_fold(avld_ctx* c, int n, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
   FoldParams P{};
-  P.xs = c->d_xs;
+  P.x = c->cur_x;
+  P.x16 = c->cur_x16;
+  P.chunk_par = c->d_chunk_par;
   P.a_hi = c->d_A2hi;
   P.a_lo = c->d_A2lo;
   P.F = c->F;
   P.hop = c->p.hop;
   P.n_fft = c->p.n_fft;
-  P.chunk_stride = c->R * c->p.hop;
+  P.L = c->L;
+  P.quantize = c->cur_quantize;
+  P.vec_ok = (c->L % 8 == 0) && (reinterpret_cast<uintptr_t>(P.x) % 16 == 0) && (reinterpret_cast<uintptr_t>(P.x16) % 16 == 0);
   P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / 16);
   const long long blocks = (P.total + 255) / 256;
   const int grid = static_cast<int>(blocks < static_cast<long long>(c->sm_count) * 32 ? blocks : static_cast<long long>(c->sm_count) * 32);
-  { LaunchScope ls(c, ST_FOLD, st); fold_kernel<<<grid, 256, 0, st>>>(P); }
+  {
+    LaunchScope ls(c, ST_FOLD, st);
+    if (P.x16 != nullptr) fold_kernel<true><<<grid, 256, 0, st>>>(P);
+    else fold_kernel<false><<<grid, 256, 0, st>>>(P);
+  }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
@@ -309,7 +355,12 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.y = y_out;
   P.a_hi = (write_operand && !c->dft_fold) ? c->d_Ahi : nullptr;
   P.a_lo = (write_operand && !c->dft_fold) ? c->d_Alo : nullptr;
-  P.xs = (write_operand && c->dft_fold) ? c->d_xs : nullptr;
+  P.chunk_par = (write_operand && c->dft_fold) ? c->d_chunk_par : nullptr;
+  if (write_operand) {      // operand source of this pass, consumed by launch_fold
+    c->cur_x = x;
+    c->cur_x16 = x16;
+    c->cur_quantize = quantize ? 1 : 0;
+  }
   P.inv2 = write_operand ? c->d_inv2 : nullptr;
   P.ok = ok;
   P.rms = rms;
@@ -337,8 +388,7 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
     configured = true;
   }
   P.n = n;
-  const int grid = n < c->sm_count ? n : c->sm_count;
-  { LaunchScope ls(c, ST_PREP, st); prep_kernel<<<grid, 1024, smem, st>>>(P); }
+  { LaunchScope ls(c, ST_PREP, st); prep_kernel<<<n, 512, smem, st>>>(P); }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
