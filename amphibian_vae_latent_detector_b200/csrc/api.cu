@@ -1,6 +1,7 @@
 // api.cu -- whole-path entry points: device-resident encode, host-buffer encode+detect with
 // double-buffered copies, and the GEMM bring-up entry used by the tests.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -157,6 +158,8 @@ extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float*
     const int hb = mode == 0 ? 0 : 1;
     P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(hb, hb, 128, bn);
     P.a_mode = 0;
+    if (const char* e = getenv("AVLD_DBG_SHIFT")) P.dbg_shift = atoi(e);
+    if (const char* e = getenv("AVLD_DBG_BASEOFF")) P.dbg_baseoff = atoi(e);
     P.M_total = M;
     P.N_total = N;
     P.out_f32 = C;

@@ -31,6 +31,7 @@ enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2, EPI_DFTF = 3 };
 
 struct Gemm3Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
+  int dbg_shift, dbg_baseoff;   // bring-up probe: A descriptor start shifted by dbg_shift rows, descriptor base-offset field
   int split_n;  // 1: a work item is one (m tile, n tile) pair (dense layers with few m tiles); 0: one m tile, all n tiles
   uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
   uint32_t idesc_last;                    // EPI_DFTF: descriptor of the last N tile when it holds only last_bins bins
@@ -237,7 +238,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t a_lo = a_hi + Cfg::A_BYTES;
             const uint32_t b_hi = a_lo + Cfg::A_BYTES;
             const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-            const uint64_t da_hi = make_smem_desc(a_hi, SWZ), da_lo = make_smem_desc(a_lo, SWZ);
+            const uint64_t dbg_bits = (static_cast<uint64_t>(P.dbg_baseoff & 7) << 49) + static_cast<uint64_t>((P.dbg_shift * SWZ) >> 4);
+            const uint64_t da_hi = make_smem_desc(a_hi, SWZ) + dbg_bits, da_lo = make_smem_desc(a_lo, SWZ) + dbg_bits;
             const uint64_t db_hi = make_smem_desc(b_hi, SWZ), db_lo = make_smem_desc(b_lo, SWZ);
 #pragma unroll
             for (int k = 0; k < Cfg::BK / 16; ++k) {
