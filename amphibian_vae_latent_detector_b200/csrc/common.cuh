@@ -57,7 +57,8 @@ struct PairNode {
 
 // encoder layer on the device
 struct LayerDev {
-  int kind;  // 0 conv (tcgen05), 1 linear (tcgen05), 2 conv direct (CUDA cores, tiny C_in)
+  int kind;  // 0 conv (tcgen05, one box per tap), 1 linear (tcgen05), 2 conv direct (CUDA cores, tiny C_in),
+             // 3 conv (tcgen05, halo reuse: convh.cu)
   int c_in, c_out, ksize, stride, pad, relu, pool;
   int in_h, in_w, out_h, out_w;  // out = after pooling
   int bn, swz, cblk, cblocks;    // tcgen05 tiling
@@ -196,6 +197,10 @@ int launch_fold(avld_ctx* c, int n, cudaStream_t st);
 int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
+int convh_encode_input_map(CUtensorMap* out, const void* base, int n, int H, int W, int C, int cblk);
+bool convh_supported(int c_in, int c_out, int ksize, int w);
+int launch_convh(const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
+                 __nv_bfloat16* out_lo, int sm_count, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
 int launch_split_f16(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t st);
 

@@ -10,6 +10,8 @@
 //   linears                         plain GEMM on tcgen05 over the flattened NHWC activations
 // Activations and weights are bf16 hi + bf16 lo pairs (3 MMAs per K step, ~2^-17 relative error).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "gemm3.cuh"
@@ -233,6 +235,9 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
         conv_direct_kernel<<<grid, 256, smem, st>>>(P);
       }
       AVLD_CUDA(cudaGetLastError());
+    } else if (L.kind == 3) {
+      LaunchScope ls(c, ST_CONV_GEMM, st);
+      AVLD_TRY(launch_convh(L, c->tm_act_hi[li], c->tm_act_lo[li], n, out_hi, out_lo, c->sm_count, st));
     } else if (L.kind == 0) {
       Gemm3Params P{};
       const int H = L.in_h, W = L.in_w;  // same-size convolution
@@ -334,6 +339,8 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
         AVLD_TRY(launch_split_bf16(L.w_f32, L.w_hi, L.w_lo, wcount, nullptr));
         AVLD_TRY(encode_tmap_2d(&L.tm_w_hi, L.w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, L.cblk, L.bn, L.swz));
         AVLD_TRY(encode_tmap_2d(&L.tm_w_lo, L.w_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, s.c_out, L.K * 2, L.cblk, L.bn, L.swz));
+        const char* cm = getenv("AVLD_CONV_MODE");       // "tap" keeps the one-box-per-tap kernel (A/B comparisons)
+        if (!(cm != nullptr && strcmp(cm, "tap") == 0) && L.pool <= 2 && convh_supported(s.c_in, s.c_out, s.ksize, w)) L.kind = 3;
       }
       h = L.out_h; w = L.out_w; ch = s.c_out;
       out_elems = static_cast<size_t>(h) * w * ch;
@@ -384,7 +391,10 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
     const LayerDev& L = out[li];
     const __nv_bfloat16* in_hi = c->d_act_hi[(li - 1) & 1];
     const __nv_bfloat16* in_lo = c->d_act_lo[(li - 1) & 1];
-    if (L.kind == 0) {
+    if (L.kind == 3) {
+      AVLD_TRY(convh_encode_input_map(&c->tm_act_hi[li], in_hi, c->max_batch, L.in_h, L.in_w, L.c_in, L.cblk));
+      AVLD_TRY(convh_encode_input_map(&c->tm_act_lo[li], in_lo, c->max_batch, L.in_h, L.in_w, L.c_in, L.cblk));
+    } else if (L.kind == 0) {
       const uint64_t dims[4] = {static_cast<uint64_t>(L.c_in), static_cast<uint64_t>(L.in_w), static_cast<uint64_t>(L.in_h),
                                 static_cast<uint64_t>(c->max_batch)};
       const uint64_t strides[3] = {static_cast<uint64_t>(L.c_in) * 2, static_cast<uint64_t>(L.in_w) * L.c_in * 2,
