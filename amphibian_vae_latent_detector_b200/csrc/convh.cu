@@ -144,13 +144,17 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the (warp-uniform) schedule so that addresses and descriptors live in uniform registers;
+    // one elected lane issues.  With `if (lane == 0)` around the loop every UTCHMMA paid ~75 cycles of R2UR traffic,
+    // which made the small N = 64 MMAs (32 tensor cycles each) issue bound.
+    {
       int hs = 0, ws = 0, acc = 0;
       uint32_t hphase = 0, wphase = 0, acc_phase = 0;
       if (resident) {
         mbar_wait(&w_full[0], 0, 250);
         tcgen05_fence_after();
       }
+      const uint64_t sbo_fix = (static_cast<uint64_t>((kHW * ROWB) >> 4) << 32) - (static_cast<uint64_t>((8 * ROWB) >> 4) << 32);
       for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
         tcgen05_fence_after();
@@ -159,6 +163,8 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait(&h_full[hs], hphase, 300 + hs);
           tcgen05_fence_after();
           const uint32_t halo_hi = smem_u32(s_halo + hs * Cfg::HSTAGE), halo_lo = halo_hi + Cfg::HALO_BYTES;
+          const uint64_t dh_hi = make_smem_desc(halo_hi, ROWB) + sbo_fix, dh_lo = make_smem_desc(halo_lo, ROWB) + sbo_fix;
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             uint32_t w_hi;
             if (resident) {
@@ -168,30 +174,32 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               tcgen05_fence_after();
               w_hi = smem_u32(s_w + ws * Cfg::WSTAGE);
             }
-            const uint32_t w_lo = w_hi + Cfg::WBLK;
             const int kh = tap / 3, kw = tap - kh * 3;
-            const uint32_t shift = static_cast<uint32_t>((kh * kHW + kw) * ROWB);
             // A: 16 groups of 8 pixel rows; group stride = halo pitch (10 rows); swizzle follows absolute addresses
-            const uint64_t sbo_fix = (static_cast<uint64_t>((kHW * ROWB) >> 4) << 32) - (static_cast<uint64_t>((8 * ROWB) >> 4) << 32);
-            const uint64_t da_hi = make_smem_desc(halo_hi + shift, ROWB) + sbo_fix;
-            const uint64_t da_lo = make_smem_desc(halo_lo + shift, ROWB) + sbo_fix;
-            const uint64_t db_hi = make_smem_desc(w_hi, ROWB), db_lo = make_smem_desc(w_lo, ROWB);
+            const uint64_t shift = static_cast<uint64_t>(((kh * kHW + kw) * ROWB) >> 4);
+            const uint64_t da_hi = dh_hi + shift, da_lo = dh_lo + shift;
+            const uint64_t db_hi = make_smem_desc(w_hi, ROWB), db_lo = db_hi + static_cast<uint64_t>(Cfg::WBLK >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < CBLK / 16; ++k) {
-              const uint64_t koff = static_cast<uint64_t>(k * 2);
-              umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
-              umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              for (int k = 0; k < CBLK / 16; ++k) {
+                const uint64_t koff = static_cast<uint64_t>(k * 2);
+                umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              }
+              if (!resident) umma_commit(&w_empty[ws]);
             }
+            __syncwarp();
             if (!resident) {
-              umma_commit(&w_empty[ws]);
               if (++ws == wstages) { ws = 0; wphase ^= 1u; }
             }
           }
-          umma_commit(&h_empty[hs]);
+          if (elect_one()) umma_commit(&h_empty[hs]);
+          __syncwarp();
           if (++hs == hstages) { hs = 0; hphase ^= 1u; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
