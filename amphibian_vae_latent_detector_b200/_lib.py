@@ -62,6 +62,8 @@ _SIGNATURES = {
     "avld_order_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(RankQuery), C.c_int32,
                                    C.POINTER(C.c_float), _P]),
     "avld_decide": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "avld_map_score": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "avld_cov_accumulate": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "avld_encode_detect_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "avld_encode_detect_host_pcm16": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "avld_pairwise_plan": (C.c_int64, [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64]),

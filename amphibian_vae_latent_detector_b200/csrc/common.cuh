@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...);
 // kernel families, for the launch counter and the optional per-stage CUDA-event timing
 enum Stage {
   ST_PREP = 0, ST_STFT_MEL, ST_LOGMEL_POST, ST_CONV_DIRECT, ST_CONV_GEMM, ST_DENSE_GEMM, ST_RADII, ST_DECIDE,
-  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_FOLD, ST_COUNT
+  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_FOLD, ST_MAP, ST_COUNT
 };
 
 #define AVLD_CUDA(expr)                                                                       \

@@ -540,7 +540,7 @@ extern "C" int avld_stage_count(void) { return ST_COUNT; }
 extern "C" const char* avld_stage_name(int stage) {
   static const char* names[ST_COUNT] = {"prep_kernel", "gemm3_kernel<DFT>", "logmel_post_kernel", "conv_direct_kernel",
                                         "gemm3_kernel<CONV>", "gemm3_kernel<PLAIN>", "radii_kernel", "decide_kernel",
-                                        "centroid_kernel", "select_hist_kernel", "split_kernel", "fold_kernel"};
+                                        "centroid_kernel", "select_hist_kernel", "split_kernel", "fold_kernel", "map_kernels"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 

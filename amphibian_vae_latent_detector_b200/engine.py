@@ -26,6 +26,7 @@ import torch
 
 from . import _lib
 from .radial_fit import RadialFit, fit_radial
+from .map_fit import MapFit, fit_map
 from .encoder import ConvOp, EncoderProgram, LinearOp, export_program
 
 DEFAULTS = dict(sr=48000, n_fft=2048, hop_length=384, n_mels=64, fmin=150.0, fmax=15000.0, target_frames=192,
@@ -255,6 +256,46 @@ class Engine:
             self._h, xt.data_ptr(), n, int(pcm16), centroid.ctypes.data, thr.ctypes.data, priority_rank.ctypes.data, K,
             pred.ctypes.data, best.ctypes.data, None if mu is None else mu.ctypes.data, ok.ctypes.data))
         return pred, best, ok, mu
+
+    # ------------------------------------------------------------------ N1: Gaussian-MAP detector
+    def cov_accumulate(self, Z: torch.Tensor, label: torch.Tensor, mean: torch.Tensor, k_sel: int = -1,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """float64 second moments of centred latents (08b:60-81, :276-296); ``k_sel < 0`` pools all classes (LDA)."""
+        Z = self._dev(Z, torch.float32, "Z")
+        label = self._dev(label, torch.int32, "label")
+        mean = self._dev(mean, torch.float32, "mean")
+        K, D = mean.shape
+        if out is None:
+            out = torch.zeros(D, D, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.avld_cov_accumulate(self._h, _ptr(Z), _ptr(label), _ptr(mean), int(k_sel), _ptr(out),
+                                                Z.shape[0], K, D, _stream()))
+        return out
+
+    def map_score(self, Z: torch.Tensor, fit: MapFit, want_scores: bool = False, tau: Optional[float] = "fit"):
+        """-> ``(pred [n] int32 index into fit.species or -1, best [n] f64, scores [n,K] f64 | None)``
+        (09n:114-140, 10b:146-169)."""
+        Z = self._dev(Z, torch.float32, "Z")
+        K, D = fit.means.shape
+        a, lp = fit.constants()
+        dev = self.device
+        mean = torch.from_numpy(np.ascontiguousarray(fit.means, np.float32)).to(dev)
+        prec = torch.from_numpy(np.ascontiguousarray(fit.precision, np.float32)).to(dev)
+        a_d, lp_d = torch.from_numpy(a).to(dev), torch.from_numpy(lp).to(dev)
+        n = Z.shape[0]
+        pred = torch.empty(n, dtype=torch.int32, device=dev)
+        best = torch.empty(n, dtype=torch.float64, device=dev)
+        scores = torch.empty(n, K, dtype=torch.float64, device=dev) if want_scores else None
+        t = fit.tau if tau == "fit" else tau
+        _lib.check(self.lib.avld_map_score(self._h, _ptr(Z), _ptr(mean), _ptr(prec), _ptr(a_d), _ptr(lp_d),
+                                           float(t) if t is not None else 0.0, int(t is not None), _ptr(pred), _ptr(best),
+                                           _ptr(scores), n, K, D, _stream()))
+        return pred, best, scores
+
+    def fit_map(self, Z: torch.Tensor, label: torch.Tensor, species_names: Sequence[str], **kw) -> MapFit:
+        """See :func:`map_fit.fit_map` (08b_fit_map_detector.py:255-319)."""
+        Z = self._dev(Z, torch.float32, "Z")
+        label = self._dev(label, torch.int32, "label")
+        return fit_map(self, Z, label, species_names, **kw)
 
     # ------------------------------------------------------------------ bring-up entry of the tcgen05 GEMM core
     def dbg_gemm(self, A: torch.Tensor, B: torch.Tensor, mode: int = 1) -> torch.Tensor:

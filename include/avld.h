@@ -149,6 +149,22 @@ int avld_order_stats(avld_ctx* ctx, const float* radii, const int32_t* label, in
 int avld_decide(avld_ctx* ctx, const float* radii, const double* thr, const int32_t* priority_rank,
                 int32_t* pred, float* best_d, int64_t n, int32_t K, void* stream);
 
+/* ---- N1: Gaussian-MAP detector on latents (map_detector_core.py:319-323; 09n_evaluate_wav_detection.py:114-140;
+ * 10b_benchmark_folder_detection_map.py:146-169) ------------------------------------------------------------------
+ * score[i,k] = -0.5 * (d^T P_k d + a_const[k]) + log_prior[k], d = Z[i] - mean[k], a_const = logdet_cov + D ln(2 pi),
+ * log_prior = ln(prior + 1e-12); the quadratic form is accumulated in float32 (as `diff.T @ prec @ diff` is), the rest in
+ * float64.  pred[i] = first k (caller passes the species in sorted-name order) with the strictly largest score, or -1
+ * when use_tau and best < tau; best[i] = the largest score.  mean dev [K,D] f32, precision dev [K,D,D] f32, a_const /
+ * log_prior dev [K] f64, scores dev [n,K] f64 or NULL.  D <= 256. */
+int avld_map_score(avld_ctx* ctx, const float* Z, const float* mean, const float* precision, const double* a_const,
+                   const double* log_prior, double tau, int use_tau, int32_t* pred, double* best, double* scores,
+                   int64_t n, int32_t K, int32_t D, void* stream);
+/* second moments for the MAP fit (08b_fit_map_detector.py:60-81, :276-296: np.cov of centred latents, float64):
+ * out[D,D] (dev f64, ACCUMULATES) += sum over rows with label == k_sel (k_sel < 0: every labelled row, each centred by
+ * its own class mean = the LDA pooling) of (z - mean[label]) (z - mean[label])^T. */
+int avld_cov_accumulate(avld_ctx* ctx, const float* Z, const int32_t* label, const float* mean, int32_t k_sel,
+                        double* out, int64_t n, int32_t K, int32_t D, void* stream);
+
 /* ---- end to end with HOST buffers (the call the drop-in Python layer makes per batch) -----------
  * x_host float32 [n, chunk_len] (pinned or pageable) -> pred_host int32 [n], best_host float32 [n],
  * mu_host float32 [n, D] (nullable), ok_host uint8 [n] (nullable).  centroid/thr/priority_rank are

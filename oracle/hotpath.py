@@ -264,3 +264,99 @@ def decide_batch(Z: np.ndarray, species: Sequence[str], centroids: np.ndarray, t
         for k, s in enumerate(species):
             radii[i, k] = l2(z - cd[s])
     return pred, best, radii
+
+
+# ----------------------------------------------------------------------------------------
+# N1: Gaussian-MAP detector
+#   map_detector_core.py:306-323 (inv_and_logdet, gaussian_logpdf_from_precision)
+#   08b_fit_map_detector.py:60-81 (estimate_cov), :255-319 (fit)
+#   09n_evaluate_wav_detection.py:114-140 / 10b_benchmark_folder_detection_map.py:146-169 (decision)
+# ----------------------------------------------------------------------------------------
+def inv_and_logdet(cov: np.ndarray) -> Tuple[np.ndarray, float]:
+    """core:306-316."""
+    sign, ld = np.linalg.slogdet(cov)
+    if sign <= 0:
+        d = cov.shape[0]
+        cov2 = cov + (1e-3 * np.eye(d, dtype=cov.dtype))
+        sign, ld = np.linalg.slogdet(cov2)
+        if sign <= 0:
+            raise RuntimeError("Covarianza no PD incluso tras regularización.")
+        cov = cov2
+    prec = np.linalg.inv(cov).astype(np.float32)
+    return prec, float(ld)
+
+
+def gaussian_logpdf_from_precision(z: np.ndarray, mu: np.ndarray, prec: np.ndarray, logdet_cov: float) -> float:
+    """core:319-323."""
+    d = int(z.shape[0])
+    diff = (z - mu).astype(np.float32)
+    quad = float(diff.T @ prec @ diff)
+    return -0.5 * (quad + float(logdet_cov) + d * float(np.log(2.0 * np.pi)))
+
+
+def estimate_cov(Z: np.ndarray, eps: float, shrink: float, cov_structure: str) -> np.ndarray:
+    """08b:60-81."""
+    n, d = Z.shape
+    if n < 2:
+        cov = np.eye(d, dtype=np.float32)
+    else:
+        cov = np.cov(Z, rowvar=False, bias=False).astype(np.float32)
+    if cov_structure == "diag":
+        cov = np.diag(np.diag(cov)).astype(np.float32)
+    if shrink > 0:
+        avg_var = float(np.mean(np.diag(cov))) if d > 0 else 1.0
+        cov = (1.0 - shrink) * cov + shrink * (avg_var * np.eye(d, dtype=np.float32))
+    cov = cov + (eps * np.eye(d, dtype=np.float32))
+    return cov.astype(np.float32)
+
+
+def fit_map(Z_by_species: Dict[str, np.ndarray], *, cov_type="lda", cov_structure="full", priors="empirical",
+            eps=1e-6, shrink=0.0, set_tau_q=None):
+    """08b:255-319 on in-memory latents -> dict(means, cov, precision, logdet_cov, priors, tau, scores_true)."""
+    species = sorted(Z_by_species.keys())
+    K = len(species)
+    if priors == "uniform":
+        pri = {sp: 1.0 / K for sp in species}
+    else:
+        total = float(sum(Z_by_species[sp].shape[0] for sp in species))
+        pri = {sp: float(Z_by_species[sp].shape[0]) / total for sp in species}
+    means = {sp: np.mean(Z_by_species[sp], axis=0).astype(np.float32) for sp in species}
+    covs, precs, logdets = {}, {}, {}
+    if cov_type == "lda":
+        Zc = np.concatenate([Z_by_species[sp] - means[sp][None, :] for sp in species], axis=0)
+        cov_shared = estimate_cov(Zc, eps=float(eps), shrink=float(shrink), cov_structure=cov_structure)
+        prec_shared, logdet_shared = inv_and_logdet(cov_shared)
+        for sp in species:
+            covs[sp], precs[sp], logdets[sp] = cov_shared, prec_shared, logdet_shared
+    else:
+        for sp in species:
+            Zc = Z_by_species[sp] - means[sp][None, :]
+            covs[sp] = estimate_cov(Zc, eps=float(eps), shrink=float(shrink), cov_structure=cov_structure)
+            precs[sp], logdets[sp] = inv_and_logdet(covs[sp])
+    scores_true: List[float] = []
+    for sp in species:
+        lp = float(np.log(pri[sp] + 1e-12))
+        scores_true.extend(gaussian_logpdf_from_precision(z, means[sp], precs[sp], logdets[sp]) + lp
+                           for z in Z_by_species[sp])
+    arr = np.array(scores_true, dtype=np.float64)
+    tau = float(np.quantile(arr, float(set_tau_q))) if set_tau_q is not None else None
+    return dict(species=species, means=means, cov=covs, precision=precs, logdet_cov=logdets, priors=pri, tau=tau,
+                scores_true=arr)
+
+
+def decide_map_one(z: np.ndarray, species: Sequence[str], means, precisions, logdets, priors, tau):
+    """09n:114-140 -> (detected, species | None, best_score)."""
+    best_sp, best_score = None, -float("inf")
+    for sp in species:
+        mu, prec = means[sp], precisions[sp]
+        if mu.shape[0] != z.shape[0] or prec.shape[0] != z.shape[0] or prec.shape[1] != z.shape[0]:
+            continue
+        lp = float(np.log(float(priors.get(sp, 1e-12)) + 1e-12))
+        s = gaussian_logpdf_from_precision(z, mu, prec, logdets[sp]) + lp
+        if s > best_score:
+            best_score, best_sp = s, sp
+    if best_sp is None:
+        return False, None, best_score
+    if tau is not None and best_score < float(tau):
+        return False, None, best_score
+    return True, best_sp, best_score
