@@ -461,3 +461,190 @@ def detect_species(wav_path, *, config_path=None, encoder_pt=None, encoder_yaml=
                              hop_length=hop_length, n_fft=n_fft, target_frames=target_frames)
     det, sp, _ = _decide_many(z[None], centroids, thresholds)[0]
     return det, sp
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Row N1 -- Gaussian-MAP detector: map_detector_core.py:306-420, 08b_fit_map_detector.py:60-81,
+# 09n_evaluate_wav_detection.py:51-140, 10b_benchmark_folder_detection_map.py:88-169
+# ----------------------------------------------------------------------------------------------------------
+from .map_fit import MapFit, inv_and_logdet, regularise_cov  # noqa: E402  (inv_and_logdet: core:306-316, host D x D)
+
+
+def estimate_cov(Z: np.ndarray, eps: float, shrink: float, cov_structure: str) -> np.ndarray:
+    """08b:60-81: covariance of the rows of ``Z`` (second moments on the GPU in float64) + diag / shrink / eps I."""
+    Z = np.ascontiguousarray(Z, dtype=np.float32)
+    n, d = Z.shape
+    if n < 2:
+        cov = np.eye(d, dtype=np.float32)
+    else:
+        eng = _engine(144000, 0)
+        Zd = _dev_rows(Z)
+        lab = torch.zeros(n, dtype=torch.int32, device=eng.device)
+        zero = torch.zeros(1, d, dtype=torch.float32, device=eng.device)
+        S = eng.cov_accumulate(Zd, lab, zero, 0).cpu().numpy()
+        s1, _ = eng.centroid_accumulate(Zd, lab, 1)
+        m = s1[0].cpu().numpy() / n
+        cov = ((S - n * np.outer(m, m)) / (n - 1)).astype(np.float32)
+    return regularise_cov(cov, float(eps), float(shrink), cov_structure)
+
+
+def gaussian_logpdf_from_precision(z: np.ndarray, mu: np.ndarray, prec: np.ndarray, logdet_cov: float) -> float:
+    """core:319-323 (one latent; batches go through ``Engine.map_score``)."""
+    d = int(z.shape[0])
+    fit = MapFit(["_"], np.zeros(1, np.int32), np.asarray(mu, np.float32)[None], np.zeros((1, d, d), np.float32),
+                 np.asarray(prec, np.float32)[None], np.array([float(logdet_cov)]), np.array([1.0 - 1e-12]), None,
+                 np.ones(1, np.int64))
+    eng = _engine(144000, 0)
+    _, best, _ = eng.map_score(_dev_rows(np.asarray(z, np.float32)[None]), fit)
+    return float(best[0].item())
+
+
+def get_priors_from_map_meta(cfg: Dict[str, Any], species: List[str]) -> Dict[str, float]:
+    """core:326-355."""
+    priors: Dict[str, float] = {}
+    md = cfg.get("map_detector", {})
+    meta = md.get("meta_fit", {}) if isinstance(md, dict) else {}
+    per = meta.get("per_species", {}) if isinstance(meta, dict) else {}
+    ok = True
+    for sp in species:
+        try:
+            priors[sp] = float(per.get(sp, {}).get("prior"))
+        except Exception:
+            ok = False
+            break
+    if ok and priors:
+        s = sum(max(0.0, v) for v in priors.values())
+        if s > 0:
+            priors = {k: max(0.0, v) / s for k, v in priors.items()}
+        return priors
+    K = len(species)
+    return {sp: 1.0 / K for sp in species} if K else {}
+
+
+def get_chunk_seconds_for_map(cfg: Dict[str, Any]) -> float:
+    """core:358-370."""
+    md = cfg.get("map_detector", {})
+    if isinstance(md, dict):
+        meta = md.get("meta_fit", {})
+        if isinstance(meta, dict) and "chunk_seconds" in meta:
+            try:
+                return float(meta["chunk_seconds"])
+            except Exception:
+                pass
+    try:
+        return float(cfg.get("chunk_seconds", 5.0))
+    except Exception:
+        return 5.0
+
+
+def read_map_detector_params(cfg: Dict[str, Any]):
+    """core:373-420 -> ``(means, precisions, logdets, tau)``."""
+    md = cfg.get("map_detector", None)
+    if not isinstance(md, dict):
+        raise ValueError("config.json no contiene map_detector (dict). Ejecuta antes 08b_fit_map_detector.py")
+    if md.get("model", "") != "gaussian_map":
+        raise ValueError(f"map_detector.model inesperado: {md.get('model')}")
+    means_raw, prec_raw, logdet_raw = md.get("means"), md.get("precision"), md.get("logdet_cov")
+    if not isinstance(means_raw, dict) or not isinstance(prec_raw, dict) or not isinstance(logdet_raw, dict):
+        raise ValueError("map_detector debe contener 'means', 'precision' y 'logdet_cov' como dicts.")
+    means = {sp: np.array(v, dtype=np.float32) for sp, v in means_raw.items()
+             if isinstance(sp, str) and isinstance(v, list) and len(v) > 0}
+    precisions: Dict[str, np.ndarray] = {}
+    for sp, mat in prec_raw.items():
+        if isinstance(sp, str) and isinstance(mat, list) and len(mat) > 0:
+            Pm = np.array(mat, dtype=np.float32)
+            if Pm.ndim != 2 or Pm.shape[0] != Pm.shape[1]:
+                raise ValueError(f"precision[{sp}] debe ser matriz cuadrada, obtuve shape={Pm.shape}")
+            precisions[sp] = Pm
+    logdets = {sp: float(v) for sp, v in logdet_raw.items() if isinstance(sp, str)}
+    tau = md.get("tau", None)
+    if not means or not precisions or not logdets:
+        raise ValueError("means/precision/logdet_cov vacíos o mal formateados en config.json.")
+    return means, precisions, logdets, (float(tau) if tau is not None else None)
+
+
+def _map_fit_from_params(means, precisions, logdets, priors, tau, D: int) -> Optional[MapFit]:
+    species = sorted(set(means) & set(precisions) & set(logdets))
+    species = [sp for sp in species if means[sp].shape[0] == D and precisions[sp].shape == (D, D)]   # 09n:120-123
+    if not species:
+        return None
+    pri = np.array([float(priors.get(sp, 1e-12)) for sp in species], dtype=np.float64)
+    return MapFit(species, np.arange(len(species), dtype=np.int32), np.stack([means[sp] for sp in species]),
+                  np.zeros((len(species), D, D), np.float32), np.stack([precisions[sp] for sp in species]),
+                  np.array([logdets[sp] for sp in species], dtype=np.float64), pri, tau,
+                  np.zeros(len(species), np.int64))
+
+
+def _decide_map_many(Z: np.ndarray, means, precisions, logdets, priors, tau):
+    fit = _map_fit_from_params(means, precisions, logdets, priors, tau, Z.shape[1])
+    if fit is None or Z.shape[0] == 0:
+        return [(False, None, -float("inf"))] * Z.shape[0]
+    eng = _engine(144000, 0)
+    pred, best, _ = eng.map_score(_dev_rows(Z), fit)
+    pred, best = pred.cpu().numpy(), best.cpu().numpy()
+    return [(bool(p >= 0), fit.species[p] if p >= 0 else None, float(b)) for p, b in zip(pred, best)]
+
+
+class MapDetectorSession:
+    """10b:88-169: MAP analogue of :class:`DetectorSession`."""
+
+    def __init__(self, project_root: Path = Path("."), config_path: Path = Path("config.json"),
+                 encoder_pt: Path = Path("model.pt"), encoder_yaml: Path = Path("model.yaml"), device: str = "cpu",
+                 sr: int = 48000, n_mels: int = 64, target_frames: int = 192, fmin: float = 150.0,
+                 fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048):
+        self.project_root, self.config_path = Path(project_root), Path(config_path)
+        self.encoder_pt, self.encoder_yaml, self.device = Path(encoder_pt), Path(encoder_yaml), device
+        self.sr, self.n_mels, self.target_frames = sr, n_mels, target_frames
+        self.fmin, self.fmax, self.hop_length, self.n_fft = fmin, fmax, hop_length, n_fft
+        self.means, self.precisions, self.logdets, self.priors = {}, {}, {}, {}
+        self.tau: Optional[float] = None
+        self.species: List[str] = []
+        self.duration = 5.0
+        self.encoder: Optional[torch.nn.Module] = None
+
+    def load(self) -> None:
+        cfg = load_json(self.config_path)
+        self.set_params(cfg)
+        self.encoder = load_encoder(self.encoder_pt, self.encoder_yaml, self.project_root, self.device)
+
+    def set_params(self, cfg: Dict[str, Any]) -> None:
+        self.means, self.precisions, self.logdets, self.tau = read_map_detector_params(cfg)
+        self.species = sorted(set(self.means) & set(self.precisions) & set(self.logdets))
+        if not self.species:
+            raise RuntimeError("map_detector inconsistente: no hay intersección entre means/precision/logdet_cov.")
+        self.priors = get_priors_from_map_meta(cfg, self.species)
+        self.duration = float(get_chunk_seconds_for_map(cfg))
+
+    def _mel_kw(self):
+        return dict(sr=self.sr, duration=self.duration, n_mels=self.n_mels, fmin=self.fmin, fmax=self.fmax,
+                    hop_length=self.hop_length, n_fft=self.n_fft, target_frames=self.target_frames)
+
+    def predict_one(self, wav_path: Path) -> Tuple[bool, Optional[str], float]:
+        z = encode_wav_to_latent(self.encoder, wav_path, self.device, **self._mel_kw())
+        return _decide_map_many(z[None], self.means, self.precisions, self.logdets, self.priors, self.tau)[0]
+
+    def predict_many(self, wav_paths: Sequence[Path]) -> List[Tuple[bool, Optional[str], float]]:
+        Z, failed = encode_wavs_to_latents(self.encoder, wav_paths, self.device, return_failed=True, **self._mel_kw())
+        good = iter(_decide_map_many(Z, self.means, self.precisions, self.logdets, self.priors, self.tau))
+        bad = set(map(str, failed))
+        return [(False, "ERROR", float("nan")) if str(p) in bad else next(good) for p in wav_paths]
+
+
+def detect_species_map(wav_path, *, config_path=None, encoder_pt=None, encoder_yaml=None, device: str = "cpu",
+                       sr: int = 48000, n_mels: int = 64, target_frames: int = 192, fmin: float = 150.0,
+                       fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048,
+                       encoder: Optional[torch.nn.Module] = None) -> Tuple[bool, Optional[str], float]:
+    """09n:51-140 -> ``(detected, species | None, best_score)``."""
+    wav_p = Path(wav_path).expanduser()
+    if not wav_p.is_absolute():
+        wav_p = (Path.cwd() / wav_p).resolve()
+    if not wav_p.exists():
+        raise FileNotFoundError(f"No existe WAV: {wav_p}")
+    root = Path.cwd()
+    sess = MapDetectorSession(root, Path(config_path).expanduser().resolve() if config_path else root / "config.json",
+                              Path(encoder_pt) if encoder_pt else root / "models" / "model.pt",
+                              Path(encoder_yaml) if encoder_yaml else root / "models" / "model.yaml", device, sr, n_mels,
+                              target_frames, fmin, fmax, hop_length, n_fft)
+    sess.set_params(load_json(sess.config_path))
+    sess.encoder = encoder if encoder is not None else load_encoder(sess.encoder_pt, sess.encoder_yaml, root, device)
+    return sess.predict_one(wav_p)
