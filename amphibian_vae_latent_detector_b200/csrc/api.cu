@@ -1,8 +1,10 @@
 // api.cu -- whole-path entry points: device-resident encode, host-buffer encode+detect with
 // double-buffered copies, and the GEMM bring-up entry used by the tests.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm3.cuh"
@@ -71,6 +73,17 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
   AVLD_CUDA(cudaMemcpyAsync(c->d_thr, thr, K * sizeof(double), cudaMemcpyHostToDevice, sc));
   AVLD_CUDA(cudaMemcpyAsync(c->d_prio, priority_rank, K * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
 
+  // AVLD_HOST_TRACE=<file>: per-slab device timeline (copy start/end, compute start/end, ms since the first copy)
+  const char* trace_path = getenv("AVLD_HOST_TRACE");
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t s) {
+    if (!trace_path) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    tev.push_back(e);
+  };
+
   // slab i: H2D on the copy stream into buffer i&1 while the compute stream works on slab i-1;
   // results of slab i are read back on the compute stream right after its kernels.
   int64_t slab = 0;
@@ -78,10 +91,13 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
     const int b = static_cast<int>(slab & 1);
     if (slab >= 2) AVLD_CUDA(cudaStreamWaitEvent(sx, c->ev_done[b], 0));   // buffer b free again
+    mark(sx);
     AVLD_CUDA(cudaMemcpyAsync(c->d_xbuf[b], static_cast<const char*>(x_host) + static_cast<size_t>(i) * c->L * sample_bytes,
                               static_cast<size_t>(m) * c->L * sample_bytes, cudaMemcpyHostToDevice, sx));
     AVLD_CUDA(cudaEventRecord(c->ev_h2d[b], sx));
+    mark(sx);
     AVLD_CUDA(cudaStreamWaitEvent(sc, c->ev_h2d[b], 0));
+    mark(sc);
     AVLD_TRY(encode_pass(c, sample_bytes == 4 ? c->d_xbuf[b] : nullptr,
                          sample_bytes == 2 ? reinterpret_cast<const int16_t*>(c->d_xbuf[b]) : nullptr, c->d_mu, c->d_ok, m,
                          0.05f, 1e-4f, 1e-8f, quantize_pcm16, sc));
@@ -94,9 +110,22 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
       AVLD_CUDA(cudaMemcpyAsync(s_mu + i * D, c->d_mu, static_cast<size_t>(m) * D * sizeof(float), cudaMemcpyDeviceToHost, sc));
     if (ok_host)
       AVLD_CUDA(cudaMemcpyAsync(s_ok + i, c->d_ok, static_cast<size_t>(m), cudaMemcpyDeviceToHost, sc));
+    mark(sc);
   }
   AVLD_CUDA(cudaStreamSynchronize(sc));
   AVLD_CUDA(cudaStreamSynchronize(sx));
+  if (trace_path && !tev.empty()) {
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "slab copy_start copy_end compute_start compute_end (ms)\n");
+      for (size_t k = 0; k + 3 < tev.size(); k += 4) {
+        float t[4];
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[k + j]);
+        fprintf(f, "%zu %.3f %.3f %.3f %.3f\n", k / 4, t[0], t[1], t[2], t[3]);
+      }
+      fclose(f);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   memcpy(pred_host, s_pred, n_sz * sizeof(int32_t));
   memcpy(best_host, s_best, n_sz * sizeof(float));
   if (mu_host) memcpy(mu_host, s_mu, n_sz * D * sizeof(float));

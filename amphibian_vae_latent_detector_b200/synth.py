@@ -52,3 +52,33 @@ def make_chunks(n: int, length: int = 144000, *, sr: int = 48000, n_species: int
         if hot.any():
             x[hot] = x[hot] * (2.0 / x[hot].abs().amax(dim=1, keepdim=True).clamp_min(1e-9))
     return x.to(torch.float32).contiguous(), label
+
+
+def write_wav_tree(root, species, n_per_class: int, length: int = 144000, *, sr: int = 48000, seed: int = 123,
+                   special_every: int = 0):
+    """``<root>/<species>/<species>_<iii>.wav`` (PCM_16 mono): the folder layout 00 / 08 / 10 walk
+    (00_normalize_dataset_rms.py:41-57, 08_fit_radial_detector.py:461-486, 10_benchmark_folder_detection.py:387-395).
+    Always generated on the CPU so that the files are identical wherever they are made."""
+    import wave
+    from pathlib import Path
+
+    import numpy as np
+
+    root = Path(root)
+    K = len(species)
+    x, label = make_chunks(n_per_class * K, length, sr=sr, n_species=K, seed=seed, special_every=special_every)
+    pcm = torch.clamp(torch.round(x * 32767.0), -32768, 32767).to(torch.int16).numpy()
+    label = label.numpy()
+    files = []
+    for k, sp in enumerate(species):
+        d = root / sp
+        d.mkdir(parents=True, exist_ok=True)
+        for j, i in enumerate(np.nonzero(label == k)[0]):
+            path = d / f"{sp}_{j:03d}.wav"
+            with wave.open(str(path), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(int(sr))
+                w.writeframes(pcm[i].astype("<i2").tobytes())
+            files.append(path)
+    return files

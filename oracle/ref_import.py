@@ -74,16 +74,22 @@ def _install_matplotlib_stub() -> None:
     """10_benchmark_folder_detection.py imports matplotlib for its (out-of-scope) plots."""
     import types
 
-    mpl = types.ModuleType("matplotlib")
-    plt = types.ModuleType("matplotlib.pyplot")
-    mpl.use = lambda *a, **k: None
+    class _Anything(types.ModuleType):
+        """Every attribute is a callable that returns another such object (plots are out of scope)."""
 
-    def _noop(*a, **k):
-        return None
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return _Anything(name)
 
-    for name in ("figure", "bar", "title", "ylabel", "xlabel", "tight_layout", "savefig", "close",
-                 "imshow", "colorbar", "xticks", "yticks", "text", "ylim", "subplots"):
-        setattr(plt, name, _noop)
+        def __call__(self, *a, **k):
+            return _Anything("result")
+
+        def __iter__(self):
+            return iter((_Anything("a"), _Anything("b")))
+
+    mpl = _Anything("matplotlib")
+    plt = _Anything("matplotlib.pyplot")
     mpl.pyplot = plt
     sys.modules.setdefault("matplotlib", mpl)
     sys.modules.setdefault("matplotlib.pyplot", plt)
