@@ -120,6 +120,23 @@ struct avld_ctx {
   CUtensorMap tm_A2pf_hi, tm_A2pf_lo; // un-swizzled 256-tap x 128-row boxes of A2, used only for L2 prefetch (4x fewer TMA rows)
   int dft_pair = 1;                   // folded GEMM on CTA pairs (cta_group::2); AVLD_DFT_MODE=fold1 selects the 1-CTA kernel
 
+  // twice-folded STFT ("fold2", default when n_fft % 512 == 0): a second time-reversal fold splits the bins by parity,
+  //   even b:  Re X = sum_{k<N/4} (E[k] + E[N/2-k]) cos(2 pi k b / N) + E[N/4] cos(pi b / 2),   -Im X = sum (O[k] - O[N/2-k]) sin(.)
+  //   odd  b:  Re X = sum_{k<N/4} (E[k] - E[N/2-k]) cos(.),   -Im X = sum (O[k] + O[N/2-k]) sin(.) + O[N/4] sin(pi b / 2)
+  // (E/O = first fold of the WINDOWED frame), i.e. K = N/4 per cos / sin GEMM: a quarter of the plain DFT GEMM's tensor
+  // work.  fold2.cu writes the four folded sequences per frame (same bytes as one fold) and the two edge terms; dftf3.cu
+  // runs 160-bin work items per class and adds the edge term in its epilogue; the two classes accumulate mel power into
+  // separate planes (summed by logmel_post_kernel) so that the float sums stay order independent.
+  int dft_fold2 = 0;
+  int f2_items = 0, f2_tiles_per_class = 0;
+  __half* d_B3hi = nullptr;        // [f2_items * 2 * 160][N/4]: per item 160 cos rows then 160 sin rows (no window)
+  __half* d_B3lo = nullptr;
+  CUtensorMap tm_B3_hi, tm_B3_lo;  // 64-tap x 80-row boxes (one CTA's half of an item)
+  avld::MelTap* d_taps3 = nullptr; // [f2_items * 160], .pad = bits of the edge coefficient
+  float2* d_edge = nullptr;        // [max_batch * F + 256] (E[N/4], O[N/4]) per frame
+  float* d_win = nullptr;          // [N/2 + 1] periodic Hann
+  long long melpow_plane = 0;      // elements per mel-power plane (fold2: two planes)
+
   // per-pass scratch (max_batch chunks)
   int max_batch = 0;
   __half* d_Ahi = nullptr;         // padded, pow2-scaled audio rows [max_batch * R + 128][hop]
@@ -194,6 +211,8 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st);
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold(avld_ctx* c, int n, cudaStream_t st);
+int launch_fold2(avld_ctx* c, int n, cudaStream_t st);
+int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st);
 int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);

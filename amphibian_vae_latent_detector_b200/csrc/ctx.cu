@@ -321,6 +321,8 @@ static int build_ctx(avld_ctx* c) {
     const char* mode = getenv("AVLD_DFT_MODE");          // "direct" selects the un-folded K = n_fft GEMM (A/B comparisons)
     c->dft_fold = !(mode != nullptr && strcmp(mode, "direct") == 0) && (p.n_fft % 128 == 0);
     c->dft_pair = !(mode != nullptr && strcmp(mode, "fold1") == 0);
+    // default: the twice-folded kernel; "fold" keeps the once-folded CTA-pair kernel (A/B comparisons)
+    c->dft_fold2 = c->dft_fold && mode == nullptr && (p.n_fft % 512 == 0) && (c->sm_count % 2 == 0);
   }
   c->n_tiles2 = (nbins + 255) / 256;
   c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;
@@ -388,6 +390,76 @@ static int build_ctx(avld_ctx* c) {
     AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
     AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
     AVLD_TRY(dev_alloc(&c->d_chunk_par, c->max_batch));
+    if (c->dft_fold2) {
+      // ---- twice-folded operands: per class (bin parity) `tpc` items of 160 bins; item rows = 160 cos then 160 sin
+      const int Q = nf / 4, kItem = 160;
+      std::vector<int> cls_bins[2];
+      for (int b = bin_lo; b <= bin_hi; ++b) cls_bins[b & 1].push_back(b);
+      const int tpc = static_cast<int>((std::max(cls_bins[0].size(), cls_bins[1].size()) + kItem - 1) / kItem);
+      c->f2_tiles_per_class = tpc;
+      c->f2_items = 2 * tpc;
+      const size_t rows3 = static_cast<size_t>(c->f2_items) * 2 * kItem;
+      std::vector<__half> h3(rows3 * Q), l3(rows3 * Q);
+      std::vector<MelTap> taps3(static_cast<size_t>(c->f2_items) * kItem);
+      for (int it = 0; it < c->f2_items; ++it) {
+        const int cl = it / tpc, t = it % tpc;
+        int run = 0;
+        for (int j = 0; j < kItem; ++j) {
+          const size_t idx = static_cast<size_t>(t) * kItem + j;
+          const bool have = idx < cls_bins[cl].size();
+          const int bin = have ? cls_bins[cl][idx] : -1;
+          // epilogue taps: mel filter pair of the bin and the coefficient of the edge term (k = N/4):
+          // cos(pi b / 2) for even bins, sin(pi b / 2) for odd bins, both in {-1, 0, +1}
+          MelTap tp{run, 0.f, 0.f, 0};
+          if (have && first[bin] >= 0) {
+            run = first[bin];
+            const int r4 = bin & 3;
+            const float coef = static_cast<float>(bscale) * (cl == 0 ? (r4 == 0 ? 1.f : -1.f) : (r4 == 1 ? 1.f : -1.f));
+            int32_t bits;
+            memcpy(&bits, &coef, 4);
+            tp = {first[bin], w0[bin], w1[bin], bits};
+          }
+          if (j == 0 && !(have && first[bin] >= 0)) {      // keep `first` monotone from the item's first column on
+            for (size_t u = idx; u < cls_bins[cl].size(); ++u)
+              if (first[cls_bins[cl][u]] >= 0) { run = first[cls_bins[cl][u]]; break; }
+            tp.first = run;
+          }
+          taps3[static_cast<size_t>(it) * kItem + j] = tp;
+          for (int part = 0; part < 2; ++part) {
+            const size_t r = (static_cast<size_t>(it) * 2 + part) * kItem + j;
+            for (int k = 0; k < Q; ++k) {
+              double v = 0.0;
+              if (have) {
+                const long long ph = (static_cast<long long>(k) * bin) % nf;
+                const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
+                v = bscale * (part == 0 ? std::cos(ang) : std::sin(ang));
+              }
+              const __half h = __float2half_rn(static_cast<float>(v));
+              h3[r * Q + k] = h;
+              l3[r * Q + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+            }
+          }
+        }
+      }
+      AVLD_TRY(dev_alloc(&c->d_B3hi, h3.size()));
+      AVLD_TRY(dev_alloc(&c->d_B3lo, l3.size()));
+      AVLD_CUDA(cudaMemcpy(c->d_B3hi, h3.data(), h3.size() * 2, cudaMemcpyHostToDevice));
+      AVLD_CUDA(cudaMemcpy(c->d_B3lo, l3.data(), l3.size() * 2, cudaMemcpyHostToDevice));
+      AVLD_TRY(encode_tmap_2d(&c->tm_B3_hi, c->d_B3hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
+      AVLD_TRY(encode_tmap_2d(&c->tm_B3_lo, c->d_B3lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
+      AVLD_TRY(dev_alloc(&c->d_taps3, taps3.size()));
+      AVLD_CUDA(cudaMemcpy(c->d_taps3, taps3.data(), taps3.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
+      std::vector<float> win(half + 1);
+      for (int k = 0; k <= half; ++k) win[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf));
+      AVLD_TRY(dev_alloc(&c->d_win, win.size()));
+      AVLD_CUDA(cudaMemcpy(c->d_win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
+      AVLD_TRY(dev_alloc(&c->d_edge, frames));
+      AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float2)));
+      if (fbk != 64) {   // the fold2 kernel loads 64-tap boxes of A
+        AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
+        AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
+      }
+    }
   } else {
     const int nf = p.n_fft;
     std::vector<double> win(nf), ct(nf), stab(nf);
@@ -433,7 +505,8 @@ static int build_ctx(avld_ctx* c) {
     AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
   }
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
-  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->max_batch) * c->R * c->M));
+  c->melpow_plane = static_cast<long long>(c->max_batch) * c->R * c->M;
+  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 2 : 1)));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
   AVLD_TRY(dev_alloc(&c->d_ok, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_rms, c->max_batch));
@@ -481,7 +554,7 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
-                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
+                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_B3hi, c->d_B3lo, c->d_taps3, c->d_edge, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
                   c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
                   c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)

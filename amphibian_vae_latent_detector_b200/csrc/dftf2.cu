@@ -6,6 +6,13 @@
 //   warp 0 lane 0 (both CTAs)   TMA producer: own A rows, own half of the B rows, bytes counted on the leader's barrier
 //   warp 1 lane 0 (leader only) MMA issuer: tcgen05.mma.cta_group::2, commits multicast to both CTAs
 //   warps 2..9    (both CTAs)   epilogue on the CTA's own TMEM: |X|^2, un-scale, sparse slaney mel, atomicAdd
+//
+// TMEM holds ONE accumulator set (256 Re + 256 Im columns = all 512), so the epilogue cannot be double-buffered by tile.
+// Instead it is split by HALF: the K loop runs the E half (-> Re) and then the O half (-> Im); as soon as Re is complete
+// the epilogue warps pull their Re columns into registers (128 per thread) and release the Re columns, while the O half is
+// still being multiplied; when Im completes they stream it 16 columns at a time, combine with the held Re, and release
+// Im.  The issuer therefore starts the next tile's E half right after the O half: no drain bubble between tiles
+// (it was ~20 000 of ~80 000 cycles per tile with a single full/empty barrier pair).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -32,7 +39,9 @@ struct Dftf2Params {
 namespace {
 constexpr int kBM = 128, kBN = 256;
 constexpr int kExtra = 16384;
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;      // 2 per TMEM lane quarter: 128-bin ranges, so a mel filter (<= 67 bins) gets at most two
+                                  // atomic contributions and the float sum stays order independent (bit-reproducible)
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 // KBK taps per pipeline stage: 64 (128-byte swizzled rows, 3 stages of 64 KB) or 32 (64-byte rows, 6 stages of 32 KB)
 template <int KBK>
 struct PairCfg {
@@ -59,9 +68,9 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint8_t* tail = smem + kStages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [8]  (used in the leader)
   uint64_t* empty_bar = full_bar + 8;                         // [8]  (per CTA)
-  uint64_t* tmem_full = empty_bar + 8;                        // [1]  (per CTA)
-  uint64_t* tmem_empty = tmem_full + 1;                       // [1]        (leader)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_full = empty_bar + 8;                        // [2]  Re / Im complete (per CTA)
+  uint64_t* tmem_empty = tmem_full + 2;                       // [2]  Re / Im columns drained (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,8 +90,10 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       mbar_init(&full_bar[s], 2);          // leader's expect_tx arrive + the peer producer's arrive
       mbar_init(&empty_bar[s], 1);         // one multicast commit
     }
-    mbar_init(&tmem_full[0], 1);
-    mbar_init(&tmem_empty[0], 16);         // lane 0 of the 8 epilogue warps of both CTAs
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&tmem_full[h], 1);
+      mbar_init(&tmem_empty[h], 2 * kEpiWarps);   // lane 0 of the epilogue warps of both CTAs
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -156,9 +167,11 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
         for (int nt = 0; nt < P.num_n_tiles; ++nt) {
           const uint32_t idesc = (nt == P.num_n_tiles - 1) ? P.idesc_last : P.idesc_full;
-          mbar_wait(&tmem_empty[0], acc_phase ^ 1u, 200);
-          tcgen05_fence_after();
           for (int kb = 0; kb < nkb; ++kb) {
+            if (kb == 0 || kb == hk) {       // the half's accumulator columns must have been drained
+              mbar_wait(&tmem_empty[kb == 0 ? 0 : 1], acc_phase ^ 1u, 200 + (kb == 0 ? 0 : 1));
+              tcgen05_fence_after();
+            }
             mbar_wait(&full_bar[stage], phase, 300 + stage);
             if (P.trace && cluster == 0 && tk < 256) P.trace[(2 * 2 + 0) * 256 + tk] = clock64();
             tcgen05_fence_after();
@@ -176,7 +189,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
             }
             umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
-            if (kb == nkb - 1) umma_commit_pair(&tmem_full[0], 0x3);     // accumulators complete in both CTAs
+            if (kb == hk - 1) umma_commit_pair(&tmem_full[0], 0x3);      // Re complete in both CTAs
+            if (kb == nkb - 1) umma_commit_pair(&tmem_full[1], 0x3);     // Im complete in both CTAs
             if (P.trace && cluster == 0 && tk < 256) P.trace[(3 * 2 + 0) * 256 + tk] = clock64();
             ++tk;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -187,7 +201,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
-    const int quarter = warp & 3, half_id = (warp - 2) >> 2;
+    // warp w may touch TMEM lanes 32 (w % 4) .. +32; the two warps of a lane quarter split the tile's bins
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t acc_phase = 0;
@@ -197,49 +212,66 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const float s2 = valid ? P.inv2[g / P.F] : 0.f;
       float* mrow = P.melpow + g * P.n_mels;
       for (int nt = 0; nt < P.num_n_tiles; ++nt) {
+        const int nb_tile = (nt == P.num_n_tiles - 1) ? P.last_bins : kBN;
+        const int wbins = nb_tile >> 1, b0 = sub * wbins;       // 128 bins per warp (64 in a 128-bin last tile)
+        const bool skip = (P.dbg & 1) != 0;
+        // ---- Re: into registers while the O half is still being multiplied
+        uint32_t re[8][16];
         mbar_wait(&tmem_full[0], acc_phase, 400);
         tcgen05_fence_after();
-        const int nb_tile = (nt == P.num_n_tiles - 1) ? P.last_bins : kBN;
-        const int hbins = nb_tile >> 1, b0 = half_id * hbins;
-        const MelTap* tile_taps = s_taps + nt * kBN;
-        int mcur = tile_taps[b0].first;
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll 1
-        for (int c0 = b0; c0 < b0 + ((P.dbg & 1) ? 0 : hbins); c0 += 16) {
-          uint32_t re[16], im[16];
-          tmem_ld16(t_acc + c0, re);
-          tmem_ld16(t_acc + kBN + c0, im);
-          tmem_ld_wait();
-          float pw[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
-            pw[j] = (a * a + b * b) * s2;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const MelTap tp = tile_taps[c0 + j];
-            if (mcur < tp.first) {
-#pragma unroll 1
-              while (mcur < tp.first) {
-                if (valid && a0 != 0.f) atomicAdd(mrow + mcur, a0);
-                a0 = a1;
-                a1 = 0.f;
-                ++mcur;
-              }
-            }
-            a0 = fmaf(tp.w0, pw[j], a0);
-            a1 = fmaf(tp.w1, pw[j], a1);
-          }
-        }
-        if (valid && a0 != 0.f && mcur < P.n_mels) atomicAdd(mrow + mcur, a0);
-        if (valid && a1 != 0.f && mcur + 1 < P.n_mels) atomicAdd(mrow + mcur + 1, a1);
+        for (int q = 0; q < 8; ++q)
+          if (q * 16 < wbins) tmem_ld16(t_acc + b0 + q * 16, re[q]);
+        tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (leader) mbar_arrive(&tmem_empty[0]);
           else mbar_arrive_cluster(&tmem_empty[0], 0);
         }
+        // ---- Im: streamed, combined with the held Re
+        const MelTap* tile_taps = s_taps + nt * kBN;
+        int mcur = tile_taps[b0].first;
+        float a0 = 0.f, a1 = 0.f;
+        mbar_wait(&tmem_full[1], acc_phase, 401);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 16 < wbins) {
+            uint32_t im[16];
+            tmem_ld16(t_acc + kBN + b0 + q * 16, im);
+            tmem_ld_wait();
+            if (q * 16 + 16 >= wbins) {      // last Im read of this warp: the columns may be overwritten
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (leader) mbar_arrive(&tmem_empty[1]);
+                else mbar_arrive_cluster(&tmem_empty[1], 0);
+              }
+            }
+            if (!skip) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a = __uint_as_float(re[q][j]), b = __uint_as_float(im[j]);
+                const float pw = (a * a + b * b) * s2;
+                const MelTap tp = tile_taps[b0 + q * 16 + j];
+                if (mcur < tp.first) {
+#pragma unroll 1
+                  while (mcur < tp.first) {
+                    if (valid && a0 != 0.f) atomicAdd(mrow + mcur, a0);
+                    a0 = a1;
+                    a1 = 0.f;
+                    ++mcur;
+                  }
+                }
+                a0 = fmaf(tp.w0, pw, a0);
+                a1 = fmaf(tp.w1, pw, a1);
+              }
+            }
+          }
+        }
+        if (valid && a0 != 0.f && mcur < P.n_mels) atomicAdd(mrow + mcur, a0);
+        if (valid && a1 != 0.f && mcur + 1 < P.n_mels) atomicAdd(mrow + mcur + 1, a1);
         acc_phase ^= 1u;
       }
     }

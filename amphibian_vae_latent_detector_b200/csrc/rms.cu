@@ -12,6 +12,7 @@
 // Memory: phase 1 streams the chunk once (4*L bytes), phase 2 re-reads it (L2-resident: 148 CTAs x
 // 576 KB < 126 MB L2) and writes either y (4*L bytes) or the 16-bit operand pair (4*(L+n_fft) bytes).
 #include "common.cuh"
+#include "sample.cuh"
 
 namespace avld {
 
@@ -35,21 +36,9 @@ struct PrepParams {
   float target_rms, rms_min, eps;
   int normalize, quantize;
   int dft_scale_log2;
+  int headroom_log2;      // max |scaled sample| < 2^(headroom_log2 + 1): 14 (one fold: sums of two) or 13 (two folds)
   int n;
 };
-
-__device__ __forceinline__ float finish_sample(float v, float scale, int scaled, int quantize) {
-  if (scaled) {
-    v = __fmul_rn(v, scale);
-    v = v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v);   // np.clip keeps NaN
-  }
-  if (quantize) {   // sf.write PCM_16 (lrintf(x * 0x7FFF)) + librosa.load (s / 0x8000); through int so that -0.0 -> +0.0
-    int q = __float2int_rn(__fmul_rn(v, 32767.0f));
-    q = q < -32768 ? -32768 : (q > 32767 ? 32767 : q);
-    v = __fmul_rn(static_cast<float>(q), 1.0f / 32768.0f);
-  }
-  return v;
-}
 
 // sample loaders: float32 chunk or PCM_16 chunk (exact: |s| < 2^15, scale 2^-15)
 struct LoadF32 {
@@ -151,7 +140,7 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     float bound = scaled ? fminf(__fmul_rn(m, scale), 1.0f) : m;
     int s = 0;
     if (bound > 0.f && bound < 3.0e38f) {
-      s = 14 - ilogbf(bound);
+      s = P.headroom_log2 - ilogbf(bound);
       s = s > 60 ? 60 : (s < -60 ? -60 : s);
     }
     s_scale = scale;
@@ -381,6 +370,7 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.normalize = normalize ? 1 : 0;
   P.quantize = quantize ? 1 : 0;
   P.dft_scale_log2 = c->dft_scale_log2;
+  P.headroom_log2 = c->dft_fold2 ? 13 : 14;
   const size_t smem = static_cast<size_t>(c->n_leaves + c->n_nodes + 1) * sizeof(float);
   static bool configured = false;
   if (!configured) {
