@@ -617,6 +617,37 @@ extern "C" const char* avld_stage_name(int stage) {
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 
+extern "C" int avld_ctx_dft_info(const avld_ctx* c, const char** mode, double* algorithmic, double* issued) {
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  const double F = c->F, N = c->p.n_fft;
+  int first_bin = 0, bins = 0;
+  {
+    std::vector<int32_t> first;
+    std::vector<float> w0, w1;
+    int lo = 0, hi = 0;
+    AVLD_TRY(mel_taps_host(c->p, first, w0, w1, &lo, &hi));
+    for (int b = lo; b <= hi; ++b) bins += first[b] >= 0;
+    first_bin = lo;
+  }
+  (void)first_bin;
+  if (algorithmic) *algorithmic = 2.0 * F * N * 2.0 * bins;
+  const char* m = "direct";
+  double iss = 0.0;
+  if (c->dft_fold2) {            // items x (cos + sin) x K = N/4 x 160 columns, three passes
+    m = "fold2";
+    iss = 3.0 * 2.0 * F * c->f2_items * 2.0 * (N / 4) * 160.0;
+  } else if (c->dft_fold) {      // per 256-bin tile: K = N/2 for Re and for Im, three passes
+    m = c->dft_pair ? "fold" : "fold1";
+    const double cols = (c->n_tiles2 - 1) * 256.0 + c->last_tile_bins;
+    iss = 3.0 * 2.0 * F * (N / 2) * 2.0 * cols;
+  } else {                       // junk rows between chunks are multiplied too (R rows per chunk)
+    iss = 3.0 * 2.0 * c->R * N * c->ncols;
+  }
+  if (mode) *mode = m;
+  if (issued) *issued = iss;
+  return AVLD_OK;
+}
+
 extern "C" int avld_ctx_info(const avld_ctx* c, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count) {
   AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
   if (n_frames) *n_frames = c->F;

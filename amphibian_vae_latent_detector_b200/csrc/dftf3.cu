@@ -32,7 +32,8 @@ struct Dftf3Params {
   float* melpow;            // [2 planes][rows][n_mels]
   long long plane_stride;
   int F, n_mels;
-  int dbg;                  // bring-up: 1 = skip the epilogue math, 2 = A rows fixed (always L2 resident)
+  int dbg;                  // bring-up: 1 = skip the epilogue math, 2 = A rows fixed (always L2 resident),
+                            // 4 = no operand loads after the first pipeline fill (MMA issue rate alone)
 };
 
 namespace {
@@ -117,18 +118,26 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
       };
       for (int i = 0; i < PF; ++i) pf_step();
+      int filled = 0;
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
         const int ay = (P.dbg & 2) ? (cluster * 2 * kBM + static_cast<int>(rank) * kBM)
                                    : pair * 2 * kBM + static_cast<int>(rank) * kBM;
         for (int it = 0; it < P.num_items; ++it) {
           const int a_col0 = (it / P.tiles_per_class) * nkb * kBK;      // the class's N/2 columns: cos part | sin part
           for (int kb = 0; kb < nkb; ++kb) {
-            if (!(P.dbg & 2)) pf_step();
+            if (!(P.dbg & 6)) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
             uint8_t* sa_hi = smem + stage * kStageBytes;
             uint8_t* sa_lo = sa_hi + kABytes;
             uint8_t* sb_hi = sa_lo + kABytes;
             uint8_t* sb_lo = sb_hi + kBBytes;
+            if ((P.dbg & 4) && filled >= kStages) {     // bring-up: stale operands, barrier protocol only
+              if (leader) mbar_arrive(&full_bar[stage]);
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+            ++filled;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
             else mbar_arrive_cluster(&full_bar[stage], 0);
             const int part = kb < kbp ? 0 : 1;
@@ -166,9 +175,13 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t koff = static_cast<uint64_t>(k * 2);
-              umma_f16_pair(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (kb_acc | k) != 0 ? 1u : 0u);
-              umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
-              umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              // bring-up (dbg & 8, garbage results): alternate the accumulator between consecutive MMAs to see whether
+              // back-to-back accumulation into the same TMEM columns is what paces the issue
+              const uint32_t x = (P.dbg & 8) ? static_cast<uint32_t>(kImCol) : 0u;
+              const uint32_t d0 = (k & 1) ? (d_tmem ^ x) : d_tmem, d1 = d0 ^ x;
+              umma_f16_pair(d0, da_hi + koff, db_hi + koff, P.idesc, (kb_acc | k) != 0 ? 1u : 0u);
+              umma_f16_pair(d1, da_lo + koff, db_hi + koff, P.idesc, 1u);
+              umma_f16_pair(d0, da_hi + koff, db_lo + koff, P.idesc, 1u);
             }
             umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
             if (kb == kbp - 1) umma_commit_pair(&tmem_full[0], 0x3);     // Re complete in both CTAs
@@ -286,6 +299,8 @@ int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st) {
   {
     const char* d = getenv("AVLD_DBG");
     P.dbg = d ? atoi(d) : 0;
+    const char* dn = getenv("AVLD_DBG_N");      // bring-up (with AVLD_DBG=5): MMA N override, results are garbage
+    if (dn && (P.dbg & 4)) P.idesc = avld_make_idesc(0, 0, 256, atoi(dn));
   }
   static bool configured = false;
   if (!configured) {

@@ -96,6 +96,13 @@ class Engine:
         return {self.lib.avld_stage_name(i).decode(): dict(ms=ms[i], timed_launches=int(tl[i]), launches=int(ln[i]))
                 for i in range(ns)}
 
+    def dft_info(self) -> Dict[str, object]:
+        """How the STFT is evaluated: ``{mode, algorithmic_flops_per_chunk, issued_flops_per_chunk}``."""
+        mode = C.c_char_p()
+        alg, iss = C.c_double(), C.c_double()
+        _lib.check(self.lib.avld_ctx_dft_info(self._h, C.byref(mode), C.byref(alg), C.byref(iss)))
+        return {"mode": mode.value.decode(), "algorithmic_flops_per_chunk": alg.value, "issued_flops_per_chunk": iss.value}
+
     # ------------------------------------------------------------------ R1 / R2
     def rms_normalize(self, x: torch.Tensor, target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8,
                       pcm16: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -58,12 +58,12 @@ def _engine(chunk_len: int, device=0, *, sr=48000, n_mels=64, fmin=150.0, fmax=1
     return eng
 
 
-def _engine_with_encoder(encoder, chunk_len, device, **mel_kw) -> Engine:
-    """One engine per (geometry, encoder object); the layer program is exported and uploaded once."""
-    key = (_cuda_index(device), int(chunk_len), tuple(sorted(mel_kw.items())), id(encoder))
+def _engine_with_encoder(encoder, chunk_len, device, *, max_batch: int = 64, **mel_kw) -> Engine:
+    """One engine per (geometry, encoder object, pass size); the layer program is exported and uploaded once."""
+    key = (_cuda_index(device), int(chunk_len), tuple(sorted(mel_kw.items())), id(encoder), int(max_batch))
     eng = _ENGINES.get(key)
     if eng is None:
-        eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=64, **mel_kw)
+        eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=int(max_batch), **mel_kw)
         eng.load_encoder(encoder)
         _ENGINES[key] = eng
     return eng

@@ -89,6 +89,13 @@ void avld_ctx_destroy(avld_ctx* ctx);
 /* derived sizes: frames per chunk F = 1 + chunk_len / hop, latent dim D (0 before encoder_load) */
 int avld_ctx_info(const avld_ctx* ctx, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count);
 
+/* How the STFT is evaluated on this context (accounting for bench.py's roofline line): `mode` receives a static string
+ * ("fold2" twice-folded, "fold"/"fold1" once-folded, "direct"), algorithmic = the flops of the plain windowed DFT GEMM
+ * restricted to the bins with mel weight (2 * F * n_fft * 2 * bins), issued = the tensor-core
+ * flops the selected kernel actually issues per chunk (all split-precision passes, padded tiles included). */
+int avld_ctx_dft_info(const avld_ctx* ctx, const char** mode, double* algorithmic_flops_per_chunk,
+                      double* issued_flops_per_chunk);
+
 /* ---- accounting -------------------------------------------------------------------------------
  * Every kernel launch is counted per kernel family ("stage"); with profiling enabled each launch is
  * additionally bracketed by CUDA events on its own stream.  avld_profile_collect synchronises on the
