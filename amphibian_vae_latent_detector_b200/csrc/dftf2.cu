@@ -160,7 +160,8 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // (whole warp on the warp-uniform schedule, one elected lane issues: see dftf3.cu)
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       int tk = 0;
@@ -173,7 +174,7 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               tcgen05_fence_after();
             }
             mbar_wait(&full_bar[stage], phase, 300 + stage);
-            if (P.trace && cluster == 0 && tk < 256) P.trace[(2 * 2 + 0) * 256 + tk] = clock64();
+            if (P.trace && cluster == 0 && tk < 256 && lane == 0) P.trace[(2 * 2 + 0) * 256 + tk] = clock64();
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (kb < hk ? 0u : static_cast<uint32_t>(kBN));
             const int kb_acc = kb < hk ? kb : kb - hk;
@@ -181,17 +182,20 @@ dftf2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t a_lo = a_hi + kABytes, b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
             const uint64_t da_hi = make_smem_desc(a_hi, kSwz), da_lo = make_smem_desc(a_lo, kSwz);
             const uint64_t db_hi = make_smem_desc(b_hi, kSwz), db_lo = make_smem_desc(b_lo, kSwz);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t koff = static_cast<uint64_t>(k * 2);
-              umma_f16_pair(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb_acc | k) != 0 ? 1u : 0u);
-              umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
-              umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t koff = static_cast<uint64_t>(k * 2);
+                umma_f16_pair(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+                umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
+                umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+              }
+              umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
+              if (kb == hk - 1) umma_commit_pair(&tmem_full[0], 0x3);      // Re complete in both CTAs
+              if (kb == nkb - 1) umma_commit_pair(&tmem_full[1], 0x3);     // Im complete in both CTAs
             }
-            umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
-            if (kb == hk - 1) umma_commit_pair(&tmem_full[0], 0x3);      // Re complete in both CTAs
-            if (kb == nkb - 1) umma_commit_pair(&tmem_full[1], 0x3);     // Im complete in both CTAs
-            if (P.trace && cluster == 0 && tk < 256) P.trace[(3 * 2 + 0) * 256 + tk] = clock64();
+            __syncwarp();
+            if (P.trace && cluster == 0 && tk < 256 && lane == 0) P.trace[(3 * 2 + 0) * 256 + tk] = clock64();
             ++tk;
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

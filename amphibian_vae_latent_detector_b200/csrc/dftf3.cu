@@ -5,8 +5,8 @@
 // bins.  One item = 256 frames (a CTA pair) x 160 bins: K loop over the cos part (-> Re, TMEM columns 0..159) and then
 // the sin part (-> Im, columns 256..415), N/4 taps each -- a quarter of the taps of the plain DFT GEMM and half of the
 // once-folded one (dftf2.cu), for the same bins.  Split precision as everywhere: hi*hi + lo*hi + hi*lo, fp32 in TMEM.
-//   warp 0 lane 0 (both CTAs)   TMA producer: own 128 frames of A, own half (80 rows) of the B tile
-//   warp 1 lane 0 (leader only) MMA issuer: tcgen05.mma.cta_group::2 (M 256, N 160), commits multicast to both CTAs
+//   warp 0 (both CTAs)          TMA producer: own 128 frames of A, own half (80 rows) of the B tile
+//   warp 1 (leader only)        MMA issuer: tcgen05.mma.cta_group::2 (M 256, N 160), commits multicast to both CTAs
 //   warps 2..9    (both CTAs)   epilogue: Re into registers as soon as the cos part is done (the issuer moves on to the
 //                               sin part and, after it, straight to the next item's cos part), then Im streamed from
 //                               TMEM; edge term, |X|^2, un-scale, sparse slaney mel, atomicAdd into the class's plane.
@@ -99,7 +99,8 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // whole warp on the warp-uniform schedule, one elected lane issues (same reason as for the MMA issuer below)
+    {
       int stage = 0;
       uint32_t phase = 0;
       // L2 prefetch of this CTA's A rows, PF K blocks ahead of the loads
@@ -109,8 +110,11 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (pf_pair < P.num_pairs) {
           const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
           const int x = (pf_it / P.tiles_per_class) * nkb * kBK + pf_kb * kBK;
-          tma_prefetch_2d(&tmA_hi, x, y);
-          tma_prefetch_2d(&tmA_lo, x, y);
+          if (elect_one()) {
+            tma_prefetch_2d(&tmA_hi, x, y);
+            tma_prefetch_2d(&tmA_lo, x, y);
+          }
+          __syncwarp();
           if (++pf_kb == nkb) {
             pf_kb = 0;
             if (++pf_it == P.num_items) { pf_it = 0; pf_pair += n_clusters; }
@@ -131,22 +135,27 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             uint8_t* sa_lo = sa_hi + kABytes;
             uint8_t* sb_hi = sa_lo + kABytes;
             uint8_t* sb_lo = sb_hi + kBBytes;
-            if ((P.dbg & 4) && filled >= kStages) {     // bring-up: stale operands, barrier protocol only
-              if (leader) mbar_arrive(&full_bar[stage]);
-              else mbar_arrive_cluster(&full_bar[stage], 0);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-              continue;
-            }
+            const bool stale = (P.dbg & 4) && filled >= kStages;     // bring-up: stale operands, barrier protocol only
             ++filled;
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-            else mbar_arrive_cluster(&full_bar[stage], 0);
             const int part = kb < kbp ? 0 : 1;
             const int bx = (kb - part * kbp) * kBK;
             const int by = (it * 2 + part) * kBN + static_cast<int>(rank) * (kBN / 2);
-            tma_load_2d_pair(sa_hi, &tmA_hi, &full_bar[stage], a_col0 + kb * kBK, ay);
-            tma_load_2d_pair(sa_lo, &tmA_lo, &full_bar[stage], a_col0 + kb * kBK, ay);
-            tma_load_2d_pair(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
-            tma_load_2d_pair(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
+            if (elect_one()) {
+              if (stale) {
+                if (leader) mbar_arrive(&full_bar[stage]);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+              } else {
+                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+                // (L2 eviction-priority hints on these loads -- evict_last for B and for A until its class's last
+                // tile -- measured no difference: the K loop is bound by L2 -> SM throughput, not by misses)
+                tma_load_2d_pair(sa_hi, &tmA_hi, &full_bar[stage], a_col0 + kb * kBK, ay);
+                tma_load_2d_pair(sa_lo, &tmA_lo, &full_bar[stage], a_col0 + kb * kBK, ay);
+                tma_load_2d_pair(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
+                tma_load_2d_pair(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
+              }
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -154,7 +163,11 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // The whole warp walks the (warp-uniform) schedule so that addresses and descriptors stay in uniform registers and
+    // one elected lane issues.  Under `if (lane == 0)` the compiler brackets every UTCHMMA with ELECT + 5 R2UR.BROADCAST
+    // (cuobjdump), which paced the issue at ~115 cycles per MMA whatever N (measured with AVLD_DBG=5 and N = 64..192):
+    // more than the 80 tensor cycles of an N = 160 MMA.
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
@@ -172,20 +185,19 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint32_t a_lo = a_hi + kABytes, b_hi = a_lo + kABytes, b_lo = b_hi + kBBytes;
             const uint64_t da_hi = make_smem_desc(a_hi, kSwz), da_lo = make_smem_desc(a_lo, kSwz);
             const uint64_t db_hi = make_smem_desc(b_hi, kSwz), db_lo = make_smem_desc(b_lo, kSwz);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t koff = static_cast<uint64_t>(k * 2);
-              // bring-up (dbg & 8, garbage results): alternate the accumulator between consecutive MMAs to see whether
-              // back-to-back accumulation into the same TMEM columns is what paces the issue
-              const uint32_t x = (P.dbg & 8) ? static_cast<uint32_t>(kImCol) : 0u;
-              const uint32_t d0 = (k & 1) ? (d_tmem ^ x) : d_tmem, d1 = d0 ^ x;
-              umma_f16_pair(d0, da_hi + koff, db_hi + koff, P.idesc, (kb_acc | k) != 0 ? 1u : 0u);
-              umma_f16_pair(d1, da_lo + koff, db_hi + koff, P.idesc, 1u);
-              umma_f16_pair(d0, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t koff = static_cast<uint64_t>(k * 2);
+                umma_f16_pair(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (kb_acc | k) != 0 ? 1u : 0u);
+                umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              }
+              umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
+              if (kb == kbp - 1) umma_commit_pair(&tmem_full[0], 0x3);     // Re complete in both CTAs
+              if (kb == nkb - 1) umma_commit_pair(&tmem_full[1], 0x3);     // Im complete in both CTAs
             }
-            umma_commit_pair(&empty_bar[stage], 0x3);                    // stage reusable in both CTAs
-            if (kb == kbp - 1) umma_commit_pair(&tmem_full[0], 0x3);     // Re complete in both CTAs
-            if (kb == nkb - 1) umma_commit_pair(&tmem_full[1], 0x3);     // Im complete in both CTAs
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
           acc_phase ^= 1u;

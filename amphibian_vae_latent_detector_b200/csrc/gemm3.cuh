@@ -213,7 +213,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // the whole warp walks the warp-uniform schedule (descriptors stay in uniform registers), one elected lane issues:
+    // under `if (lane == 0)` every UTCHMMA is bracketed by ELECT + R2UR.BROADCAST moves (~115 cycles per MMA, measured)
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -241,15 +243,18 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const uint64_t dbg_bits = (static_cast<uint64_t>(P.dbg_baseoff & 7) << 49) + static_cast<uint64_t>((P.dbg_shift * SWZ) >> 4);
             const uint64_t da_hi = make_smem_desc(a_hi, SWZ) + dbg_bits, da_lo = make_smem_desc(a_lo, SWZ) + dbg_bits;
             const uint64_t db_hi = make_smem_desc(b_hi, SWZ), db_lo = make_smem_desc(b_lo, SWZ);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              const uint64_t koff = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B, in 16 B units
-              umma_f16(d_tmem, da_hi + koff, db_hi + koff, id_hh, (kb_acc | k) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, da_lo + koff, db_hi + koff, id_lh, 1u);
-              umma_f16(d_tmem, da_hi + koff, db_lo + koff, id_hl, 1u);
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t koff = static_cast<uint64_t>(k * 2);  // 16 elements * 2 B = 32 B, in 16 B units
+                umma_f16(d_tmem, da_hi + koff, db_hi + koff, id_hh, (kb_acc | k) != 0 ? 1u : 0u);
+                umma_f16(d_tmem, da_lo + koff, db_hi + koff, id_lh, 1u);
+                umma_f16(d_tmem, da_hi + koff, db_lo + koff, id_hl, 1u);
+              }
+              umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
+              if (kb == nkb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
             }
-            umma_commit(&empty_bar[stage]);                    // smem slot reusable once these MMAs retire
-            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
           if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
