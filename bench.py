@@ -64,6 +64,21 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def traffic_of(mode: str, chunks_per_launch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/dominant_kernel_traffic.json); null when the capture is of another kernel / size."""
+    p = REPO / "profiles" / "dominant_kernel_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+    except Exception:
+        return None
+    kernel = {"fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)
+    if d.get("kernel") != kernel or int(d.get("chunks_per_launch", 0)) != int(chunks_per_launch):
+        return None
+    return {"bytes_per_launch": d["traffic_bytes"], "dram_read": d["dram_bytes_read"], "dram_write": d["dram_bytes_write"],
+            "source": d.get("source")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -365,7 +380,7 @@ def main():
             "issued_tflops": issued_tflops,
             "tensor_pipe_frac": (issued_tflops / peaks["tflops_sustained"]) if issued_tflops else None,
             "dft_mode": info["mode"], "chunks_per_launch": args.max_batch,
-            "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": None,
+            "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": traffic_of(info["mode"], args.max_batch),
             "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None}
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
