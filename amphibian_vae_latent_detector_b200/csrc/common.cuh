@@ -127,15 +127,20 @@ struct avld_ctx {
   // work.  fold2.cu writes the four folded sequences per frame (same bytes as one fold) and the two edge terms; dftf3.cu
   // runs 160-bin work items per class and adds the edge term in its epilogue; the two classes accumulate mel power into
   // separate planes (summed by logmel_post_kernel) so that the float sums stay order independent.
+  // f2_levels == 3 (default) folds the even bins once more (b = 0 / 2 mod 4: K = N/8 per cos / sin GEMM; the odd bins'
+  // symmetry is spent), see fold2.cu::fold3_kernel; AVLD_DFT_MODE=fold2 keeps the two-level form.
   int dft_fold2 = 0;
-  int f2_items = 0, f2_tiles_per_class = 0;
+  int f2_levels = 3;
+  int f2_items = 0, f2_classes = 0;
+  struct F2Item { int a_col0, kbp, cls, edge_im; };   // A column of the cos part, 64-tap K blocks per part, bin class
+  F2Item f2_item[8] = {};                              // (= mel plane and edge component), edge term goes to Im?
   __half* d_B3hi = nullptr;        // [f2_items * 2 * 160][N/4]: per item 160 cos rows then 160 sin rows (no window)
   __half* d_B3lo = nullptr;
   CUtensorMap tm_B3_hi, tm_B3_lo;  // 64-tap x 80-row boxes (one CTA's half of an item)
   avld::MelTap* d_taps3 = nullptr; // [f2_items * 160], .pad = bits of the edge coefficient
-  float2* d_edge = nullptr;        // [max_batch * F + 256] (E[N/4], O[N/4]) per frame
+  float4* d_edge = nullptr;        // [max_batch * F + 256] per frame: the self-paired tap of each bin class
   float* d_win = nullptr;          // [N/2 + 1] periodic Hann
-  long long melpow_plane = 0;      // elements per mel-power plane (fold2: two planes)
+  long long melpow_plane = 0;      // elements per mel-power plane (fold2: one plane per bin class)
 
   // per-pass scratch (max_batch chunks)
   int max_batch = 0;

@@ -322,7 +322,9 @@ static int build_ctx(avld_ctx* c) {
     c->dft_fold = !(mode != nullptr && strcmp(mode, "direct") == 0) && (p.n_fft % 128 == 0);
     c->dft_pair = !(mode != nullptr && strcmp(mode, "fold1") == 0);
     // default: the twice-folded kernel; "fold" keeps the once-folded CTA-pair kernel (A/B comparisons)
-    c->dft_fold2 = c->dft_fold && mode == nullptr && (p.n_fft % 512 == 0) && (c->sm_count % 2 == 0);
+    const bool two = mode != nullptr && strcmp(mode, "fold2") == 0;
+    c->dft_fold2 = c->dft_fold && (mode == nullptr || two) && (p.n_fft % 512 == 0) && (c->sm_count % 2 == 0);
+    c->f2_levels = two ? 2 : 3;
   }
   c->n_tiles2 = (nbins + 255) / 256;
   c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;
@@ -391,45 +393,62 @@ static int build_ctx(avld_ctx* c) {
     AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
     AVLD_TRY(dev_alloc(&c->d_chunk_par, c->max_batch));
     if (c->dft_fold2) {
-      // ---- twice-folded operands: per class (bin parity) `tpc` items of 160 bins; item rows = 160 cos then 160 sin
+      // ---- folded operands: bin classes, each covered by work items of 160 bins; item rows = 160 cos then 160 sin
       const int Q = nf / 4, kItem = 160;
-      std::vector<int> cls_bins[2];
-      for (int b = bin_lo; b <= bin_hi; ++b) cls_bins[b & 1].push_back(b);
-      const int tpc = static_cast<int>((std::max(cls_bins[0].size(), cls_bins[1].size()) + kItem - 1) / kItem);
-      c->f2_tiles_per_class = tpc;
-      c->f2_items = 2 * tpc;
+      struct ClassDef { int mod, rem, a_col0, K, edge_im; };
+      std::vector<ClassDef> classes;
+      if (c->f2_levels == 3) {
+        classes = {{2, 1, 0, Q, 1},                       // odd bins: K = N/4, edge O[N/4] sin(pi b / 2) -> Im
+                   {4, 0, nf / 2, Q / 2, 0},              // b = 0 mod 4: K = N/8, edge P[N/8] cos(pi b / 4) -> Re
+                   {4, 2, nf / 2 + Q, Q / 2, 1}};         // b = 2 mod 4: K = N/8, edge R[N/8] sin(pi b / 4) -> Im
+      } else {
+        classes = {{2, 0, 0, Q, 0},                       // even bins: edge E[N/4] cos(pi b / 2) -> Re
+                   {2, 1, nf / 2, Q, 1}};                 // odd bins:  edge O[N/4] sin(pi b / 2) -> Im
+      }
+      c->f2_classes = static_cast<int>(classes.size());
+      struct ItemBins { std::vector<int> bins; };
+      std::vector<ItemBins> item_bins;
+      c->f2_items = 0;
+      for (size_t ci = 0; ci < classes.size(); ++ci) {
+        std::vector<int> bins;
+        for (int b = bin_lo; b <= bin_hi; ++b)
+          if (b % classes[ci].mod == classes[ci].rem) bins.push_back(b);
+        for (size_t o = 0; o < bins.size(); o += kItem) {
+          AVLD_CHECK(c->f2_items < 8, AVLD_ERR_UNSUPPORTED, "too many FFT bins for the folded STFT kernel");
+          c->f2_item[c->f2_items++] = {classes[ci].a_col0, classes[ci].K / 64, static_cast<int>(ci), classes[ci].edge_im};
+          item_bins.push_back({std::vector<int>(bins.begin() + o, bins.begin() + std::min(bins.size(), o + kItem))});
+        }
+      }
       const size_t rows3 = static_cast<size_t>(c->f2_items) * 2 * kItem;
       std::vector<__half> h3(rows3 * Q), l3(rows3 * Q);
       std::vector<MelTap> taps3(static_cast<size_t>(c->f2_items) * kItem);
       for (int it = 0; it < c->f2_items; ++it) {
-        const int cl = it / tpc, t = it % tpc;
+        const ClassDef& cd = classes[c->f2_item[it].cls];
+        const std::vector<int>& bins = item_bins[it].bins;
         int run = 0;
+        for (size_t u = 0; u < bins.size(); ++u)             // `first` must be monotone from the item's first column on
+          if (first[bins[u]] >= 0) { run = first[bins[u]]; break; }
         for (int j = 0; j < kItem; ++j) {
-          const size_t idx = static_cast<size_t>(t) * kItem + j;
-          const bool have = idx < cls_bins[cl].size();
-          const int bin = have ? cls_bins[cl][idx] : -1;
-          // epilogue taps: mel filter pair of the bin and the coefficient of the edge term (k = N/4):
-          // cos(pi b / 2) for even bins, sin(pi b / 2) for odd bins, both in {-1, 0, +1}
+          const bool have = j < static_cast<int>(bins.size());
+          const int bin = have ? bins[j] : -1;
+          // epilogue taps: mel filter pair of the bin and the coefficient of the class's self-paired tap:
+          // cos(pi b / 2), sin(pi b / 2), cos(pi b / 4) or sin(pi b / 4) at the class's bins, all +-1
           MelTap tp{run, 0.f, 0.f, 0};
           if (have && first[bin] >= 0) {
             run = first[bin];
-            const int r4 = bin & 3;
-            const float coef = static_cast<float>(bscale) * (cl == 0 ? (r4 == 0 ? 1.f : -1.f) : (r4 == 1 ? 1.f : -1.f));
+            const double ang = M_PI * bin / (cd.K == Q ? 2.0 : 4.0);
+            const double cf = cd.edge_im ? std::sin(ang) : std::cos(ang);
+            const float coef = static_cast<float>(bscale * std::round(cf));
             int32_t bits;
             memcpy(&bits, &coef, 4);
             tp = {first[bin], w0[bin], w1[bin], bits};
-          }
-          if (j == 0 && !(have && first[bin] >= 0)) {      // keep `first` monotone from the item's first column on
-            for (size_t u = idx; u < cls_bins[cl].size(); ++u)
-              if (first[cls_bins[cl][u]] >= 0) { run = first[cls_bins[cl][u]]; break; }
-            tp.first = run;
           }
           taps3[static_cast<size_t>(it) * kItem + j] = tp;
           for (int part = 0; part < 2; ++part) {
             const size_t r = (static_cast<size_t>(it) * 2 + part) * kItem + j;
             for (int k = 0; k < Q; ++k) {
               double v = 0.0;
-              if (have) {
+              if (have && k < cd.K) {
                 const long long ph = (static_cast<long long>(k) * bin) % nf;
                 const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
                 v = bscale * (part == 0 ? std::cos(ang) : std::sin(ang));
@@ -454,7 +473,7 @@ static int build_ctx(avld_ctx* c) {
       AVLD_TRY(dev_alloc(&c->d_win, win.size()));
       AVLD_CUDA(cudaMemcpy(c->d_win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
       AVLD_TRY(dev_alloc(&c->d_edge, frames));
-      AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float2)));
+      AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float4)));
       if (fbk != 64) {   // the fold2 kernel loads 64-tap boxes of A
         AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
         AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
@@ -506,7 +525,7 @@ static int build_ctx(avld_ctx* c) {
   }
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
   c->melpow_plane = static_cast<long long>(c->max_batch) * c->R * c->M;
-  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 2 : 1)));
+  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 3 : 1)));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
   AVLD_TRY(dev_alloc(&c->d_ok, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_rms, c->max_batch));
@@ -633,9 +652,9 @@ extern "C" int avld_ctx_dft_info(const avld_ctx* c, const char** mode, double* a
   if (algorithmic) *algorithmic = 2.0 * F * N * 2.0 * bins;
   const char* m = "direct";
   double iss = 0.0;
-  if (c->dft_fold2) {            // items x (cos + sin) x K = N/4 x 160 columns, three passes
-    m = "fold2";
-    iss = 3.0 * 2.0 * F * c->f2_items * 2.0 * (N / 4) * 160.0;
+  if (c->dft_fold2) {            // items x (cos + sin) x K x 160 columns, three passes
+    m = c->f2_levels == 3 ? "fold3" : "fold2";
+    for (int it = 0; it < c->f2_items; ++it) iss += 3.0 * 2.0 * F * 2.0 * (c->f2_item[it].kbp * 64.0) * 160.0;
   } else if (c->dft_fold) {      // per 256-bin tile: K = N/2 for Re and for Im, three passes
     m = c->dft_pair ? "fold" : "fold1";
     const double cols = (c->n_tiles2 - 1) * 256.0 + c->last_tile_bins;

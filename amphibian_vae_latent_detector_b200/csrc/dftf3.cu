@@ -1,7 +1,7 @@
 // dftf3.cu -- twice-folded STFT GEMM on CTA pairs (tcgen05 cta_group::2); operands from fold2.cu.
 //
-// The FFT bins with mel weight are split by parity into two classes; each class has its own A columns (N/2 of the N
-// columns of a folded row: cos part | sin part, N/4 taps each) and is covered by `tiles_per_class` work items of 160
+// The FFT bins with mel weight are split into classes (odd | 0 mod 4 | 2 mod 4, or even | odd in the two-level form);
+// each class has its own A columns (cos part | sin part, N/4 or N/8 taps each) and is covered by work items of 160
 // bins.  One item = 256 frames (a CTA pair) x 160 bins: K loop over the cos part (-> Re, TMEM columns 0..159) and then
 // the sin part (-> Im, columns 256..415), N/4 taps each -- a quarter of the taps of the plain DFT GEMM and half of the
 // once-folded one (dftf2.cu), for the same bins.  Split precision as everywhere: hi*hi + lo*hi + hi*lo, fp32 in TMEM.
@@ -22,12 +22,20 @@
 
 namespace avld {
 
+struct Dftf3Item {
+  int a_col0;   // first A column of the item's class: cos part | sin part, kbp * 64 taps each
+  int kbp;      // 64-tap K blocks per part
+  int cls;      // bin class = mel plane = component of the per-frame edge vector
+  int edge_im;  // the class's self-paired tap belongs to the sin part (Im) instead of the cos part (Re)
+};
+
 struct Dftf3Params {
-  int num_pairs, num_items, tiles_per_class, kb_part;   // kb_part = (N/4) / 64 K blocks per cos / sin part
+  int num_pairs, num_items;
+  Dftf3Item item[8];
   uint32_t idesc;
   long long M_total;
   const float* inv2;
-  const float2* edge;
+  const float4* edge;
   const MelTap* taps;       // [num_items * 160]; .pad holds the bit pattern of the edge coefficient
   float* melpow;            // [2 planes][rows][n_mels]
   long long plane_stride;
@@ -95,7 +103,6 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   cluster_sync_all();                      // the peer's barriers exist before anything can signal them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int kbp = P.kb_part, nkb = 2 * kbp;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -109,13 +116,13 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       auto pf_step = [&]() {
         if (pf_pair < P.num_pairs) {
           const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
-          const int x = (pf_it / P.tiles_per_class) * nkb * kBK + pf_kb * kBK;
+          const int x = P.item[pf_it].a_col0 + pf_kb * kBK;
           if (elect_one()) {
             tma_prefetch_2d(&tmA_hi, x, y);
             tma_prefetch_2d(&tmA_lo, x, y);
           }
           __syncwarp();
-          if (++pf_kb == nkb) {
+          if (++pf_kb == 2 * P.item[pf_it].kbp) {
             pf_kb = 0;
             if (++pf_it == P.num_items) { pf_it = 0; pf_pair += n_clusters; }
           }
@@ -127,7 +134,7 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         const int ay = (P.dbg & 2) ? (cluster * 2 * kBM + static_cast<int>(rank) * kBM)
                                    : pair * 2 * kBM + static_cast<int>(rank) * kBM;
         for (int it = 0; it < P.num_items; ++it) {
-          const int a_col0 = (it / P.tiles_per_class) * nkb * kBK;      // the class's N/2 columns: cos part | sin part
+          const int a_col0 = P.item[it].a_col0, kbp = P.item[it].kbp, nkb = 2 * kbp;
           for (int kb = 0; kb < nkb; ++kb) {
             if (!(P.dbg & 6)) pf_step();
             mbar_wait(&empty_bar[stage], phase ^ 1u, 100 + stage);
@@ -172,6 +179,7 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       uint32_t phase = 0, acc_phase = 0;
       for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
         for (int it = 0; it < P.num_items; ++it) {
+          const int kbp = P.item[it].kbp, nkb = 2 * kbp;
           for (int kb = 0; kb < nkb; ++kb) {
             if (kb == 0 || kb == kbp) {      // the part's accumulator columns must have been drained
               mbar_wait(&tmem_empty[kb == 0 ? 0 : 1], acc_phase ^ 1u, 200 + (kb == 0 ? 0 : 1));
@@ -217,11 +225,12 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const long long g = static_cast<long long>(pair) * 2 * kBM + static_cast<long long>(rank) * kBM + row;
       const bool valid = g < P.M_total;
       const float s2 = valid ? P.inv2[g / P.F] : 0.f;
-      const float2 edge = valid ? P.edge[g] : make_float2(0.f, 0.f);
+      const float4 edge = valid ? P.edge[g] : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int it = 0; it < P.num_items; ++it) {
-        const int cls = it / P.tiles_per_class;
+        const int cls = P.item[it].cls;
         float* mrow = P.melpow + cls * P.plane_stride + g * P.n_mels;
-        const float e_re = cls == 0 ? edge.x : 0.f, e_im = cls == 0 ? 0.f : edge.y;
+        const float e_cls = cls == 0 ? edge.x : (cls == 1 ? edge.y : edge.z);
+        const float e_re = P.item[it].edge_im ? 0.f : e_cls, e_im = P.item[it].edge_im ? e_cls : 0.f;
         // ---- Re: into registers while the sin part is still being multiplied
         uint32_t re[kGroups][16];
         mbar_wait(&tmem_full[0], acc_phase, 400);
@@ -297,8 +306,8 @@ int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st) {
   const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
   P.num_pairs = (m_tiles + 1) / 2;
   P.num_items = c->f2_items;
-  P.tiles_per_class = c->f2_tiles_per_class;
-  P.kb_part = (c->p.n_fft / 4) / kBK;
+  for (int it = 0; it < c->f2_items; ++it)
+    P.item[it] = {c->f2_item[it].a_col0, c->f2_item[it].kbp, c->f2_item[it].cls, c->f2_item[it].edge_im};
   P.idesc = avld_make_idesc(0, 0, 256, kBN);
   P.M_total = rows;
   P.inv2 = c->d_inv2;
@@ -321,7 +330,7 @@ int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st) {
   }
   AVLD_CHECK(static_cast<size_t>(P.num_items) * kBN * sizeof(MelTap) <= kExtra - 512, AVLD_ERR_UNSUPPORTED, "too many FFT bins");
   // the epilogue accumulates mel outputs with atomicAdd, one plane per bin class
-  for (int pl = 0; pl < 2; ++pl)
+  for (int pl = 0; pl < c->f2_classes; ++pl)
     AVLD_CUDA(cudaMemsetAsync(c->d_melpow + pl * c->melpow_plane, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
   const int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
   if (grid < 2) return AVLD_OK;

@@ -21,7 +21,7 @@ struct Fold2Params {
   const float* win;     // [H + 1] periodic Hann, win[k] = 0.5 - 0.5 cos(2 pi k / N)
   __half* a_hi;         // [n*F][N]
   __half* a_lo;
-  float2* edge;         // [n*F] (edge_e, edge_o)
+  float4* edge;         // [n*F] one self-paired tap per bin class (indexed by class), see the kernels
   int F, hop, n_fft, L, quantize;
   int vec_ok;
   long long total;      // n * F * (Q / 8) threads
@@ -144,7 +144,148 @@ __global__ void __launch_bounds__(256) fold2_kernel(const Fold2Params P) {
       const float wq = P.win[Q];
       const float p = finish_sample(raw_sample<PCM>(xf, xi, reflect_src(pf + Q, H, P.L)), scale, scaled, P.quantize) * pow2;
       const float m = finish_sample(raw_sample<PCM>(xf, xi, reflect_src(pf + N - Q, H, P.L)), scale, scaled, P.quantize) * pow2;
-      P.edge[row] = make_float2(wq * (p + m), wq * (p - m));
+      P.edge[row] = make_float4(wq * (p + m), wq * (p - m), 0.f, 0.f);     // class 0 = even bins, class 1 = odd bins
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fold3_kernel: as fold2_kernel, with one more fold for the even bins (their cos / sin kernels are again symmetric
+// about k = N/8 once restricted to b = 0 or 2 mod 4; the odd bins' symmetry is spent).  With Q = N/4, E = N/8 and, for
+// k = 1 .. E-1,  u1 = u[k], u2 = u[N-k], u3 = u[2Q-k], u4 = u[2Q+k], u5 = u[Q-k], u6 = u[3Q+k], u7 = u[Q+k], u8 = u[3Q-k]:
+//   P = u1+u2+u3+u4, P' = u5+u6+u7+u8, R = (u1-u2)-(u3-u4), R' = (u5-u6)-(u7-u8)
+//   b = 0 mod 4:  Re X = sum_k (P + P') cos(2 pi k b / N) + edge cos(pi b / 4),    -Im X = sum_k (R - R') sin(.)
+//   b = 2 mod 4:  Re X = sum_k (P - P') cos(.),                                   -Im X = sum_k (R + R') sin(.) + edge sin(pi b / 4)
+//   odd b (k < Q): Re X = sum_k ((u1+u2)-(u3+u4)) cos(.),  -Im X = sum_k ((u1-u2)+(u3-u4)) sin(.) + edge sin(pi b / 2)
+// Row layout of A3: [ odd: cos (Q) | sin (Q) | b = 0 mod 4: cos (E) | sin (E) | b = 2 mod 4: cos (E) | sin (E) ].
+// One thread = 8 consecutive k < E of one frame: eight runs of the chunk (the four of the second half also give the odd
+// class at k' = Q - k, which lands on an aligned block when shifted by one tap), 256 B out.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// 9 samples x[i0 + j], j = 0..8 (ascending): aligned vector of 8 + one scalar
+template <bool PCM>
+__device__ __forceinline__ void load9_up(const float* xf, const int16_t* xi, int i0, float (&r)[9]) {
+  float v[8];
+  load8<PCM>(xf, xi, i0, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+  r[8] = raw_sample<PCM>(xf, xi, i0 + 8);
+}
+// 9 samples x[i0 - j], j = 0..8 (descending): scalar at i0 + aligned vector of 8 below it
+template <bool PCM>
+__device__ __forceinline__ void load9_down(const float* xf, const int16_t* xi, int i0, float (&r)[9]) {
+  float v[8];
+  load8<PCM>(xf, xi, i0 - 8, v);
+  r[0] = raw_sample<PCM>(xf, xi, i0);
+#pragma unroll
+  for (int j = 1; j < 9; ++j) r[j] = v[8 - j];
+}
+
+}  // namespace
+
+template <bool PCM>
+__global__ void __launch_bounds__(128) fold3_kernel(const Fold2Params P) {
+  const int N = P.n_fft, H = N >> 1, Q = N >> 2, E = N >> 3, per_frame = E >> 3;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < P.total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = t / per_frame;
+    const int k0 = static_cast<int>(t - row * per_frame) << 3;
+    const long long chunk = row / P.F;
+    const int f = static_cast<int>(row - chunk * P.F);
+    const float4 par = P.chunk_par[chunk];
+    const float scale = par.x, pow2 = par.y;
+    const int scaled = par.z != 0.f;
+    const float* xf = PCM ? nullptr : P.x + chunk * P.L;
+    const int16_t* xi = PCM ? P.x16 + chunk * P.L : nullptr;
+    const int pf = f * P.hop;
+    const int s0 = pf - H;                               // source index of tap 0 when nothing is reflected
+    // x1[q] = xs[k], x4[q] = xs[2Q+k], x6[q] = xs[3Q+k], x7[q] = xs[Q+k]   (ascending in q, k = k0 + q)
+    // x2[q] = xs[N-k], x3[q] = xs[2Q-k], x5[q] = xs[Q-k], x8[q] = xs[3Q-k] (descending)
+    float x1[9], x2[9], x3[9], x4[9], x5[9], x6[9], x7[9], x8[9];
+    if (P.vec_ok && s0 >= 0 && s0 + N + 8 <= P.L) {
+      load9_up<PCM>(xf, xi, s0 + k0, x1);
+      load9_up<PCM>(xf, xi, s0 + H + k0, x4);
+      load9_up<PCM>(xf, xi, s0 + H + Q + k0, x6);
+      load9_up<PCM>(xf, xi, s0 + Q + k0, x7);
+      load9_down<PCM>(xf, xi, s0 + N - k0, x2);
+      load9_down<PCM>(xf, xi, s0 + H - k0, x3);
+      load9_down<PCM>(xf, xi, s0 + Q - k0, x5);
+      load9_down<PCM>(xf, xi, s0 + H + Q - k0, x8);
+    } else {
+      const int plen = P.L + N;
+      auto get = [&](int p) -> float {
+        return (p >= 0 && p < plen) ? raw_sample<PCM>(xf, xi, reflect_src(p, H, P.L)) : 0.f;
+      };
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const int k = k0 + q;
+        x1[q] = get(pf + k);         x2[q] = get(pf + N - k);
+        x3[q] = get(pf + H - k);     x4[q] = get(pf + H + k);
+        x5[q] = get(pf + Q - k);     x6[q] = get(pf + H + Q + k);
+        x7[q] = get(pf + Q + k);     x8[q] = get(pf + H + Q - k);
+      }
+    }
+    float oc[8], os[8], c0[8], s0v[8], c2[8], s2v[8], oc2[8], os2[8];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+      const int k = k0 + q;
+      const float w5 = P.win[Q - k], w7 = P.win[Q + k];
+      const float a5 = finish_sample(x5[q], scale, scaled, P.quantize) * pow2;
+      const float a6 = finish_sample(x6[q], scale, scaled, P.quantize) * pow2;
+      float a7 = finish_sample(x7[q], scale, scaled, P.quantize) * pow2;
+      float a8 = finish_sample(x8[q], scale, scaled, P.quantize) * pow2;
+      if (k == 0) {                                      // u[Q] and u[3Q] are one pair, not two
+        a7 = 0.f;
+        a8 = 0.f;
+      }
+      const float fp = w5 * (a5 + a6), fm = w7 * (a7 + a8);   // integer sums are exact; only the window products round
+      const float gp = w5 * (a5 - a6), gm = w7 * (a7 - a8);
+      if (q >= 1) {                                      // odd bins at k' = Q - k: block element 8 - q of [Q-k0-8, Q-k0)
+        oc2[8 - q] = fp - fm;
+        os2[8 - q] = gp + gm;
+      }
+      if (q < 8) {
+        const float wk = P.win[k], wh = P.win[H - k];
+        const float a1 = finish_sample(x1[q], scale, scaled, P.quantize) * pow2;
+        float a2 = finish_sample(x2[q], scale, scaled, P.quantize) * pow2;
+        const float a3 = finish_sample(x3[q], scale, scaled, P.quantize) * pow2;
+        float a4 = finish_sample(x4[q], scale, scaled, P.quantize) * pow2;
+        if (k == 0) {                                    // u[0] and u[H] pair with nothing
+          a2 = 0.f;
+          a4 = 0.f;
+        }
+        const float ep = wk * (a1 + a2), em = wh * (a3 + a4);
+        const float op = wk * (a1 - a2), om = wh * (a3 - a4);
+        const float Pk = ep + em, Pm = fp + fm, Rk = op - om, Rm = gp - gm;
+        const bool z = k == 0;
+        oc[q] = ep - em;
+        os[q] = z ? 0.f : op + om;
+        c0[q] = Pk + Pm;
+        c2[q] = Pk - Pm;
+        s0v[q] = z ? 0.f : Rk - Rm;
+        s2v[q] = z ? 0.f : Rk + Rm;
+      }
+    }
+    const size_t base = static_cast<size_t>(row) * N;
+    split_store(P.a_hi, P.a_lo, base + k0, oc);
+    split_store(P.a_hi, P.a_lo, base + Q + k0, os);
+    split_store(P.a_hi, P.a_lo, base + (Q - k0 - 8), oc2);
+    split_store(P.a_hi, P.a_lo, base + Q + (Q - k0 - 8), os2);
+    split_store(P.a_hi, P.a_lo, base + H + k0, c0);
+    split_store(P.a_hi, P.a_lo, base + H + E + k0, s0v);
+    split_store(P.a_hi, P.a_lo, base + H + Q + k0, c2);
+    split_store(P.a_hi, P.a_lo, base + H + Q + E + k0, s2v);
+    if (k0 == 0) {
+      auto xs = [&](int tap) -> float {
+        return finish_sample(raw_sample<PCM>(xf, xi, reflect_src(pf + tap, H, P.L)), scale, scaled, P.quantize) * pow2;
+      };
+      const float wq = P.win[Q], we = P.win[E], w3 = P.win[Q + E];     // w[3E] = w[N - 5E] ...: w[Q+E] = w[H+Q-E+...]
+      const float xe = xs(E), x7e = xs(N - E), x3e = xs(Q + E), x5e = xs(H + E);
+      const float e_odd = wq * (xs(Q) - xs(H + Q));                         // O[Q]
+      const float e_m0 = we * (xe + x7e) + w3 * (x3e + x5e);                // P[E] = u[E] + u[N-E] + u[3E] + u[5E]
+      const float e_m2 = we * (xe - x7e) - w3 * (x3e - x5e);                // R[E]
+      P.edge[row] = make_float4(e_odd, e_m0, e_m2, 0.f);                    // class 0 = odd, 1 = 0 mod 4, 2 = 2 mod 4
     }
   }
 }
@@ -166,14 +307,22 @@ int launch_fold2(avld_ctx* c, int n, cudaStream_t st) {
   P.quantize = c->cur_quantize;
   P.vec_ok = (c->L % 8 == 0) && (c->p.hop % 8 == 0) && (reinterpret_cast<uintptr_t>(P.x) % 16 == 0) &&
              (reinterpret_cast<uintptr_t>(P.x16) % 16 == 0);
-  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / 32);
+  const bool three = c->f2_levels == 3;
+  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / (three ? 64 : 32));
   const long long blocks = (P.total + 255) / 256;
   const long long cap = static_cast<long long>(c->sm_count) * 32;
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
   {
     LaunchScope ls(c, ST_FOLD, st);
-    if (P.x16 != nullptr) fold2_kernel<true><<<grid, 256, 0, st>>>(P);
-    else fold2_kernel<false><<<grid, 256, 0, st>>>(P);
+    if (three) {      // ~145 registers per thread: 128-thread blocks keep three blocks per SM resident
+      const long long b3 = (P.total + 127) / 128;
+      const int g3 = static_cast<int>(b3 < 2 * cap ? b3 : 2 * cap);
+      if (P.x16 != nullptr) fold3_kernel<true><<<g3, 128, 0, st>>>(P);
+      else fold3_kernel<false><<<g3, 128, 0, st>>>(P);
+    } else {
+      if (P.x16 != nullptr) fold2_kernel<true><<<grid, 256, 0, st>>>(P);
+      else fold2_kernel<false><<<grid, 256, 0, st>>>(P);
+    }
   }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;

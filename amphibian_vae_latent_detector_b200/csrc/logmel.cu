@@ -74,7 +74,8 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
 
 struct PostParams {
   const float* melpow;  // [n*R][M]
-  long long plane2;     // fold2: offset of the second (odd-bin) plane, added in a fixed order; 0 = single plane
+  long long plane2;     // fold2: stride between the per-class planes, added in a fixed order; 0 = single plane
+  int n_planes;
   float* feat;          // [n][T][M]
   int R, F, M, T, crop_start, pad_left, frames_copy;
   float amin, top_db;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
   float mx = -INFINITY;
   bool has_nan = false;
   for (int i = tid; i < n; i += blockDim.x) {
-    const float v = P.plane2 ? src[i] + src[P.plane2 + i] : src[i];
+    float v = src[i];
+    for (int pl = 1; pl < P.n_planes; ++pl) v += src[pl * P.plane2 + i];
     s_db[i] = v;
     has_nan |= (v != v);
     mx = fmaxf(mx, v);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
 
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
-  PostParams P{c->d_melpow, c->dft_fold2 ? c->melpow_plane : 0, feat, c->dft_fold ? c->F : c->R, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
+  PostParams P{c->d_melpow, c->dft_fold2 ? c->melpow_plane : 0, c->dft_fold2 ? c->f2_classes : 1, feat, c->dft_fold ? c->F : c->R, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
   const size_t smem = static_cast<size_t>(c->F) * c->M * sizeof(float);
   static bool configured = false;
   if (!configured) {

@@ -72,8 +72,8 @@ def traffic_of(mode: str, chunks_per_launch: int):
         d = json.loads(p.read_text())
     except Exception:
         return None
-    kernel = {"fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)
-    if d.get("kernel") != kernel or int(d.get("chunks_per_launch", 0)) != int(chunks_per_launch):
+    kernel = {"fold3": "dftf3_kernel", "fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)
+    if d.get("kernel") != kernel or d.get("mode", "fold2") != mode or int(d.get("chunks_per_launch", 0)) != int(chunks_per_launch):
         return None
     return {"bytes_per_launch": d["traffic_bytes"], "dram_read": d["dram_bytes_read"], "dram_write": d["dram_bytes_write"],
             "source": d.get("source")}
@@ -360,7 +360,8 @@ def main():
         if fold and fold["ms"] > 0:   # reads the chunk once from HBM (re-reads hit L1/L2), writes the folded hi+lo rows
             hbm["fold_kernel"] = round((4 * CHUNK_LEN + 4 * 376 * 2048) * chunks_timed / (fold["ms"] / 1e3) / 1e9, 1)
         info = eng_info
-        kname = {"fold2": "dftf3_kernel (twice-folded windowed DFT as GEMM, cta_group::2, + |X|^2 + mel)",
+        kname = {"fold3": "dftf3_kernel (windowed DFT as GEMM, folded twice and a third time for the even bins, cta_group::2, + |X|^2 + mel)",
+                 "fold2": "dftf3_kernel (twice-folded windowed DFT as GEMM, cta_group::2, + |X|^2 + mel)",
                  "fold": "dftf2_kernel (once-folded windowed DFT as GEMM, cta_group::2, + |X|^2 + mel)",
                  "fold1": "gemm3_kernel<256,*,EPI_DFTF> (once-folded windowed DFT as GEMM + |X|^2 + mel)",
                  "direct": "gemm3_kernel<256,128,EPI_DFT> (windowed DFT as GEMM + |X|^2 + mel)"}[info["mode"]]
