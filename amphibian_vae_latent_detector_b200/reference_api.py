@@ -648,3 +648,142 @@ def detect_species_map(wav_path, *, config_path=None, encoder_pt=None, encoder_y
     sess.set_params(load_json(sess.config_path))
     sess.encoder = encoder if encoder is not None else load_encoder(sess.encoder_pt, sess.encoder_yaml, root, device)
     return sess.predict_one(wav_p)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Row N4b -- 07_encode_wav_to_latent.py: output unpacking, guarded forward and the target_frames probe for foreign
+# encoders (07:195-199, :264-409).  Host logic around an arbitrary nn.Module; only wav_to_mel runs on the GPU library.
+# ----------------------------------------------------------------------------------------------------------
+def find_first_linear(module: torch.nn.Module) -> torch.nn.Linear:
+    """07:195-199."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.Linear):
+            return m
+    raise RuntimeError("No encontré ningún nn.Linear dentro del encoder.")
+
+
+_VECTOR_KEYS_07 = ("z", "latent", "mu", "mean", "embedding", "enc")        # 07:278 (core:283 has no "enc")
+
+
+def extract_vector(out: Any) -> torch.Tensor:
+    """07:264-297: encoder output -> ``[B, D]`` tensor.  Tensor as is; list/tuple -> first tensor (a VAE's ``mu``); dict ->
+    first present of ``z, latent, mu, mean, embedding, enc`` else the first tensor value; ``[B, T', C]`` -> mean over
+    ``T'`` (an empty ``T'`` gives ``[B, 0]``); more than two dims -> flattened per row."""
+    t: Optional[torch.Tensor]
+    if isinstance(out, torch.Tensor):
+        t = out
+    elif isinstance(out, (list, tuple)):
+        t = next((o for o in out if isinstance(o, torch.Tensor)), None)
+        if t is None:
+            raise ValueError("Salida list/tuple sin tensors.")
+    elif isinstance(out, dict):
+        t = next((out[k] for k in _VECTOR_KEYS_07 if isinstance(out.get(k), torch.Tensor)), None)
+        if t is None:
+            t = next((v for v in out.values() if isinstance(v, torch.Tensor)), None)
+        if t is None:
+            raise ValueError("Salida dict sin tensors.")
+    else:
+        raise ValueError(f"No sé interpretar salida: {type(out)}")
+    if t.ndim == 3:
+        if t.shape[1] == 0:
+            return t[:, :0]
+        t = t.mean(dim=1)
+    if t.ndim > 2:
+        t = t.view(t.shape[0], -1)
+    return t
+
+
+def try_forward(encoder: torch.nn.Module, x: torch.Tensor) -> Tuple[bool, Optional[torch.Tensor], Optional[str]]:
+    """07:300-310 -> ``(ok, vec, err)``; any exception of the forward or the unpacking becomes ``(False, None, str(e))``."""
+    try:
+        with torch.no_grad():
+            vec = extract_vector(encoder(x))
+    except Exception as e:      # noqa: BLE001 -- the reference reports, it does not raise
+        return False, None, str(e)
+    if vec.numel() == 0 or vec.shape[1] == 0:
+        return False, None, "Salida vacía (numel=0)."
+    return True, vec, None
+
+
+@torch.no_grad()
+def probe_linear_input_shape(encoder: torch.nn.Module, linear: torch.nn.Linear, x: torch.Tensor):
+    """07:317-352 -> ``(ok, (N, F) | None, err | None)``: the shape entering ``linear`` during ``encoder(x)``, with every
+    leading dimension collapsed into N.  A forward that fails *after* the hook fired still reports the shape (with the
+    error text)."""
+    seen: Dict[str, Any] = {"shape": None}
+
+    def pre_hook(_mod, inputs):
+        inp = inputs[0] if inputs else None
+        if isinstance(inp, torch.Tensor) and inp.ndim >= 2 and inp.shape[-1] > 0:
+            feat = int(inp.shape[-1])
+            seen["shape"] = (int(inp.numel() // feat), feat)
+
+    handle = linear.register_forward_pre_hook(pre_hook)
+    err: Optional[str] = None
+    try:
+        encoder(x)
+    except Exception as e:      # noqa: BLE001
+        err = str(e)
+    finally:
+        handle.remove()
+    if seen["shape"] is None:
+        return False, None, err if err is not None else "No pude capturar la entrada al Linear (hook no disparó)."
+    return True, seen["shape"], err
+
+
+def auto_find_frames_with_hook(encoder: torch.nn.Module, wav_path: Path, device, sr: int, duration: float, n_mels: int,
+                               fmin: float, fmax: float, hop_length: int, n_fft: int, start_frames: int, max_frames: int,
+                               step: int) -> int:
+    """07:355-409: the first ``target_frames`` in ``start, start + step, ... <= max_frames`` (start >= 8) for which the
+    tensor reaching the encoder's first ``nn.Linear`` has the width that layer expects and is not empty.  The log-mel
+    features are computed once at the largest size the loop can ask for and cropped / padded per candidate exactly as
+    ``crop_or_pad_time`` does, instead of one feature pass per candidate."""
+    linear = find_first_linear(encoder)
+    want = int(linear.in_features)
+    start = max(8, int(start_frames))
+    step = max(1, int(step))
+    max_frames = max(start, int(max_frames))
+    dev = torch.device(device) if not isinstance(device, torch.device) else device
+    chunk_len = int(sr * duration)
+    n_native = 1 + chunk_len // hop_length
+    # one GPU pass: ask for every frame (target_frames = native count), crop / pad on the host per candidate
+    full = wav_to_mel(Path(wav_path), sr=sr, duration=duration, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length,
+                      n_fft=n_fft, target_frames=n_native).numpy()
+    for frames in range(start, max_frames + 1, step):
+        mel = torch.from_numpy(crop_or_pad_time(full, frames).astype(np.float32))
+        x = mel.T.unsqueeze(0).unsqueeze(0).to(dev)                  # [1, 1, T, M] (07:395)
+        ok, shp, _ = probe_linear_input_shape(encoder, linear, x)
+        if ok and shp is not None and shp[1] == want and shp[0] > 0:
+            return frames
+    raise SystemExit("❌ No encontré un target_frames válido usando el hook.\n"
+                     f"Probé frames desde {start} hasta {max_frames} step={step}.\n"
+                     "Tip: sube --auto-max-frames (ej. 4096) o baja --auto-step (ej. 1).")
+
+
+def encode_wav_report(wav_path: Path, encoder: torch.nn.Module, *, device="cuda", sr: int = 48000, duration: float = 3.0,
+                      n_mels: int = 64, fmin: float = 150.0, fmax: float = 15000.0, hop_length: int = 384,
+                      n_fft: int = 2048, target_frames: int = 192, auto_frames: bool = False, auto_max_frames: int = 512,
+                      auto_step: int = 8, jsonl: bool = False, precision: int = 6, log=print) -> np.ndarray:
+    """07 ``main`` after the encoder is loaded (07:472-527): optional frame search, features on the GPU library, the
+    encoder module's own forward (any architecture), and the script's two output formats."""
+    import json as _json
+    wav_path = Path(wav_path)
+    frames = auto_find_frames_with_hook(encoder, wav_path, device, sr, duration, n_mels, fmin, fmax, hop_length, n_fft,
+                                        target_frames, auto_max_frames, auto_step) if auto_frames else target_frames
+    log(f"✅ target_frames usado: {frames}")
+    mel = wav_to_mel(wav_path, sr=sr, duration=duration, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length,
+                     n_fft=n_fft, target_frames=frames)
+    dev = torch.device(device) if not isinstance(device, torch.device) else device
+    x = mel.T.unsqueeze(0).unsqueeze(0).to(dev)
+    ok, vec, err = try_forward(encoder.to(dev), x)
+    if not ok or vec is None:
+        raise SystemExit(f"❌ Forward falló incluso con target_frames={frames}. Error: {err}")
+    v = vec.detach().cpu().numpy()[0]
+    if jsonl:
+        log(_json.dumps({"wav": str(wav_path), "latent_dim": int(v.size), "vector": v.astype(float).tolist()},
+                        ensure_ascii=False))
+    else:
+        with np.printoptions(precision=int(precision), suppress=True, linewidth=180):
+            log(f"✅ Latent dim: {v.size}")
+            log(str(v))
+    return v

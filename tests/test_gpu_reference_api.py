@@ -95,3 +95,37 @@ def test_fit_species_and_helpers_vs_oracle():
     assert api.quantile_safe(np.array([], dtype=np.float32), 0.5) == 0.0
     assert api.summarize_dist(rho) == hp.summarize_dist(rho)
     assert api.l2(Z[0]) == pytest.approx(hp.l2(Z[0]), rel=1e-6)
+
+
+def test_auto_find_frames_and_report(tmp_path):
+    """07:355-409 / :472-527 -- the frame search walks start, start + step, ... and returns the first target_frames whose
+    flattened conv output matches the first Linear (stand-in encoder: 128 x (T // 16) x 4 == 6144 <=> 192 <= T < 208)."""
+    import json
+    import wave
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
+    x, _ = synth.make_chunks(1, 144000, seed=9, special_every=0)
+    pcm = torch.clamp(torch.round(x[0] * 32767.0), -32768, 32767).to(torch.int16).numpy()
+    wav = tmp_path / "a.wav"
+    with wave.open(str(wav), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(48000); w.writeframes(pcm.astype("<i2").tobytes())
+    enc = build_standin_encoder(seed=123)
+    kw = dict(sr=48000, duration=3.0, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048)
+    assert api.auto_find_frames_with_hook(enc, wav, "cpu", start_frames=192, max_frames=512, step=8, **kw) == 192
+    assert api.auto_find_frames_with_hook(enc, wav, "cpu", start_frames=100, max_frames=512, step=8, **kw) == 196
+    assert api.auto_find_frames_with_hook(enc, wav, "cpu", start_frames=1, max_frames=512, step=23, **kw) == 192   # 8 + 23 k
+    with pytest.raises(SystemExit):                                  # 8, 58, ..., 208, 258, ...: never in [192, 208)
+        api.auto_find_frames_with_hook(enc, wav, "cpu", start_frames=1, max_frames=512, step=50, **kw)
+    with pytest.raises(SystemExit):
+        api.auto_find_frames_with_hook(enc, wav, "cpu", start_frames=8, max_frames=150, step=8, **kw)
+    lines = []
+    v = api.encode_wav_report(wav, enc, device="cpu", jsonl=True, auto_frames=True, target_frames=100, log=lines.append, **kw)
+    assert lines[0] == "✅ target_frames usado: 196"
+    rec = json.loads(lines[1])
+    assert rec["latent_dim"] == 128 and np.allclose(rec["vector"], v)
+    # same vector as the batched CUDA encoder gives for the 192-frame crop?  no: 196 frames is a different crop; check 192
+    v192 = api.encode_wav_report(wav, enc, device="cpu", log=lambda s: None, **kw)
+    z = api.encode_wav_to_latent(enc, wav, None, duration=3.0, sr=48000, n_mels=64, fmin=150.0, fmax=15000.0,
+                                 hop_length=384, n_fft=2048, target_frames=192)
+    assert np.max(np.abs(v192 - z)) / np.max(np.abs(z)) < 1e-3
