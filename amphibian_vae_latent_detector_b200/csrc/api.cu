@@ -23,7 +23,9 @@ static int encode_pass(avld_ctx* c, const float* x, const int16_t* x16, float* m
 
 extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, int64_t n, float target_rms,
                            float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c && x && mu, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(x && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
   AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -38,7 +40,9 @@ extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, 
 static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_bytes, int64_t n, int quantize_pcm16,
                                    const float* centroid, const double* thr, const int32_t* priority_rank, int32_t K,
                                    int32_t* pred_host, float* best_host, float* mu_host, uint8_t* ok_host) {
-  AVLD_CHECK(c && x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0 && K >= 1 && K <= 64, AVLD_ERR_INVALID, "bad n / K");
   AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
   AVLD_CUDA(cudaSetDevice(c->device));

@@ -236,18 +236,18 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         if (P.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+          for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
         }
         if (P.pool == 2) {     // partners: lane ^ 1 (w), lane ^ 8 (h): same warp
           float u[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], 1);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
+          for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], kTW);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
+          for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
         }
         if (writer && c0 < P.Cout) {
           __align__(16) __nv_bfloat16 hi[16];

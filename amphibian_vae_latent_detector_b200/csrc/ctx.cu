@@ -325,6 +325,18 @@ static int build_ctx(avld_ctx* c) {
     const bool two = mode != nullptr && strcmp(mode, "fold2") == 0;
     c->dft_fold2 = c->dft_fold && (mode == nullptr || two) && (p.n_fft % 512 == 0) && (c->sm_count % 2 == 0);
     c->f2_levels = two ? 2 : 3;
+    if (c->dft_fold2) {
+      // the folded kernel keeps one 16-byte tap record per accumulator column of every work item in shared memory and
+      // has room for 8 items of 160 bins; other geometries (many more FFT bins) use the once-folded kernel
+      int items = 0;
+      const int mods[3][2] = {{2, 1}, {c->f2_levels == 3 ? 4 : 2, 0}, {4, 2}};
+      for (int ci = 0; ci < (c->f2_levels == 3 ? 3 : 2); ++ci) {
+        int nb = 0;
+        for (int b = bin_lo; b <= bin_hi; ++b) nb += (b % mods[ci][0]) == mods[ci][1];
+        items += (nb + 159) / 160;
+      }
+      if (items > 8 || static_cast<size_t>(items) * 160 * sizeof(MelTap) > 12288 - 512) c->dft_fold2 = 0;
+    }
   }
   c->n_tiles2 = (nbins + 255) / 256;
   c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;

@@ -111,12 +111,12 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectConvParams
                   if (co0 + q < P.Cout) a[q] = fmaf(v, s_w[(co0 + q) * kk + wi], a[q]);
               }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) best[q] = fmaxf(best[q], a[q]);
+          for (int q = 0; q < 8; ++q) best[q] = max_nan(best[q], a[q]);
         }
       }
       for (int q = 0; q < 8 && co0 + q < P.Cout; ++q) {
         float t = best[q];
-        if (P.relu) t = fmaxf(t, 0.f);
+        if (P.relu) t = relu_nan(t);
         const __nv_bfloat16 h = __float2bfloat16_rn(t);
         P.out_hi[obase + co0 + q] = h;
         P.out_lo[obase + co0 + q] = __float2bfloat16_rn(t - __bfloat162float(h));
@@ -179,14 +179,14 @@ __global__ void __launch_bounds__(256) conv1_kernel(const DirectConvParams P) {
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) a = fmaf(patch[ph + kh][pw + kw], wreg[q][kh * 3 + kw], a);
-          best[q] = fmaxf(best[q], a);
+          best[q] = max_nan(best[q], a);
         }
     __align__(16) __nv_bfloat16 hi[8];
     __align__(16) __nv_bfloat16 lo[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float t = best[q];
-      if (P.relu) t = fmaxf(t, 0.f);
+      if (P.relu) t = relu_nan(t);
       hi[q] = __float2bfloat16_rn(t);
       lo[q] = __float2bfloat16_rn(t - __bfloat162float(hi[q]));
     }
@@ -415,7 +415,9 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
 }
 
 extern "C" int avld_encoder_forward(avld_ctx* c, const float* feat, float* mu, int64_t n, void* stream) {
-  AVLD_CHECK(c && feat && mu, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(feat && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t i = 0; i < n; i += c->max_batch) {

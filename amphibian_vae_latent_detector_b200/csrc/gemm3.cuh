@@ -381,7 +381,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float t = __uint_as_float(v[j]) + s_bias[n0 + j];
-                if (P.relu) t = fmaxf(t, 0.f);
+                if (P.relu) t = relu_nan(t);
                 o[j] = t;
               }
               if (P.out_f32 != nullptr) {
@@ -463,18 +463,18 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
             if (P.relu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+              for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
             }
             if (P.pool == 2) {   // 16 independent shuffles in flight per stage
               float u[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], 1);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
+              for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
 #pragma unroll
               for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], P.tw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], u[j]);
+              for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
             }
             if (writer && n0 < P.Cout) {
               __align__(16) __nv_bfloat16 hi[16];

@@ -192,14 +192,18 @@ static int features_pass(avld_ctx* c, const float* x, float* feat, uint8_t* ok, 
 }
 
 extern "C" int avld_logmel(avld_ctx* c, const float* y, float* feat, int64_t n, void* stream) {
-  AVLD_CHECK(c && y && feat, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(y && feat, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
   return features_pass(c, y, feat, nullptr, nullptr, n, false, 0.f, 0.f, 0.f, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int avld_normalize_logmel(avld_ctx* c, const float* x, float* feat, uint8_t* ok, float* rms, int64_t n,
                                      float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c && x && feat, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(x && feat, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
   return features_pass(c, x, feat, ok, rms, n, true, target_rms, rms_min, eps, quantize_pcm16,
                        static_cast<cudaStream_t>(stream));

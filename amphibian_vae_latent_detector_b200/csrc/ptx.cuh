@@ -9,6 +9,10 @@
 
 namespace avld {
 
+// ReLU / max as torch computes them: NaN propagates (fmaxf would drop it and turn a poisoned chunk into a plausible one)
+__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

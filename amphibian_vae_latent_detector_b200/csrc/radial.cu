@@ -150,7 +150,9 @@ using namespace avld;
 
 extern "C" int avld_centroid_accumulate(avld_ctx* c, const float* Z, const int32_t* label, double* sum, int64_t* cnt,
                                         int64_t n, int32_t K, int32_t D, void* stream) {
-  AVLD_CHECK(c && Z && label && sum && cnt, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(Z && label && sum && cnt, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && K <= 64 && D >= 1 && static_cast<size_t>(K) * D * 8 <= 96 * 1024, AVLD_ERR_UNSUPPORTED,
              "K must be in [1,64] and K*D*8 <= 96 KB");
   if (n <= 0) return AVLD_OK;
@@ -169,7 +171,9 @@ extern "C" int avld_centroid_accumulate(avld_ctx* c, const float* Z, const int32
 
 extern "C" int avld_radii(avld_ctx* c, const float* Z, const float* centroid, float* radii, int64_t n, int32_t K,
                           int32_t D, void* stream) {
-  AVLD_CHECK(c && Z && centroid && radii, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(Z && centroid && radii, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && D >= 1 && static_cast<size_t>(K) * D * 4 <= 96 * 1024, AVLD_ERR_UNSUPPORTED, "K*D*4 must be <= 96 KB");
   if (n <= 0) return AVLD_OK;
   const size_t smem = static_cast<size_t>(K) * D * sizeof(float);
@@ -187,7 +191,9 @@ extern "C" int avld_radii(avld_ctx* c, const float* Z, const float* centroid, fl
 
 extern "C" int avld_decide(avld_ctx* c, const float* radii, const double* thr, const int32_t* priority_rank,
                            int32_t* pred, float* best_d, int64_t n, int32_t K, void* stream) {
-  AVLD_CHECK(c && radii && thr && priority_rank && pred && best_d, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(radii && thr && priority_rank && pred && best_d, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1, AVLD_ERR_INVALID, "K must be >= 1");
   if (n <= 0) return AVLD_OK;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(c->sm_count) * 8));
@@ -198,7 +204,7 @@ extern "C" int avld_decide(avld_ctx* c, const float* radii, const double* thr, c
 
 extern "C" int avld_order_stats(avld_ctx* c, const float* radii, const int32_t* label, int64_t n, int32_t K,
                                 const avld_rank_query* queries, int32_t n_q, float* out, void* stream) {
-  AVLD_CHECK(c && radii && label && queries && out, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c && radii && label && queries && out, AVLD_ERR_INVALID, "NULL argument");   // an order statistic of
   AVLD_CHECK(n > 0 && K >= 1 && n_q >= 1 && n_q <= 4096, AVLD_ERR_INVALID, "bad n / K / n_q");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   struct QState { uint32_t lo; int64_t rank; };

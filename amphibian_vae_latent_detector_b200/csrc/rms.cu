@@ -146,7 +146,11 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     s_scale = scale;
     s_scaled = scaled;
     s_pow2 = ldexpf(1.0f, s);
-    if (P.inv2) P.inv2[c] = ldexpf(1.0f, -2 * (s + P.dft_scale_log2));
+    // A chunk holding NaN / Inf has a non-finite rms.  The PCM_16 round trip would launder it into digital silence
+    // (cvt.rni(NaN) = 0) and a perfectly plausible latent; poisoning the power un-scale factor instead makes the
+    // chunk's features, latent and distances NaN, i.e. NO_DETECT with best distance inf -- what the reference's float
+    // path (librosa.load -> melspectrogram -> encoder, 09:416-436) yields for such a file.
+    if (P.inv2) P.inv2[c] = (rms - rms == 0.0f) ? ldexpf(1.0f, -2 * (s + P.dft_scale_log2)) : NAN;
     if (P.chunk_par) P.chunk_par[c] = make_float4(scale, ldexpf(1.0f, s), scaled ? 1.0f : 0.0f, 0.0f);
     if (P.ok) P.ok[c] = P.normalize ? static_cast<uint8_t>(scaled) : static_cast<uint8_t>(1);
     if (P.rms) P.rms[c] = rms;
@@ -389,7 +393,9 @@ using namespace avld;
 
 extern "C" int avld_rms_normalize(avld_ctx* c, const float* x, float* y, uint8_t* ok, float* rms, int64_t n,
                                   float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c && x && y, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(x && y, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t step = 1 << 20;   // grid size limit is far above this; chunk the launch only for int safety
