@@ -140,6 +140,7 @@ struct avld_ctx {
   avld::MelTap* d_taps3 = nullptr; // [f2_items * 160], .pad = bits of the edge coefficient
   float4* d_edge = nullptr;        // [max_batch * F + 256] per frame: the self-paired tap of each bin class
   float* d_win = nullptr;          // [N/2 + 1] periodic Hann
+  bool planes_dirty = false;       // a GEMM pass accumulated into the planes and logmel_post has not consumed them yet
   long long melpow_plane = 0;      // elements per mel-power plane (fold2: one plane per bin class)
 
   // per-pass scratch (max_batch chunks)

@@ -538,6 +538,7 @@ static int build_ctx(avld_ctx* c) {
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
   c->melpow_plane = static_cast<long long>(c->max_batch) * c->R * c->M;
   AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 3 : 1)));
+  AVLD_CUDA(cudaMemset(c->d_melpow, 0, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 3 : 1) * sizeof(float)));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
   AVLD_TRY(dev_alloc(&c->d_ok, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_rms, c->max_batch));

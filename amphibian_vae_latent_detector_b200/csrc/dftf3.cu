@@ -329,9 +329,11 @@ int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st) {
     configured = true;
   }
   AVLD_CHECK(static_cast<size_t>(P.num_items) * kBN * sizeof(MelTap) <= kExtra - 512, AVLD_ERR_UNSUPPORTED, "too many FFT bins");
-  // the epilogue accumulates mel outputs with atomicAdd, one plane per bin class
-  for (int pl = 0; pl < c->f2_classes; ++pl)
-    AVLD_CUDA(cudaMemsetAsync(c->d_melpow + pl * c->melpow_plane, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
+  // the epilogue accumulates mel outputs with atomicAdd, one plane per bin class; the planes are zero on entry: cleared at
+  // context creation and again by logmel_post_kernel as it reads them (the two always run as a pair)
+  if (c->planes_dirty)     // only after a pass that failed between the two kernels
+    AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(c->melpow_plane) * c->f2_classes * sizeof(float), st));
+  c->planes_dirty = true;
   const int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
   if (grid < 2) return AVLD_OK;
   LaunchScope ls(c, ST_STFT_MEL, st);

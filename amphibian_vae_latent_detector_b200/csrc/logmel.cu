@@ -73,7 +73,8 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
 }
 
 struct PostParams {
-  const float* melpow;  // [n*R][M]
+  float* melpow;        // [n*R][M]; fold2: the per-class planes are zeroed again right after they are read, so the
+                        // GEMM epilogue can accumulate into them on the next pass without a separate memset
   long long plane2;     // fold2: stride between the per-class planes, added in a fixed order; 0 = single plane
   int n_planes;
   float* feat;          // [n][T][M]
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
   __shared__ float s_red_f[16];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int n = P.F * P.M;
-  const float* __restrict__ src = P.melpow + static_cast<size_t>(c) * P.R * P.M;   // frames 0..F-1 are contiguous
+  float* __restrict__ src = P.melpow + static_cast<size_t>(c) * P.R * P.M;   // frames 0..F-1 are contiguous
 
   // ref = np.max(S); NaN anywhere poisons the chunk exactly like numpy's max would
   float mx = -INFINITY;
@@ -109,6 +110,9 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
   for (int i = tid; i < n; i += blockDim.x) {
     float v = src[i];
     for (int pl = 1; pl < P.n_planes; ++pl) v += src[pl * P.plane2 + i];
+    if (P.plane2) {
+      for (int pl = 0; pl < P.n_planes; ++pl) src[pl * P.plane2 + i] = 0.f;
+    }
     s_db[i] = v;
     has_nan |= (v != v);
     mx = fmaxf(mx, v);
@@ -169,6 +173,7 @@ int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st) {
     configured = true;
   }
   { LaunchScope ls(c, ST_LOGMEL_POST, st); logmel_post_kernel<<<n, 512, smem, st>>>(P); }
+  c->planes_dirty = false;
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }

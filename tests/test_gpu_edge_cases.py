@@ -119,3 +119,47 @@ def test_other_feature_parameters_vs_oracle(kw):
     errs = [rel(feat[i].cpu().numpy(), fo[i]) for i in range(len(fo))]
     assert max(errs) < 2e-4, (eng.dft_info()["mode"], errs)
     eng.close()
+
+
+def test_outputs_do_not_overrun_their_buffers(engine3s):
+    """Every caller-owned output lives inside a larger allocation with sentinel bytes on both sides (the pool has no
+    compute-sanitizer: this is the bounds check for writes).  Odd n so that tile tails are exercised."""
+    from amphibian_vae_latent_detector_b200 import synth
+    e, n, pad = engine3s, 37, 4096
+    x, lab = synth.make_chunks(n, L, seed=12, special_every=9)
+    X = x.cuda()
+
+    def guarded(shape, dtype):
+        numel = int(np.prod(shape))
+        big = torch.full((numel + 2 * pad,), 77, dtype=dtype, device="cuda")
+        return big, big[pad:pad + numel].view(*shape)
+
+    def intact(big, numel):
+        return bool((big[:pad] == 77).all() and (big[pad + numel:] == 77).all())
+
+    lib, h, st = e.lib, e._h, torch.cuda.current_stream().cuda_stream
+    big_y, y = guarded((n, L), torch.float32)
+    big_ok, ok = guarded((n,), torch.uint8)
+    big_rms, rms = guarded((n,), torch.float32)
+    _lib.check(lib.avld_rms_normalize(h, X.data_ptr(), y.data_ptr(), ok.data_ptr(), rms.data_ptr(), n, 0.05, 1e-4, 1e-8, 1, st))
+    big_f, feat = guarded((n, 192, 64), torch.float32)
+    _lib.check(lib.avld_normalize_logmel(h, X.data_ptr(), feat.data_ptr(), ok.data_ptr(), rms.data_ptr(), n, 0.05, 1e-4, 1e-8, 1, st))
+    big_mu, mu = guarded((n, 128), torch.float32)
+    _lib.check(lib.avld_encoder_forward(h, feat.data_ptr(), mu.data_ptr(), n, st))
+    big_mu2, mu2 = guarded((n, 128), torch.float32)
+    _lib.check(lib.avld_encode(h, X.data_ptr(), mu2.data_ptr(), ok.data_ptr(), n, 0.05, 1e-4, 1e-8, 1, st))
+    cent = torch.randn(4, 128, device="cuda")
+    big_r, radii = guarded((n, 4), torch.float32)
+    _lib.check(lib.avld_radii(h, mu.data_ptr(), cent.data_ptr(), radii.data_ptr(), n, 4, 128, st))
+    big_p, pred = guarded((n,), torch.int32)
+    big_b, best = guarded((n,), torch.float32)
+    thr = torch.full((4,), 50.0, dtype=torch.float64, device="cuda")
+    prio = torch.arange(4, dtype=torch.int32, device="cuda")
+    _lib.check(lib.avld_decide(h, radii.data_ptr(), thr.data_ptr(), prio.data_ptr(), pred.data_ptr(), best.data_ptr(), n, 4, st))
+    torch.cuda.synchronize()
+    for name, big, numel in (("y", big_y, n * L), ("ok", big_ok, n), ("rms", big_rms, n), ("feat", big_f, n * 192 * 64),
+                             ("mu", big_mu, n * 128), ("mu2", big_mu2, n * 128), ("radii", big_r, n * 4),
+                             ("pred", big_p, n), ("best", big_b, n)):
+        assert intact(big, numel), name
+    assert torch.equal(mu, mu2)
+    assert not bool((y == 77).all()) and not bool((feat == 77).any())
