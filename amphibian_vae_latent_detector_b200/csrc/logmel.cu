@@ -107,15 +107,32 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
   // ref = np.max(S); NaN anywhere poisons the chunk exactly like numpy's max would
   float mx = -INFINITY;
   bool has_nan = false;
-  for (int i = tid; i < n; i += blockDim.x) {
-    float v = src[i];
-    for (int pl = 1; pl < P.n_planes; ++pl) v += src[pl * P.plane2 + i];
-    if (P.plane2) {
-      for (int pl = 0; pl < P.n_planes; ++pl) src[pl * P.plane2 + i] = 0.f;
+  if (P.plane2 && (P.M & 3) == 0 && (P.plane2 & 3) == 0) {
+    // folded STFT: sum the per-class planes in a fixed order and clear them for the next pass, 16 bytes at a time
+    float4* src4 = reinterpret_cast<float4*>(src);
+    const long long p4 = P.plane2 >> 2;
+    for (int i = tid; i < (n >> 2); i += blockDim.x) {
+      float4 v = src4[i];
+      for (int pl = 1; pl < P.n_planes; ++pl) {
+        const float4 u = src4[pl * p4 + i];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      for (int pl = 0; pl < P.n_planes; ++pl) src4[pl * p4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(s_db)[i] = v;
+      has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
     }
-    s_db[i] = v;
-    has_nan |= (v != v);
-    mx = fmaxf(mx, v);
+  } else {
+    for (int i = tid; i < n; i += blockDim.x) {
+      float v = src[i];
+      for (int pl = 1; pl < P.n_planes; ++pl) v += src[pl * P.plane2 + i];
+      if (P.plane2) {
+        for (int pl = 0; pl < P.n_planes; ++pl) src[pl * P.plane2 + i] = 0.f;
+      }
+      s_db[i] = v;
+      has_nan |= (v != v);
+      mx = fmaxf(mx, v);
+    }
   }
   mx = block_reduce<float>(mx, s_red_f, true);
   const float nan_cnt = block_reduce<float>(has_nan ? 1.f : 0.f, s_red_f, false);

@@ -19,12 +19,16 @@ Everything numeric runs on the GPU: ``device`` arguments are accepted for signat
 """
 from __future__ import annotations
 
+import os
+
 import importlib
 import json
 import sys
 import wave
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -39,6 +43,7 @@ PRIORITY_ORDER = [
 ]
 
 _ENGINES: Dict[tuple, Engine] = {}
+_IO_POOL = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 4)))
 _LOADED: Dict[tuple, int] = {}
 
 
@@ -184,19 +189,28 @@ def encode_wavs_to_latents(encoder: torch.nn.Module, wav_paths: Sequence[Path], 
     mel_kw = dict(sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length, n_fft=n_fft,
                   target_frames=target_frames)
     chunk_len = int(sr * duration)
-    eng = _engine_with_encoder(encoder, chunk_len, device if device is not None else 0, **mel_kw)
-    rows, failed = [], []
-    for p in wav_paths:
+    # decode on a few threads (file reads and numpy conversions release the GIL), slabs of files so that a large folder
+    # never sits in host memory at once; order and the count-and-continue semantics are those of the per-file loop
+    def _load(p):
         try:
-            rows.append(_fix_length(load_wav(p, sr), sr, duration))
+            return _fix_length(load_wav(p, sr), sr, duration)
         except Exception:
-            failed.append(p)
-    if not rows:
-        Z = np.zeros((0, eng.latent_dim), dtype=np.float32)
-    else:
-        x = torch.from_numpy(np.stack(rows)).to(eng.device)
-        feat = eng.logmel(x)                       # files on disk are already normalised (00) -> no RMS stage here
-        Z = eng.encoder_forward(feat).cpu().numpy()
+            return None
+
+    wav_paths = list(wav_paths)
+    eng = _engine_with_encoder(encoder, chunk_len, device if device is not None else 0,
+                               max_batch=64 if len(wav_paths) <= 256 else 512, **mel_kw)
+    failed, parts = [], []
+    for i in range(0, len(wav_paths), 2048):
+        piece = wav_paths[i:i + 2048]
+        rows = list(_IO_POOL.map(_load, piece)) if len(piece) > 8 else [_load(p) for p in piece]
+        failed += [p for p, r in zip(piece, rows) if r is None]
+        rows = [r for r in rows if r is not None]
+        if rows:
+            x = torch.from_numpy(np.stack(rows)).to(eng.device)
+            feat = eng.logmel(x)                   # files on disk are already normalised (00) -> no RMS stage here
+            parts.append(eng.encoder_forward(feat).cpu().numpy())
+    Z = np.concatenate(parts) if parts else np.zeros((0, eng.latent_dim), dtype=np.float32)
     return (Z, failed) if return_failed else Z
 
 

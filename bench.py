@@ -72,11 +72,10 @@ def traffic_of(mode: str, chunks_per_launch: int):
         d = json.loads(p.read_text())
     except Exception:
         return None
-    kernel = {"fold3": "dftf3_kernel", "fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)
+    kernel = {"fold3": "dftf3_kernel", "fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)   # bytes, per launch
     if d.get("kernel") != kernel or d.get("mode", "fold2") != mode or int(d.get("chunks_per_launch", 0)) != int(chunks_per_launch):
         return None
-    return {"bytes_per_launch": d["traffic_bytes"], "dram_read": d["dram_bytes_read"], "dram_write": d["dram_bytes_write"],
-            "source": d.get("source")}
+    return d["traffic_bytes"]
 
 
 class ClockSampler:
