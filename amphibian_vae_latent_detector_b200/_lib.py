@@ -58,6 +58,7 @@ _SIGNATURES = {
     "avld_encoder_load": (C.c_int, [_P, C.POINTER(Layer), C.c_int32]),
     "avld_encoder_forward": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "avld_encode": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
+    "avld_encode_pcm16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "avld_centroid_accumulate": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "avld_radii": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "avld_order_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(RankQuery), C.c_int32,

@@ -37,6 +37,22 @@ extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, 
   return AVLD_OK;
 }
 
+extern "C" int avld_encode_pcm16(avld_ctx* c, const int16_t* pcm, float* mu, uint8_t* ok, int64_t n, float target_rms,
+                                 float rms_min, float eps, int quantize_pcm16, void* stream) {
+  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
+  AVLD_CHECK(pcm && mu, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
+  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t i = 0; i < n; i += c->max_batch) {
+    const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
+    AVLD_TRY(encode_pass(c, nullptr, pcm + i * c->L, mu + i * c->latent_dim, ok ? ok + i : nullptr, m, target_rms, rms_min,
+                         eps, quantize_pcm16, st));
+  }
+  return AVLD_OK;
+}
+
 static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_bytes, int64_t n, int quantize_pcm16,
                                    const float* centroid, const double* thr, const int32_t* priority_rank, int32_t K,
                                    int32_t* pred_host, float* best_host, float* mu_host, uint8_t* ok_host) {

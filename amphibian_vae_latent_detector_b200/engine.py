@@ -182,14 +182,15 @@ class Engine:
 
     def encode(self, x: torch.Tensor, *, pcm16: bool = True, target_rms: float = 0.05, rms_min: float = 1e-4,
                eps: float = 1e-8) -> Tuple[torch.Tensor, torch.Tensor]:
-        """raw chunks ``[n, L]`` -> ``(mu [n, D], ok [n])``: normalise (+ PCM_16 round trip of the
-        ``*_norm`` dataset on disk) -> log-mel -> encoder."""
-        x = self._dev(x, torch.float32, "x")
+        """raw chunks ``[n, L]`` (float32, or int16 PCM_16 samples as the WAV files hold them) -> ``(mu [n, D], ok [n])``:
+        normalise (+ PCM_16 round trip of the ``*_norm`` dataset on disk) -> log-mel -> encoder."""
+        as_pcm = isinstance(x, torch.Tensor) and x.dtype == torch.int16
+        x = self._dev(x, torch.int16 if as_pcm else torch.float32, "x")
         n = x.shape[0]
         mu = torch.empty(n, self.latent_dim, dtype=torch.float32, device=self.device)
         ok = torch.empty(n, dtype=torch.uint8, device=self.device)
-        _lib.check(self.lib.avld_encode(self._h, _ptr(x), _ptr(mu), _ptr(ok), n, target_rms, rms_min, eps, int(pcm16),
-                                        _stream()))
+        fn = self.lib.avld_encode_pcm16 if as_pcm else self.lib.avld_encode
+        _lib.check(fn(self._h, _ptr(x), _ptr(mu), _ptr(ok), n, target_rms, rms_min, eps, int(pcm16), _stream()))
         return mu, ok
 
     # ------------------------------------------------------------------ F1-F3

@@ -135,6 +135,11 @@ int avld_encoder_forward(avld_ctx* ctx, const float* feat, float* mu, int64_t n,
 int avld_encode(avld_ctx* ctx, const float* x, float* mu, uint8_t* ok, int64_t n, float target_rms,
                 float rms_min, float eps, int quantize_pcm16, void* stream);
 
+/* same, with the chunks as device-resident PCM_16 samples (what the reference's WAV datasets hold; decoded as s / 32768
+ * like librosa.load, 00:51 / core:210): half the HBM bytes of the float32 form, bit-identical results. */
+int avld_encode_pcm16(avld_ctx* ctx, const int16_t* pcm, float* mu, uint8_t* ok, int64_t n, float target_rms,
+                      float rms_min, float eps, int quantize_pcm16, void* stream);
+
 /* ---- F1-F3: radial fit pieces (08_fit_radial_detector.py:105-106, :310-333, :530-558) ----------
  * per-species latent sums for the centroid (np.mean(Z_in, axis=0), 08:316): ACCUMULATES into
  * sum (dev float64 [K, D]) and cnt (dev int64 [K]); rows with label < 0 or >= K are skipped. */

@@ -57,3 +57,13 @@ def test_pcm16_host_input_equals_float_input(engine3s):
     b = engine3s.encode_detect_host(xf.pin_memory(), cent, thr, prio, pcm16=True, want_mu=True)
     for u, v in zip(a, b):
         assert np.array_equal(u, v)
+
+
+def test_device_pcm16_encode_equals_float_encode(engine3s):
+    """avld_encode_pcm16 (device-resident PCM_16) == avld_encode on the decoded float32 samples, bit for bit."""
+    x, _ = synth.make_chunks(70, 144000, seed=6, special_every=9)
+    pcm = torch.clamp(torch.round(x * 20000.0), -32768, 32767).to(torch.int16)
+    xf = pcm.to(torch.float32) * (1.0 / 32768.0)
+    mu_a, ok_a = engine3s.encode(pcm.cuda(), pcm16=True)
+    mu_b, ok_b = engine3s.encode(xf.cuda(), pcm16=True)
+    assert torch.equal(mu_a, mu_b) and torch.equal(ok_a, ok_b)
