@@ -219,6 +219,8 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold2(avld_ctx* c, int n, cudaStream_t st);
 int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st);
+bool dftg_supported(const avld_ctx* c);
+int launch_stft_mel_gen(avld_ctx* c, const float* x, const int16_t* x16, int n, cudaStream_t st);
 int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st);
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);

@@ -42,6 +42,9 @@ static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
 
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
   if (c->dft_fold2) {
+    // default: the operand is materialised by fold3_kernel and read back by dftf3_kernel; AVLD_DFT_GEN=1 (experimental,
+    // PCM_16-quantised input only) lets the GEMM build it from a shared-memory span of samples instead (dftg.cu)
+    if (c->cur_quantize && dftg_supported(c)) return launch_stft_mel_gen(c, c->cur_x, c->cur_x16, n, st);
     AVLD_TRY(launch_fold2(c, n, st));
     return launch_stft_mel_fold2(c, n, st);
   }

@@ -112,3 +112,23 @@ def test_feature_properties_full_batch(engine3s):
     fb = lpp.mel_filterbank(sr=48000, n_fft=2048, n_mels=64, fmin=150.0, fmax=15000.0)
     assert abs(int(band) - int(fb[:, round(2600.0 / 48000 * 2048)].argmax())) <= 1
     assert rel(feat[2], feat[1]) < 1e-4
+
+
+def test_in_kernel_operand_generation_matches_default(monkeypatch):
+    """AVLD_DFT_GEN=1 (dftg.cu: the GEMM builds its folded operand from a shared-memory span of samples instead of reading
+    what fold3_kernel materialised): same features as the default path to fp32 rounding, for float32 and PCM_16 input,
+    ragged batch, chunks that hit the gate / clip, and the reference fixtures."""
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    x, _ = synth.make_chunks(37, 144000, seed=31, special_every=9)
+    eng = Engine(0, chunk_len=144000, max_batch=16)
+    base, ok0, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+    monkeypatch.setenv("AVLD_DFT_GEN", "1")
+    gen, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+    assert torch.equal(ok0, ok1)
+    assert rel(gen.cpu().numpy(), base.cpu().numpy()) < 2e-5
+    for key in ("noise_3s", "tonal_3s", "hot_3s", "silent_3s"):
+        xg, d = _prep(key)
+        feat, _, _ = eng.normalize_logmel(torch.from_numpy(xg[None]).cuda(), pcm16=True)
+        assert rel(feat.cpu().numpy()[0], d["feat"].T) < FEAT_TOL, key
+    eng.close()
