@@ -415,10 +415,27 @@ dftg_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ 
         const int kbp = P.item[it].kbp, nkb = 2 * kbp, cls = P.item[it].cls;
         for (int kb = 0; kb < nkb; ++kb) {
           // accumulator hand-over, placed where the awaited MMAs have certainly retired (see header)
-          if (kb == 2 && epi.pending) {
-            if (epi_warp) finish_item();
-            else { acc_phase ^= 1u; epi.pending = false; }
+          // Stage 1 of an item reuses the buffer of the previous item's last stage: once it is free, that item's
+          // accumulators are complete.  The epilogue warps then read them out and sit this stage out (they arrive on its
+          // barrier first: they write nothing into it), the other eight warps build the whole stage meanwhile.  (Not at
+          // stage 0 or 2: the MMAs of stage 0 wait for this very read-out, so nothing that waits for them may precede it.)
+          const bool hand_over = kb == 1 && epi.pending;
+          if (hand_over) {
+            if (epi_warp) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u, 510 + stage);     // the barrier's previous phase is certainly over
+              if (lane == 0) {
+                if (leader) mbar_arrive(&full_bar[stage]);
+                else mbar_arrive_cluster(&full_bar[stage], 0);
+              }
+              finish_item();
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              continue;
+            }
+            acc_phase ^= 1u;
+            epi.pending = false;
           }
+          const int t_first = hand_over ? wtid - 32 * kEpiWarps : wtid;          // warps 10..17 only during a hand-over
+          const int t_step = hand_over ? 32 * (kWorkers - kEpiWarps) : 32 * kWorkers;
           // ---- build A stage: (class, part, 64 taps) for 128 rows
           mbar_wait(&empty_bar[stage], phase ^ 1u, 500 + stage);
           uint8_t* a_hi = smem + stage * kStageBytes;
@@ -426,7 +443,7 @@ dftg_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ 
           const int part = kb < kbp ? 0 : 1;
           const int kblk = (kb - part * kbp) * kBK;
 #pragma unroll 1
-          for (int t = (P.dbg & 8) ? kBM * 8 : wtid; t < kBM * 8; t += 32 * kWorkers) {      // dbg 8: barrier protocol only
+          for (int t = (P.dbg & 8) ? kBM * 8 : t_first; t < kBM * 8; t += t_step) {      // dbg 8: barrier protocol only
             const int row = t >> 3, ch = t & 7;
             const int k0 = kblk + ch * 8;
             const uint16_t* sr = s_span + row * P.hop;
@@ -486,7 +503,7 @@ dftg_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ 
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        // the item just queued is finished two stages into the next one (its last MMAs have retired by then)
+        // the item just queued is finished one stage into the next one
         epi.pending = true;
         epi.valid = valid;
         epi.s2 = s2;
@@ -513,7 +530,7 @@ bool dftg_supported(const avld_ctx* c) {
   if (c->p.n_fft != 2048 || c->p.hop != 384) return false;     // the span buffer is sized for this geometry
   if (c->f2_items > 8) return false;
   for (int it = 0; it < c->f2_items; ++it)
-    if (c->f2_item[it].kbp < 2) return false;                    // an item is finished at stage 2 of the next one
+    if (c->f2_item[it].kbp < 1) return false;
   const char* e = getenv("AVLD_DFT_GEN");                       // opt-in: see the header of this file
   return e != nullptr && atoi(e) != 0;
 }
