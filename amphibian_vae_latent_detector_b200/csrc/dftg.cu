@@ -23,7 +23,8 @@
 //   no Re hold (workers set the pace, not the tensor pipe), no spills             5.3 ms
 //   16 worker warps (2 tasks per thread and stage), two-phase even-class compute  4.2 ms
 //   vectorised span fill (the scalar loop exposed every global load's latency)    3.4 ms
-//   AVLD_DBG=1 (no epilogue math) 2.95 | =8 (no tile building) 1.89 | =9 (neither) 1.28 ms
+//   shared-memory address space kept for the workers' loads / stores (LDS, not LD) 3.1 ms
+//   (at 3.4 ms:) AVLD_DBG=1 (no epilogue math) 2.95 | =8 (no tile building) 1.89 | =9 (neither) 1.28 ms
 // i.e. tile building (~1.5 ms), epilogue math (~0.5 ms, serial on the same warps) and the MMA / span / barrier floor
 // (~1.3 ms) add up instead of overlapping: the workers issue ~1.5 instructions per cycle and share the shared-memory pipe
 // with the tensor core's operand reads.  What would make it pay: dedicated epilogue warps (needs setmaxnreg to fit the
@@ -143,7 +144,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dftg_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const DftgParams P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1 KB alignment by pointer arithmetic on the __shared__ array (not through an integer cast): the worker warps access
+  // this memory with ordinary loads / stores, and only then does the compiler know they are LDS / STS rather than generic
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint16_t* s_span = reinterpret_cast<uint16_t*>(smem + kStages * kStageBytes);   // q + 32768
   float* s_win = reinterpret_cast<float*>(smem + kStages * kStageBytes + kSpanBytes);             // w[k]
   float* s_wrv = reinterpret_cast<float*>(smem + kStages * kStageBytes + kSpanBytes + kWinBytes); // w[N/2 - k]
