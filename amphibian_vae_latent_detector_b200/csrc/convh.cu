@@ -63,7 +63,7 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   using Cfg = ConvhCfg<BN, CBLK>;
   constexpr int ROWB = Cfg::ROWB;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
   const bool resident = P.resident != 0;
   const int hstages = resident ? Cfg::HSTAGES_RES : Cfg::HSTAGES_STR;
   const int wstages = resident ? 0 : Cfg::WSTAGES_STR;

@@ -65,7 +65,7 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Dftf3Params P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
   uint8_t* tail = smem + kStages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);     // [8]  (used in the leader)
   uint64_t* empty_bar = full_bar + 8;                         // [8]  (per CTA)
