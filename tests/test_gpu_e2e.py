@@ -67,3 +67,41 @@ def test_device_pcm16_encode_equals_float_encode(engine3s):
     mu_a, ok_a = engine3s.encode(pcm.cuda(), pcm16=True)
     mu_b, ok_b = engine3s.encode(xf.cuda(), pcm16=True)
     assert torch.equal(mu_a, mu_b) and torch.equal(ok_a, ok_b)
+
+
+def test_config_c1_1000_chunks_vs_oracle(standin_encoder):
+    """BASELINE.json configs[0] at full size: 1 000 synthetic chunks, normalise + encode + radial fit over the q_out grid
+    + decision; CPU oracle (one chunk at a time, as the reference runs) against the batched CUDA path."""
+    from concurrent.futures import ThreadPoolExecutor
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    n, grid = 1000, (0.10, 0.15, 0.20, 0.25)
+    x, label = synth.make_chunks(n, 144000, seed=123, special_every=100)
+    xn, ln = x.numpy(), label.numpy()
+    yo, oko, _ = hp.rms_normalize_batch(xn, pcm16=True)
+    torch.set_num_threads(1)                       # the oracle pieces run one chunk per thread (numpy releases the GIL)
+    with ThreadPoolExecutor(16) as ex:
+        parts = list(ex.map(lambda i: hp.encode_batch(standin_encoder, yo[i:i + 25], **MEL_KW), range(0, n, 25)))
+    Zo = np.concatenate(parts)
+    eng = Engine(0, chunk_len=144000, max_batch=256)
+    eng.load_encoder(standin_encoder)
+    Z, ok = eng.encode(x.cuda(), pcm16=True)
+    assert np.array_equal(ok.cpu().numpy(), oko)
+    assert np.max(np.abs(Z.cpu().numpy() - Zo)) / np.max(np.abs(Zo)) < 1e-3
+    fit = eng.fit_radial(Z, label.cuda(), 4, 0.95, grid)
+    prio = priority_ranks(SPECIES, hp.PRIORITY_ORDER)
+    flips = 0
+    for qi, q in enumerate(grid):
+        cent_o, rk_o, rk_in_o, rk_out_o = hp.fit_radial(Zo, ln, 4, 0.95, q)
+        assert np.max(np.abs(fit.centroids - cent_o)) / np.max(np.abs(cent_o)) < 1e-3
+        assert np.allclose(fit.rk_in, rk_in_o, rtol=1e-3) and np.allclose(fit.rk_out[qi], rk_out_o, rtol=1e-3)
+        assert np.allclose(fit.rk[qi], rk_o, rtol=1e-3)
+        pred_o, best_o, radii_o = hp.decide_batch(Zo, SPECIES, cent_o, rk_o)
+        pred, best = eng.decide(fit.radii_local, torch.from_numpy(fit.rk[qi]).cuda(), torch.from_numpy(prio).cuda())
+        pred, best = pred.cpu().numpy(), best.cpu().numpy()
+        near = np.any(np.abs(radii_o - rk_o[None]) / rk_o[None] <= 2e-3, axis=1)      # both sides carry <= 1e-3
+        assert np.array_equal(pred[~near], pred_o[~near])
+        assert np.allclose(best, best_o, rtol=1e-3)
+        flips += int((pred != pred_o).sum())
+        assert near.sum() < n // 10
+    assert flips <= n // 50
+    eng.close()
