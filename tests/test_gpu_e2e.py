@@ -78,9 +78,13 @@ def test_config_c1_1000_chunks_vs_oracle(standin_encoder):
     x, label = synth.make_chunks(n, 144000, seed=123, special_every=100)
     xn, ln = x.numpy(), label.numpy()
     yo, oko, _ = hp.rms_normalize_batch(xn, pcm16=True)
+    threads = torch.get_num_threads()
     torch.set_num_threads(1)                       # the oracle pieces run one chunk per thread (numpy releases the GIL)
-    with ThreadPoolExecutor(16) as ex:
-        parts = list(ex.map(lambda i: hp.encode_batch(standin_encoder, yo[i:i + 25], **MEL_KW), range(0, n, 25)))
+    try:
+        with ThreadPoolExecutor(16) as ex:
+            parts = list(ex.map(lambda i: hp.encode_batch(standin_encoder, yo[i:i + 25], **MEL_KW), range(0, n, 25)))
+    finally:
+        torch.set_num_threads(threads)
     Zo = np.concatenate(parts)
     eng = Engine(0, chunk_len=144000, max_batch=256)
     eng.load_encoder(standin_encoder)
