@@ -106,9 +106,26 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
 
   // slab i: H2D on the copy stream into buffer i&1 while the compute stream works on slab i-1;
   // results of slab i are read back on the compute stream right after its kernels.
-  int64_t slab = 0;
-  for (int64_t i = 0; i < n; i += c->max_batch, ++slab) {
-    const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
+  // Slab sizes: full passes in the middle, a quarter pass first and last -- the first copy and the last slab's kernels are
+  // the only parts of the call that nothing overlaps, so they are kept short (the link, not the GPU, paces this call).
+  std::vector<int> sizes;
+  {
+    const int64_t mb = c->max_batch, q = std::max<int64_t>(mb / 4, 1);
+    int64_t left = n;
+    if (n >= 2 * mb) {
+      sizes.push_back(static_cast<int>(q));
+      left -= 2 * q;
+    }
+    while (left > 0) {
+      const int64_t m = std::min(left, mb);
+      sizes.push_back(static_cast<int>(m));
+      left -= m;
+    }
+    if (n >= 2 * mb) sizes.push_back(static_cast<int>(q));
+  }
+  int64_t slab = 0, i = 0;
+  for (; slab < static_cast<int64_t>(sizes.size()); i += sizes[slab], ++slab) {
+    const int m = sizes[slab];
     const int b = static_cast<int>(slab & 1);
     if (slab >= 2) AVLD_CUDA(cudaStreamWaitEvent(sx, c->ev_done[b], 0));   // buffer b free again
     mark(sx);
