@@ -78,6 +78,40 @@ def traffic_of(mode: str, chunks_per_launch: int):
     return d["traffic_bytes"]
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's CPU affinity to the NUMA node its GPU hangs off (sysfs), so that the pinned host buffers of the
+    end-to-end leg are first-touched on that node: with 8 ranks pulling ~53 GB/s each, cross-socket traffic would halve
+    what the host memory delivers.  Best effort: returns the node or None and never fails."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id       # e.g. 0000:1B:00.0 (torch >= 2.3)
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int((Path("/sys/bus/pci/devices") / bus / "numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in (Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -239,6 +273,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
@@ -386,7 +421,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16x2 split operands, fp32 accumulate (TMEM)", "data": "synthetic",
-            "config": workload_config(n, world, max_batch=args.max_batch,
+            "config": workload_config(n, world, max_batch=args.max_batch, rank0_numa_node=numa_node,
                                       l2="inputs (57.6 GB/GPU at 100k chunks) exceed the 126 MB L2; no flush needed"),
             "clocks": clocks,
             "gpu_launches": int(launches),
