@@ -1,6 +1,5 @@
 """CPU: the output-unpacking / guarded-forward / shape-probe helpers of 07_encode_wav_to_latent.py (07:195-199, :264-352)
 against explicit cases and, when the reference tree is present (build container), against the reference's own functions."""
-import numpy as np
 import pytest
 import torch
 
