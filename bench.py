@@ -414,6 +414,9 @@ def main():
             "issued_over_algorithmic": info["issued_flops_per_chunk"] / DFT_FLOP_PER_CHUNK,
             "issued_tflops": issued_tflops,
             "tensor_pipe_frac": (issued_tflops / peaks["tflops_sustained"]) if issued_tflops else None,
+            "note": "achieved/frac count the flops of the plain DFT GEMM over the 634 mel-weighted bins (SURVEY 8d); the folded "
+                    "kernel reaches the same bins with issued_over_algorithmic x those flops, so frac can exceed 1 -- "
+                    "tensor_pipe_frac (issued flops / peak) is the utilisation of the pipe; the kernel is L2->SM-feed bound",
             "dft_mode": info["mode"], "chunks_per_launch": args.max_batch,
             "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": traffic_of(info["mode"], args.max_batch),
             "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None}
