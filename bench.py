@@ -178,9 +178,16 @@ def cpu_reference_loop(x: np.ndarray, labels: np.ndarray):
     enc = build_standin_encoder(seed=123)
     t0 = time.perf_counter()
     y, ok, _ = hp.rms_normalize_batch(x, pcm16=True)
-    Z = hp.encode_batch(enc, y, **MEL_KW)
+    t1 = time.perf_counter()
+    feats = [hp.logmel_features(row, **MEL_KW) for row in y]                  # M1-M5, one chunk at a time
+    t2 = time.perf_counter()
+    Z = np.stack([hp.encode_features(enc, f) for f in feats])                 # E0-E2, batch 1
+    t3 = time.perf_counter()
     _cpu_fit_detect(Z, labels, hp)
-    return time.perf_counter() - t0
+    t4 = time.perf_counter()
+    n = x.shape[0]
+    stages = {"normalise": n / (t1 - t0), "features": n / (t2 - t1), "encoder": n / (t3 - t2), "fit+detect": n / (t4 - t3)}
+    return t4 - t0, {k: round(v, 1) for k, v in stages.items()}
 
 
 _W = {}
@@ -439,9 +446,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             nc = args.cpu_chunks
             xc, lc = synth.make_chunks(nc, CHUNK_LEN, seed=123, first_index=0)
-            dt = cpu_reference_loop(xc.numpy(), lc.numpy())
+            dt, cpu_stages = cpu_reference_loop(xc.numpy(), lc.numpy())
             line["cpu_baseline"] = {"value": nc / dt, "unit": "chunks/s", "cores": int(torch.get_num_threads()),
-                                    "kind": "port",
+                                    "kind": "port", "stages_chunks_per_s": cpu_stages,
                                     "sample": f"{nc} chunks of the same workload, one chunk at a time (batch 1) as the "
                                               f"reference runs it: numpy float64 FFT + torch CPU encoder, "
                                               f"{dt:.1f} s wall, host has {os.cpu_count()} logical cores"}
