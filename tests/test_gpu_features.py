@@ -132,3 +132,9 @@ def test_in_kernel_operand_generation_matches_default(monkeypatch):
         feat, _, _ = eng.normalize_logmel(torch.from_numpy(xg[None]).cuda(), pcm16=True)
         assert rel(feat.cpu().numpy()[0], d["feat"].T) < FEAT_TOL, key
     eng.close()
+    eng5 = Engine(0, chunk_len=240000, max_batch=4)                  # 5 s: 626 frames = 5 tiles per chunk, the last one short
+    for key in ("pulsed_5s", "tonal_5s"):
+        xg, d = _prep(key)
+        feat, _, _ = eng5.normalize_logmel(torch.from_numpy(np.stack([xg, xg, xg])).cuda(), pcm16=True)
+        assert rel(feat.cpu().numpy()[2], d["feat"].T) < FEAT_TOL, key
+    eng5.close()
