@@ -122,3 +122,57 @@ def test_fit_radial_detector_cache_roundtrip(tree):
     ref = json.loads((GOLD / "qout_0.10" / "config_used.json").read_text())["radial_detector"]["thresholds"]
     for sp, v in ref.items():
         assert abs(c1["radial_detector"]["thresholds"][sp] - v) <= TOL * v
+
+
+def test_cli_scripts_08_10_09_on_the_tree(tree, capsys, monkeypatch):
+    """The reference's command lines (run_qout_grid.sh:28-38: ``08 --root train_chunks --q-in --q-out --max-per-class --seed``,
+    then ``10 --root val_chunks``; 09 ``--wav`` with its 0 / 2 exit codes) through ``cli.main_*`` with the encoder loaded
+    from ``downloaded_models/.../model.pt`` (a state_dict) + the YAML ``_target_``, as core:150-179 does."""
+    import torch
+    from amphibian_vae_latent_detector_b200 import cli
+    from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
+    root, lse, meta = tree
+    enc_dir = root / "downloaded_models" / "bird_net_vae_audio_splitted_encoder_v0"
+    enc_dir.mkdir(parents=True, exist_ok=True)
+    torch.save(build_standin_encoder(seed=123).state_dict(), enc_dir / "model.pt")
+    (enc_dir / "bird_net_vae_audio_splitted.yaml").write_text(
+        "encoder:\n  _target_: amphibian_vae_latent_detector_b200.encoder.build_standin_encoder\n  seed: 7\n")   # weights come from model.pt
+    cfgp = root / "config_cli.json"
+    cfgp.write_text(json.dumps({"species": meta["species"], "chunk_seconds": 3.0}, indent=2))
+    monkeypatch.chdir(root)
+    here = lse
+    cli.main_08(["--config", "config_cli.json", "--root", "train_chunks", "--q-in", str(meta["q_in"]), "--q-out", "0.10",
+                 "--max-per-class", str(meta["max_per_class"]), "--seed", "123", "--device", "cuda"], here=here)
+    out = capsys.readouterr().out
+    assert "📌 Project root:" in out and "📦 WAVs por especie en root:" in out
+    got = json.loads(cfgp.read_text())["radial_detector"]
+    ref = json.loads((GOLD / "qout_0.10" / "config_used.json").read_text())["radial_detector"]
+    for sp, v in ref["thresholds"].items():
+        assert abs(got["thresholds"][sp] - v) <= TOL * v
+    # 10: folder benchmark -> <project>/outputs/detection_benchmark/{results.csv,summary.txt}
+    cli.main_10(["--root", str(lse / "val_chunks"), "--config", str(cfgp)], here=here)        # default --device cpu: notice, runs on the GPU
+    out = capsys.readouterr().out
+    assert "solo corre en GPU" in out and "✅ CSV guardado:" in out
+    rows = _read_csv(root / "outputs" / "detection_benchmark" / "results.csv")
+    rr = _read_csv(GOLD / "qout_0.10" / "results.csv")
+    assert [Path(r["file"]).name for r in rows] == [Path(r["file"]).name for r in rr]
+    thr_ref = np.array(list(ref["thresholds"].values()))
+    for a, b in zip(rows, rr):
+        db = float(b["best_distance"])
+        assert abs(float(a["best_distance"]) - db) <= TOL * db
+        if not np.any(np.abs(db - thr_ref) / thr_ref <= 2 * TOL):
+            assert (a["pred_species"], a["detected"]) == (b["pred_species"], b["detected"])
+    assert (root / "outputs" / "detection_benchmark" / "summary.txt").exists()
+    # 09: one detected and one undetected file, exit codes 0 / 2 and the reference's final line
+    by = {}
+    for r in rows:
+        by.setdefault(r["detected"], r)
+    for flag, r in by.items():
+        wav = next((lse / "val_chunks").rglob(Path(r["file"]).name))
+        with pytest.raises(SystemExit) as e:
+            cli.main_09(["--wav", str(wav), "--config", str(cfgp), "--device", "cuda:0"], here=here)
+        out = capsys.readouterr().out
+        if str(flag) in ("1", "True", "true"):
+            assert e.value.code == 0 and f"✅ DETECTADO: {r['pred_species']}" in out
+        else:
+            assert e.value.code == 2 and "❌ NO DETECTADO" in out
