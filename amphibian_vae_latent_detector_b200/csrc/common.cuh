@@ -111,6 +111,7 @@ struct avld_ctx {
   const float* cur_x = nullptr;    // operand source of the current pass (set by launch_prep, read by launch_fold)
   const int16_t* cur_x16 = nullptr;
   int cur_quantize = 0;
+  const uint16_t* cur_q16 = nullptr;   // normalised PCM_16 samples (+32768) of the current pass, or NULL (launch_prep)
   __half* d_A2hi = nullptr;        // [max_batch * F + 128][n_fft] folded frames, E in columns [0, N/2), O in [N/2, N)
   __half* d_A2lo = nullptr;
   __half* d_B2hi = nullptr;        // [n_tiles2 * 512][N/2]: per tile 256 cos rows then 256 (-sin) rows
@@ -139,6 +140,7 @@ struct avld_ctx {
   CUtensorMap tm_B3_hi, tm_B3_lo;  // 64-tap x 80-row boxes (one CTA's half of an item)
   avld::MelTap* d_taps3 = nullptr; // [f2_items * 160], .pad = bits of the edge coefficient
   float4* d_edge = nullptr;        // [max_batch * F + 256] per frame: the self-paired tap of each bin class
+  uint16_t* d_q16 = nullptr;       // [max_batch * L + 64] normalised, PCM_16-rounded samples biased by 32768 (three-level fold, quantize passes)
   float* d_win = nullptr;          // [N/2 + 1] periodic Hann
   bool planes_dirty = false;       // a GEMM pass accumulated into the planes and logmel_post has not consumed them yet
   long long melpow_plane = 0;      // elements per mel-power plane (fold2: one plane per bin class)

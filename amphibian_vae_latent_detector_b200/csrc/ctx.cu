@@ -480,10 +480,31 @@ static int build_ctx(avld_ctx* c) {
       AVLD_TRY(encode_tmap_2d(&c->tm_B3_lo, c->d_B3lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
       AVLD_TRY(dev_alloc(&c->d_taps3, taps3.size()));
       AVLD_CUDA(cudaMemcpy(c->d_taps3, taps3.data(), taps3.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
-      std::vector<float> win(half + 1);
+      // periodic Hann [half + 1], then (three-level fold) the same values regrouped per 8-tap block kb of fold3_kernel as
+      // nine float4 planes [9][E / 8]: w[k] (2), w[H-k] (2), w[Q-k] (2), w[Q+k] (2) for k = 8 kb + 0..7, and (w[Q-k], w[Q+k]) at
+      // k = 8 kb + 8 -- one coalesced 16-byte load per plane instead of 34 strided scalar loads per thread
+      const int wt_off = (half + 1 + 3) & ~3, wt_blocks = nf / 64;
+      std::vector<float> win(c->f2_levels == 3 ? wt_off + 9 * wt_blocks * 4 : half + 1, 0.f);
       for (int k = 0; k <= half; ++k) win[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf));
+      if (c->f2_levels == 3) {
+        const int Q4 = nf / 4;
+        for (int kb = 0; kb < wt_blocks; ++kb) {
+          auto cell = [&](int plane, int j) -> float& { return win[wt_off + (plane * wt_blocks + kb) * 4 + j]; };
+          for (int q = 0; q < 8; ++q) {
+            const int k = kb * 8 + q;
+            cell(0 + q / 4, q % 4) = win[k];
+            cell(2 + q / 4, q % 4) = win[half - k];
+            cell(4 + q / 4, q % 4) = win[Q4 - k];
+            cell(6 + q / 4, q % 4) = win[Q4 + k];
+          }
+          cell(8, 0) = win[Q4 - (kb * 8 + 8)];
+          cell(8, 1) = win[Q4 + (kb * 8 + 8)];
+        }
+      }
       AVLD_TRY(dev_alloc(&c->d_win, win.size()));
       AVLD_CUDA(cudaMemcpy(c->d_win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
+      if (c->f2_levels == 3 && std::getenv("AVLD_NO_Q16") == nullptr)
+        AVLD_TRY(dev_alloc(&c->d_q16, static_cast<size_t>(p.max_batch) * c->L + 64));
       AVLD_TRY(dev_alloc(&c->d_edge, frames));
       AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float4)));
       if (fbk != 64) {   // the fold2 kernel loads 64-tap boxes of A
@@ -586,7 +607,7 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
-                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_B3hi, c->d_B3lo, c->d_taps3, c->d_edge, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
+                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_B3hi, c->d_B3lo, c->d_taps3, c->d_edge, c->d_q16, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
                   c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
                   c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)

@@ -25,6 +25,7 @@ struct PrepParams {
   float4* chunk_par;      // nullable (folded STFT): per chunk (scale, pow2, scaled flag, -) for fold_kernel, which
                           // re-applies the normalisation on the fly instead of reading a materialised copy
   float* inv2;
+  uint16_t* q16;          // nullable: normalised, PCM_16-rounded samples + 32768 for fold3_kernel (quantize passes)
   uint8_t* ok;            // nullable
   float* rms;             // nullable
   const int32_t* leaf_off;
@@ -176,6 +177,46 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     } else {
       for (int i = tid; i < P.L; i += blockDim.x) yc[i] = finish_sample(xc(i), scale, scaled, P.quantize);
     }
+  }
+
+  // ---------------------------------------------------------------- phase 2c: normalised PCM_16 samples for fold3_kernel
+  // (each sample is used by ~6 operand threads; rounding it once here instead of there halves that kernel's instructions)
+  if (P.q16 != nullptr) {
+    uint16_t* __restrict__ qc = P.q16 + static_cast<size_t>(c) * P.L;
+    auto biased = [&](float v) -> uint32_t { return static_cast<uint32_t>(pcm16_of(v, scale, scaled) + 32768); };
+    const int n8 = P.L >> 3;
+    if (P.x16 == nullptr && (reinterpret_cast<uintptr_t>(P.x) & 15) == 0 && (P.L & 3) == 0) {
+      const float4* x4 = reinterpret_cast<const float4*>(P.x + static_cast<size_t>(c) * P.L);
+#pragma unroll 4
+      for (int i = tid; i < n8; i += blockDim.x) {
+        const float4 a = x4[2 * i], b = x4[2 * i + 1];
+        uint4 o;
+        o.x = biased(a.x) | (biased(a.y) << 16);
+        o.y = biased(a.z) | (biased(a.w) << 16);
+        o.z = biased(b.x) | (biased(b.y) << 16);
+        o.w = biased(b.z) | (biased(b.w) << 16);
+        reinterpret_cast<uint4*>(qc)[i] = o;
+      }
+    } else if (P.x16 != nullptr && (reinterpret_cast<uintptr_t>(P.x16) & 15) == 0) {
+      const uint4* x8 = reinterpret_cast<const uint4*>(P.x16 + static_cast<size_t>(c) * P.L);
+      auto pair = [&](uint32_t w) -> uint32_t {
+        const float lo = static_cast<float>(static_cast<int16_t>(w & 0xffffu)) * (1.0f / 32768.0f);
+        const float hi = static_cast<float>(static_cast<int16_t>(w >> 16)) * (1.0f / 32768.0f);
+        return biased(lo) | (biased(hi) << 16);
+      };
+      for (int i = tid; i < n8; i += blockDim.x) {
+        const uint4 u = x8[i];
+        reinterpret_cast<uint4*>(qc)[i] = make_uint4(pair(u.x), pair(u.y), pair(u.z), pair(u.w));
+      }
+    } else {
+      for (int i = tid; i < n8; i += blockDim.x) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = biased(xc(8 * i + 2 * j)) | (biased(xc(8 * i + 2 * j + 1)) << 16);
+        reinterpret_cast<uint4*>(qc)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    for (int i = (n8 << 3) + tid; i < P.L; i += blockDim.x) qc[i] = static_cast<uint16_t>(biased(xc(i)));
   }
 
   // ---------------------------------------------------------------- phase 2b: GEMM operand rows
@@ -353,6 +394,9 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
     c->cur_x = x;
     c->cur_x16 = x16;
     c->cur_quantize = quantize ? 1 : 0;
+    // the uint4 stores of phase 2c need 16-byte aligned chunk rows
+    c->cur_q16 = (quantize && c->dft_fold2 && c->f2_levels == 3 && c->d_q16 && (c->L & 7) == 0) ? c->d_q16 : nullptr;
+    P.q16 = c->d_q16 && c->cur_q16 ? c->d_q16 : nullptr;
   }
   P.inv2 = write_operand ? c->d_inv2 : nullptr;
   P.ok = ok;

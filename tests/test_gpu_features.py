@@ -138,3 +138,41 @@ def test_in_kernel_operand_generation_matches_default(monkeypatch):
         feat, _, _ = eng5.normalize_logmel(torch.from_numpy(np.stack([xg, xg, xg])).cuda(), pcm16=True)
         assert rel(feat.cpu().numpy()[2], d["feat"].T) < FEAT_TOL, key
     eng5.close()
+
+
+def test_prequantised_operand_source_is_bit_identical(monkeypatch, standin_encoder):
+    """Default path: prep_kernel leaves the normalised PCM_16 integers (pcm16_of, four instructions) and fold3_kernel<2> reads
+    them; AVLD_NO_Q16=1: fold3_kernel<0/1> re-normalises every sample on the fly (finish_sample).  Same bits out, for float32
+    and PCM_16 input, including samples at and beyond the clip points, +-inf / NaN chunks, the silence gate, -0.0."""
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    x, _ = synth.make_chunks(21, 144000, seed=77, special_every=4)
+    x[1, 100:200] = 50.0                      # far beyond the clip point once scaled
+    x[1, 300:400] = -50.0
+    x[2] *= 1e-7                              # gate: passed through unscaled
+    x[3, ::7] = -0.0
+    x[5, 1000] = float("nan")
+    x[6, 2000] = float("inf")
+    x[7, 3000] = float("-inf")
+    x[8] = torch.where(torch.arange(144000) % 2 == 0, 1.0, -1.0) * 0.05       # rms 0.05 exactly: scale ~ 1, samples at +-0.05
+    x[9] = torch.clamp(x[9] * 400.0, -3.0, 3.0)                               # many samples clip on both sides
+    pcm = torch.clamp(torch.round(x.nan_to_num(0.0, 1.0, -1.0) * 20000.0), -32768, 32767).to(torch.int16)
+    pcm[4, :50] = -32768
+    pcm[4, 50:100] = 32767
+    eng = Engine(0, chunk_len=144000, max_batch=8)
+    f_q, ok_q, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+    eng.load_encoder(standin_encoder)
+    mu_q, okp_q = eng.encode(pcm.cuda(), pcm16=True)
+    eng.close()
+    monkeypatch.setenv("AVLD_NO_Q16", "1")
+    eng2 = Engine(0, chunk_len=144000, max_batch=8)
+    f_d, ok_d, _ = eng2.normalize_logmel(x.cuda(), pcm16=True)
+    eng2.load_encoder(standin_encoder)
+    mu_d, okp_d = eng2.encode(pcm.cuda(), pcm16=True)
+    eng2.close()
+    assert torch.equal(okp_q, okp_d) and torch.equal(mu_q, mu_d)
+    assert torch.equal(ok_q, ok_d)
+    a, b = f_q.cpu().numpy(), f_d.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
+    assert np.isnan(a[5]).all() and np.isnan(a[6]).all() and np.isnan(a[7]).all() and not np.isnan(a[[0, 1, 2, 3, 4, 8, 9]]).any()
