@@ -173,13 +173,17 @@ __global__ void __launch_bounds__(256) conv1_kernel(const DirectConvParams P) {
 #pragma unroll
       for (int pw = 0; pw < POOL; ++pw)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float a = breg[q];
+        for (int q = 0; q < 8; q += 2) {                  // two output channels per FFMA2
+          float2 a = make_float2(breg[q], breg[q + 1]);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) a = fmaf(patch[ph + kh][pw + kw], wreg[q][kh * 3 + kw], a);
-          best[q] = max_nan(best[q], a);
+            for (int kw = 0; kw < 3; ++kw) {
+              const float pv = patch[ph + kh][pw + kw];
+              a = fma2(make_float2(pv, pv), make_float2(wreg[q][kh * 3 + kw], wreg[q + 1][kh * 3 + kw]), a);
+            }
+          best[q] = max_nan(best[q], a.x);
+          best[q + 1] = max_nan(best[q + 1], a.y);
         }
     __align__(16) __nv_bfloat16 hi[8];
     __align__(16) __nv_bfloat16 lo[8];

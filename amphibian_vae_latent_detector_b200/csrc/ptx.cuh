@@ -10,6 +10,16 @@
 namespace avld {
 
 // ReLU / max as torch computes them: NaN propagates (fmaxf would drop it and turn a poisoned chunk into a plausible one)
+// two independent fp32 FMAs in one instruction (FFMA2, sm_100): d = a * b + c per component, each rounded as fmaf
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 __device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
 __device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }
 

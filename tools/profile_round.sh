@@ -14,6 +14,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 one="--chunks 2048 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dftf3 -c 1 -f -o gpurun_out/prof_dftf3_$tag \
   python bench.py $one > gpurun_out/ncu_dftf3_$tag.log 2>&1; echo "ncu dftf3 rc $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fold2|prep_kernel|logmel_post|conv1|convh|gemm3' -c 9 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fold3|fold2|prep_kernel|logmel_post|conv1|convh|gemm3' -c 10 -f \
   -o gpurun_out/prof_stream_$tag python bench.py $one > gpurun_out/ncu_stream_$tag.log 2>&1; echo "ncu stream rc $?"
 tail -c 400 gpurun_out/bench_$tag.log
