@@ -223,7 +223,14 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       const bool fast = P.Cin == 1 && P.k == 3 && P.pad == 1 && P.Cout % 8 == 0 && groups >= 1 && 256 % groups == 0 &&
                         static_cast<size_t>(16 * P.pool + 2) * (P.W + 2) * sizeof(float) <= 48 * 1024;
       if (fast) {
+        // taller strips amortise the per-block prologue (72 filter taps per thread, the input strip) once the grid is large anyway
         P.rows_per_block = 16;
+        for (int rpb : {48, 32})
+          if (L.out_h % rpb == 0 && static_cast<size_t>(rpb * P.pool + 2) * (P.W + 2) * sizeof(float) <= 48 * 1024 &&
+              static_cast<long long>(L.out_h / rpb) * n >= 8ll * c->sm_count) {
+            P.rows_per_block = rpb;
+            break;
+          }
         const size_t smem = static_cast<size_t>(P.rows_per_block * P.pool + 2) * (P.W + 2) * sizeof(float);
         dim3 grid((L.out_h + P.rows_per_block - 1) / P.rows_per_block, n);
         LaunchScope ls(c, ST_CONV_DIRECT, st);

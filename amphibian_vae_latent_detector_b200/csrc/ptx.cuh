@@ -20,8 +20,13 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
-__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
-__device__ __forceinline__ float max_nan(float a, float b) { return (a > b || a != a) ? a : b; }
+// NaN-propagating max / ReLU (torch semantics) in one FMNMX.NAN each
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float relu_nan(float v) { return max_nan(v, 0.f); }
 
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t threads) {
