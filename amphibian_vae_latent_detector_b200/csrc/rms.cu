@@ -89,11 +89,22 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
       }
     } else {
       const int n8 = len & ~7;
-      float v = xc(off + j);
+      // numpy's leaves hold at most 128 elements (64..72 for a 3 s chunk): the first nine 8-element rows are loaded at once
+      // (nine independent loads in flight per thread instead of the four an unrolled loop gave), then added in order
+      float v9[9];
+#pragma unroll
+      for (int u = 0; u < 9; ++u) v9[u] = (8 * u < n8) ? xc(off + 8 * u + j) : 0.f;
+      float v = v9[0];
       mx = fmaxf(mx, fabsf(v));
       r = __fmul_rn(v, v);
+#pragma unroll
+      for (int u = 1; u < 9; ++u)
+        if (8 * u < n8) {
+          mx = fmaxf(mx, fabsf(v9[u]));
+          r = __fadd_rn(r, __fmul_rn(v9[u], v9[u]));
+        }
 #pragma unroll 4
-      for (int i = 8; i < n8; i += 8) {
+      for (int i = 72; i < n8; i += 8) {
         v = xc(off + i + j);
         mx = fmaxf(mx, fabsf(v));
         r = __fadd_rn(r, __fmul_rn(v, v));
