@@ -13,6 +13,7 @@
 //   warp 1 lane 0  MMA issuer: per tap and 16-channel step three kind::f16 MMAs (hi*hi, lo*hi, hi*lo), bf16 operands
 //   warps 2..5     epilogue: bias + ReLU + 2x2 max-pool (warp shuffles) + bf16 hi/lo split, NHWC stores
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -26,6 +27,7 @@ struct ConvhParams {
   int resident;                // weights resident in shared memory (loaded once)
   uint32_t idesc;
   int H, W, Cout, relu, pool;  // conv output size (= input size), before pooling
+  int dbg;                     // timing probe (AVLD_CONVH_DBG = 2, wrong results): hi*hi pass only
   const float* bias;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -164,33 +166,55 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           tcgen05_fence_after();
           const uint32_t halo_hi = smem_u32(s_halo + hs * Cfg::HSTAGE), halo_lo = halo_hi + Cfg::HALO_BYTES;
           const uint64_t dh_hi = make_smem_desc(halo_hi, ROWB) + sbo_fix, dh_lo = make_smem_desc(halo_lo, ROWB) + sbo_fix;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t w_hi;
-            if (resident) {
-              w_hi = smem_u32(s_w + tap * Cfg::WSTAGE);
-            } else {
-              mbar_wait(&w_full[ws], wphase, 350 + ws);
-              tcgen05_fence_after();
-              w_hi = smem_u32(s_w + ws * Cfg::WSTAGE);
-            }
-            const int kh = tap / 3, kw = tap - kh * 3;
-            // A: 16 groups of 8 pixel rows; group stride = halo pitch (10 rows); swizzle follows absolute addresses
-            const uint64_t shift = static_cast<uint64_t>(((kh * kHW + kw) * ROWB) >> 4);
-            const uint64_t da_hi = dh_hi + shift, da_lo = dh_lo + shift;
-            const uint64_t db_hi = make_smem_desc(w_hi, ROWB), db_lo = db_hi + static_cast<uint64_t>(Cfg::WBLK >> 4);
+          // Taps fully unrolled: the tap shift of A ((kh * pitch + kw) rows) and, with resident weights, the weight block
+          // address are compile-time offsets of descriptors that live in uniform registers.  With a rolled tap loop the
+          // compiler rebuilt both descriptors in vector registers and moved them over with a dozen R2UR per tap; the issuing
+          // warp was then busy all the time while the tensor pipe idled two thirds of it (ncu + AVLD_CONVH_DBG=2: a third of
+          // the MMAs took only 14 - 26 % off the kernel).
+          const bool lo_passes = !(P.dbg & 2);
+          if (resident) {
+            const uint64_t dw_hi = make_smem_desc(smem_u32(s_w), ROWB);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < CBLK / 16; ++k) {
-                const uint64_t koff = static_cast<uint64_t>(k * 2);
-                umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
-                umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t shift = static_cast<uint64_t>((((tap / 3) * kHW + (tap % 3)) * ROWB) >> 4);
+                const uint64_t da_hi = dh_hi + shift, da_lo = dh_lo + shift;
+                const uint64_t db_hi = dw_hi + static_cast<uint64_t>((tap * Cfg::WSTAGE) >> 4);
+                const uint64_t db_lo = db_hi + static_cast<uint64_t>(Cfg::WBLK >> 4);
+#pragma unroll
+                for (int k = 0; k < CBLK / 16; ++k) {
+                  const uint64_t koff = static_cast<uint64_t>(k * 2);
+                  umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                  if (lo_passes) {
+                    umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                    umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                  }
+                }
               }
-              if (!resident) umma_commit(&w_empty[ws]);
             }
             __syncwarp();
-            if (!resident) {
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&w_full[ws], wphase, 350 + ws);
+              tcgen05_fence_after();
+              const uint64_t shift = static_cast<uint64_t>((((tap / 3) * kHW + (tap % 3)) * ROWB) >> 4);
+              const uint64_t da_hi = dh_hi + shift, da_lo = dh_lo + shift;
+              const uint64_t db_hi = make_smem_desc(smem_u32(s_w + ws * Cfg::WSTAGE), ROWB);
+              const uint64_t db_lo = db_hi + static_cast<uint64_t>(Cfg::WBLK >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < CBLK / 16; ++k) {
+                  const uint64_t koff = static_cast<uint64_t>(k * 2);
+                  umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                  if (lo_passes) {
+                    umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                    umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                  }
+                }
+                umma_commit(&w_empty[ws]);
+              }
+              __syncwarp();
               if (++ws == wstages) { ws = 0; wphase ^= 1u; }
             }
           }
@@ -322,6 +346,8 @@ int launch_convh(const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& 
   P.idesc = avld_make_idesc(1, 1, 128, L.c_out);
   P.H = L.in_h; P.W = L.in_w; P.Cout = L.c_out; P.relu = L.relu; P.pool = L.pool;
   P.bias = L.bias;
+  static const int dbg_env = std::getenv("AVLD_CONVH_DBG") ? std::atoi(std::getenv("AVLD_CONVH_DBG")) : 0;
+  P.dbg = dbg_env;
   P.out_hi = out_hi;
   P.out_lo = out_lo;
   if (L.c_out == 64 && L.cblk == 32) return launch_one<64, 32>(a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, sm_count, st);
