@@ -249,6 +249,43 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         uint32_t v[16];
         tmem_ld16(t_acc + c0, v);
         tmem_ld_wait();
+        if (P.pool == 2) {
+          // 2x2 max-pool as a reduce-scatter over the four lanes of a window (partners lane ^ 1 (w) and lane ^ 8 (h), same
+          // warp): each exchange halves the columns a lane keeps, so a lane ends with 4 of the 16 columns, pooled, and
+          // does bias / ReLU / split / store for those only.  12 shuffles instead of 32 and a quarter of the conversion work
+          // per lane; bias and ReLU commute with the max (both monotonic, fl(x + b) is monotonic in x), so the bits are the
+          // same as pooling after them.
+          const bool odd_w = (lane & 1) != 0, odd_h = (lane & kTW) != 0;
+          float keep[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float lo8 = __uint_as_float(v[j]), hi8 = __uint_as_float(v[j + 8]);
+            const float send = odd_w ? lo8 : hi8;
+            keep[j] = max_nan(odd_w ? hi8 : lo8, __shfl_xor_sync(0xffffffffu, send, 1));
+          }
+          float q4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float send = odd_h ? keep[j] : keep[j + 4];
+            q4[j] = max_nan(odd_h ? keep[j + 4] : keep[j], __shfl_xor_sync(0xffffffffu, send, kTW));
+          }
+          const int cq = c0 + (odd_w ? 8 : 0) + (odd_h ? 4 : 0);            // first of this lane's four output channels
+          if (((h | 1) < P.H) && ((w | 1) < P.W) && cq < P.Cout) {         // the whole window lies inside the image
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cq);
+            float o4[4] = {q4[0] + b4.x, q4[1] + b4.y, q4[2] + b4.z, q4[3] + b4.w};
+            __align__(8) __nv_bfloat16 hi[4];
+            __align__(8) __nv_bfloat16 lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (P.relu) o4[j] = relu_nan(o4[j]);
+              hi[j] = __float2bfloat16_rn(o4[j]);
+              lo[j] = __float2bfloat16_rn(o4[j] - __bfloat162float(hi[j]));
+            }
+            *reinterpret_cast<uint2*>(P.out_hi + opix * P.Cout + cq) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(P.out_lo + opix * P.Cout + cq) = *reinterpret_cast<const uint2*>(lo);
+          }
+          continue;
+        }
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -261,17 +298,6 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (P.relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
-        }
-        if (P.pool == 2) {     // partners: lane ^ 1 (w), lane ^ 8 (h): same warp
-          float u[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], 1);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], kTW);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
         }
         if (writer && c0 < P.Cout) {
           __align__(16) __nv_bfloat16 hi[16];
