@@ -197,6 +197,11 @@ def _pool_init(per_worker):
     """Each worker synthesises its own chunks once (setup, untimed) and builds the encoder."""
     import torch
     torch.set_num_threads(1)
+    try:                                   # numpy's BLAS must not spawn a thread team per worker either
+        import threadpoolctl
+        _W["blas_limit"] = threadpoolctl.threadpool_limits(1)
+    except ImportError:
+        pass
     from amphibian_vae_latent_detector_b200 import synth
     from amphibian_vae_latent_detector_b200.encoder import build_standin_encoder
     x, _ = synth.make_chunks(per_worker, CHUNK_LEN, seed=123, first_index=(os.getpid() % 9973) * per_worker)
@@ -229,8 +234,12 @@ def run_reference_arm(args):
     from oracle import hotpath as hp
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    per_worker = 4
+    per_worker = 32
     n_step = workers * per_worker
+    # One thread per worker, one worker per core.  Without these the BLAS behind numpy starts a full thread team in
+    # every worker (cores x cores spinning threads) and the arm runs ~15x slower than the cores allow.
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
     ctx = mp.get_context("spawn")
     times = []
     labels = (np.arange(n_step) % 4).astype(np.int32)
