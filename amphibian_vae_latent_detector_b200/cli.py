@@ -247,6 +247,145 @@ def main_10(argv: Optional[Sequence[str]] = None, here: Optional[Path] = None) -
     print(f"✅ Resumen guardado: {out_dir / 'summary.txt'}")
 
 
+# ---------------------------------------------------------------------------------------------- 08b / 09n / 10b (MAP)
+MAP_ENCODER_DIR = ("models", "bird_net_vae_audio_splitted_encoder_v0")          # core:64-77 (models/, not downloaded_models/)
+
+
+def _map_default_files(project_root: Path, config: Optional[str], pt: Optional[str], yml: Optional[str],
+                       config_relative_to_root: bool = False):
+    """``resolve_default_config`` / ``_encoder_pt`` / ``_encoder_yaml`` of map_detector_core.py:56-77: explicit paths are
+    taken as given, defaults must exist (``FileNotFoundError`` with the reference's wording)."""
+    def must(p: Path, what: str) -> Path:
+        if not p.exists():
+            raise FileNotFoundError(f"No encontré {what} en: {p}")
+        return p
+
+    if config is None:
+        cfg_path = must(project_root / "config.json", "config.json")
+    else:
+        cfg_path = Path(config)
+        if config_relative_to_root:                                              # 08b:142-144
+            cfg_path = cfg_path if cfg_path.is_absolute() else (project_root / cfg_path).resolve()
+        else:                                                                    # 09n:88, 10b:315
+            cfg_path = cfg_path.expanduser().resolve()
+    base = project_root.joinpath(*MAP_ENCODER_DIR)
+    encoder_pt = Path(pt).expanduser().resolve() if pt else must(base / "model.pt", "encoder .pt")
+    encoder_yaml = Path(yml).expanduser().resolve() if yml else must(base / "bird_net_vae_audio_splitted.yaml", "encoder YAML")
+    return cfg_path, encoder_pt, encoder_yaml
+
+
+def parser_08b() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="Fit the Gaussian-MAP detector (08b_fit_map_detector.py)")
+    p.add_argument("--config", type=str, default="config.json")
+    p.add_argument("--root", type=str, required=True, help="Carpeta con subcarpetas por especie (train_chunks/...)")
+    p.add_argument("--device", type=str, default="cpu")
+    _add(p, MEL_FLAGS)
+    p.add_argument("--encoder-pt", type=str, default=None)
+    p.add_argument("--encoder-yaml", type=str, default=None)
+    p.add_argument("--max-per-class", type=int, default=0, help="0 = usar todos; si >0, samplea hasta este N por especie")
+    p.add_argument("--seed", type=int, default=123)
+    p.add_argument("--cache", action="store_true",
+                   help="Guardar/cargar latentes Z por especie en latent_space_exploration/cache_npz/")
+    p.add_argument("--cov-type", type=str, default="lda", choices=["lda", "qda"])
+    p.add_argument("--cov-structure", type=str, default="full", choices=["full", "diag"])
+    p.add_argument("--priors", type=str, default="empirical", choices=["empirical", "uniform"])
+    p.add_argument("--eps", type=float, default=1e-6)
+    p.add_argument("--shrink", type=float, default=0.0)
+    p.add_argument("--set-tau-q", type=float, default=None, help="Ej: 0.01 => tau=quantile(scores_true,0.01)")
+    return p
+
+
+def main_08b(argv: Optional[Sequence[str]] = None, here: Optional[Path] = None) -> None:
+    a = parser_08b().parse_args(argv)
+    if not (0.0 <= a.shrink <= 1.0):
+        raise SystemExit("❌ --shrink debe estar en [0,1].")                      # 08b:131-134
+    if a.set_tau_q is not None and not (0.0 < float(a.set_tau_q) < 1.0):
+        raise SystemExit("❌ --set-tau-q debe estar en (0,1).")
+    project_root = find_project_root(here or Path.cwd())
+    cfg_path = Path(a.config)
+    cfg_path = cfg_path if cfg_path.is_absolute() else (project_root / cfg_path).resolve()
+    cfg = api.load_json(cfg_path)
+    species = cfg.get("species")
+    if not isinstance(species, list) or not all(isinstance(s, str) for s in species):
+        raise SystemExit("❌ config.json debe tener un campo 'species' (lista de strings).")
+    chunks_dir = _resolve_root(a.root, project_root)
+    _, encoder_pt, encoder_yaml = _map_default_files(project_root, str(cfg_path), a.encoder_pt, a.encoder_yaml)
+    print(f"📌 Project root: {project_root}")
+    print(f"🧾 Config: {cfg_path}")
+    print(f"📁 Chunks dir: {chunks_dir}")
+    print(f"🖥️ Device: {a.device}")
+    _device_note(a.device)
+    encoder = api.load_encoder(encoder_pt, encoder_yaml, project_root, None)
+    pipeline.fit_map_detector(cfg_path, chunks_dir, encoder, cov_type=a.cov_type, cov_structure=a.cov_structure,
+                              priors=a.priors, eps=a.eps, shrink=a.shrink, set_tau_q=a.set_tau_q,
+                              max_per_class=a.max_per_class, seed=a.seed, cache=a.cache,
+                              cache_dir=(project_root / "latent_space_exploration" / "cache_npz").resolve(), mel=_mel_kw(a))
+
+
+def parser_09n() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="MAP detection of one WAV (09n_evaluate_wav_detection.py)")
+    p.add_argument("--wav", required=True, type=str, help="Ruta al archivo .wav a evaluar")
+    p.add_argument("--config", type=str, default=None, help="Ruta a config.json (opcional)")
+    p.add_argument("--encoder-pt", type=str, default=None, help="Ruta a model.pt (opcional)")
+    p.add_argument("--encoder-yaml", type=str, default=None, help="Ruta a .yaml del encoder (opcional)")
+    p.add_argument("--device", type=str, default="cpu")
+    _add(p, MEL_FLAGS)
+    return p
+
+
+def main_09n(argv: Optional[Sequence[str]] = None, here: Optional[Path] = None) -> None:
+    a = parser_09n().parse_args(argv)
+    project_root = find_project_root(here or Path.cwd())
+    wav_p = Path(a.wav).expanduser()
+    if not wav_p.is_absolute():
+        wav_p = (Path.cwd() / wav_p).resolve()
+    if not wav_p.exists():
+        raise FileNotFoundError(f"No existe WAV: {wav_p}")                       # 09n:81-85, before anything is loaded
+    cfg_path, encoder_pt, encoder_yaml = _map_default_files(project_root, a.config, a.encoder_pt, a.encoder_yaml)
+    _device_note(a.device)
+    detected, sp, best_score = api.detect_species_map(wav_p, config_path=str(cfg_path), encoder_pt=str(encoder_pt),
+                                                      encoder_yaml=str(encoder_yaml), device=a.device, **_mel_kw(a))
+    if detected:                                                                 # 09n:178-183
+        print(f"✅ DETECTADO (MAP): {sp} | best_score={best_score:.6f}")
+        sys.exit(0)
+    print(f"❌ NO_DETECT (MAP) | best_score={best_score:.6f}")
+    sys.exit(2)
+
+
+def parser_10b() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="MAP benchmark over a folder tree (10b_benchmark_folder_detection_map.py)")
+    p.add_argument("--root", type=str, default=None, help="Carpeta raíz a escanear (ej: latent_space_exploration/val_chunks)")
+    p.add_argument("--config", type=str, default=None, help="Ruta a config.json (opcional)")
+    p.add_argument("--encoder-pt", type=str, default=None, help="Ruta a model.pt (opcional)")
+    p.add_argument("--encoder-yaml", type=str, default=None, help="Ruta a YAML del encoder (opcional)")
+    p.add_argument("--device", type=str, default="cpu", help="cpu o cuda")
+    _add(p, MEL_FLAGS)
+    return p
+
+
+def main_10b(argv: Optional[Sequence[str]] = None, here: Optional[Path] = None) -> None:
+    project_root = find_project_root(here or Path.cwd())
+    a = parser_10b().parse_args(argv)
+    root = Path(a.root).expanduser().resolve() if a.root else project_root / "latent_space_exploration" / "val_chunks"
+    if not root.exists():
+        raise FileNotFoundError(f"No existe root: {root}")
+    config_path, encoder_pt, encoder_yaml = _map_default_files(project_root, a.config, a.encoder_pt, a.encoder_yaml)
+    out_dir = project_root / "outputs" / "detection_benchmark_map"              # 10b:318-319
+    print("=" * 70)
+    print("🔎 BENCHMARK DETECTION ON FOLDER — MAP")
+    print(f"Root: {root}")
+    print(f"Config: {config_path}")
+    print(f"Outputs: {out_dir}")
+    print("=" * 70)
+    _device_note(a.device)
+    print("⏳ Cargando detector MAP (config + encoder) una sola vez...")
+    encoder = api.load_encoder(encoder_pt, encoder_yaml, project_root, None)
+    print("✅ Listo.")
+    pipeline.benchmark_folder_map(root, config_path, encoder, out_dir, mel=_mel_kw(a))
+    print(f"\n✅ CSV guardado: {out_dir / 'results.csv'}")
+    print(f"✅ Resumen guardado: {out_dir / 'summary.txt'}")
+
+
 # ---------------------------------------------------------------------------------------------- q_out grid
 def parser_grid() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(description="q_out grid in one process (run_qout_grid.sh: encode once, radii once)")
@@ -280,11 +419,13 @@ def main_grid(argv: Optional[Sequence[str]] = None, here: Optional[Path] = None)
         print(f"q_out={q}: Acc={r['acc'] * 100:.2f}% | NO_DETECT={r['no_detect'] * 100:.2f}% | rk={r['thresholds']}")
 
 
-COMMANDS = {"normalize": main_00, "encode": main_07, "fit": main_08, "detect": main_09, "benchmark": main_10, "grid": main_grid}
+COMMANDS = {"normalize": main_00, "encode": main_07, "fit": main_08, "detect": main_09, "benchmark": main_10, "grid": main_grid,
+            "fit-map": main_08b, "detect-map": main_09n, "benchmark-map": main_10b}
 
 
 def main(argv: Optional[List[str]] = None) -> None:
-    """``python -m amphibian_vae_latent_detector_b200.cli <normalize|encode|fit|detect|benchmark|grid> <flags>``."""
+    """``python -m amphibian_vae_latent_detector_b200.cli <normalize|encode|fit|detect|benchmark|grid|fit-map|detect-map|benchmark-map>
+    <flags>``."""
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv or argv[0] not in COMMANDS:
         raise SystemExit("usage: cli.py {" + "|".join(COMMANDS) + "} <flags of the corresponding reference script>")

@@ -1,0 +1,12 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's ``10b_benchmark_folder_detection_map.py`` (same flags, messages and exit codes); the work is done by
+``amphibian_vae_latent_detector_b200.cli.main_10b`` on the GPU library."""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+from amphibian_vae_latent_detector_b200.cli import main_10b  # noqa: E402
+
+if __name__ == "__main__":
+    main_10b(here=Path(__file__).resolve().parent)

@@ -1,0 +1,302 @@
+"""CPU: the MAP scripts' surface (row N1 at file level) -- ``08b_fit_map_detector.py``, ``09n_evaluate_wav_detection.py``,
+``10b_benchmark_folder_detection_map.py``.
+
+* flags / defaults of the three parsers (expected tables read from the reference; compared with the reference's own
+  parsers where /root/reference exists);
+* the host logic of ``cli.main_08b`` -> ``main_10b`` -> ``main_09n`` end to end on the seeded WAV tree of
+  ``tests/golden/pipeline_map`` against the artefacts the reference's own ``main()``s wrote there.  No GPU here: the two
+  device entry points the glue calls (``reference_api.encode_wavs_to_latents`` and the engine's MAP ops) are replaced by the
+  numpy oracle, so what is checked is everything *around* them -- sampling, caching, ordering, schema, messages, CSV /
+  summary formats, exit codes.  The same run on the real engine is ``tests/test_gpu_zmap_cli.py``.
+"""
+import csv
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from amphibian_vae_latent_detector_b200 import cli, map_fit
+from amphibian_vae_latent_detector_b200 import reference_api as api
+from oracle import hotpath as hp
+
+REPO = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference/latent_space_exploration")
+GOLD = Path(__file__).parent / "golden" / "pipeline_map"
+MEL = {"sr": 48000, "n_mels": 64, "target_frames": 192, "fmin": 150.0, "fmax": 15000.0, "hop_length": 384, "n_fft": 2048}
+EXPECTED = {
+    "08b": (cli.parser_08b, ["--root", "train_chunks"],
+            {**MEL, "config": "config.json", "root": "train_chunks", "device": "cpu", "encoder_pt": None, "encoder_yaml": None,
+             "max_per_class": 0, "seed": 123, "cache": False, "cov_type": "lda", "cov_structure": "full", "priors": "empirical",
+             "eps": 1e-6, "shrink": 0.0, "set_tau_q": None}),
+    "09n": (cli.parser_09n, ["--wav", "x.wav"],
+            {**MEL, "wav": "x.wav", "config": None, "encoder_pt": None, "encoder_yaml": None, "device": "cpu"}),
+    "10b": (cli.parser_10b, [], {**MEL, "root": None, "config": None, "encoder_pt": None, "encoder_yaml": None, "device": "cpu"}),
+}
+SCRIPTS = {"08b": "08b_fit_map_detector.py", "09n": "09n_evaluate_wav_detection.py",
+           "10b": "10b_benchmark_folder_detection_map.py"}
+
+
+@pytest.mark.parametrize("key", sorted(EXPECTED))
+def test_parser_defaults(key):
+    make, argv, want = EXPECTED[key]
+    assert vars(make().parse_args(argv)) == want
+
+
+def _actions(parser):
+    return {a.dest: (tuple(a.option_strings), a.type, a.default, type(a).__name__, a.required,
+                     tuple(a.choices) if a.choices else None) for a in parser._actions if a.dest != "help"}
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("key", sorted(EXPECTED))
+def test_parser_equals_reference_parser(key):
+    import argparse
+    from oracle.make_golden_pipeline_map import load_map_scripts
+    mod = dict(zip(("08b", "09n", "10b"), load_map_scripts()))[key]
+    captured = {}
+
+    class Stop(Exception):
+        pass
+
+    def fake_parse(self, *a, **k):
+        captured["parser"] = self
+        raise Stop
+
+    orig = argparse.ArgumentParser.parse_args
+    argparse.ArgumentParser.parse_args = fake_parse
+    try:
+        with pytest.raises(Stop):
+            getattr(mod, "parse_args", None) and mod.parse_args() or mod._parse_args()
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    assert _actions(EXPECTED[key][0]()) == _actions(captured["parser"])
+
+
+def test_launchers_exist_under_reference_names():
+    for key, name in SCRIPTS.items():
+        text = (REPO / "latent_space_exploration" / name).read_text()
+        assert f"main_{key}" in text and "amphibian_vae_latent_detector_b200.cli" in text
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# numpy stand-ins for the two device entry points
+# ------------------------------------------------------------------------------------------------------------------
+class OracleEngine:
+    """``Engine``'s MAP surface (``fit_map`` / ``map_score`` + the two accumulators ``map_fit.fit_map`` needs) in numpy,
+    following the reference's arithmetic (float32 quadratic form, float64 constants: core:319-323)."""
+    device = torch.device("cpu")
+
+    def centroid_accumulate(self, Z, label, K):
+        Zn, ln = Z.numpy().astype(np.float64), label.numpy()
+        sums = np.stack([Zn[ln == k].sum(axis=0) for k in range(K)])
+        return torch.from_numpy(sums), torch.from_numpy(np.bincount(ln[ln >= 0], minlength=K).astype(np.int64))
+
+    def cov_accumulate(self, Z, label, mean, k_sel=-1, out=None):
+        Zn, ln, m = Z.numpy().astype(np.float64), label.numpy(), mean.numpy().astype(np.float64)
+        sel = (ln >= 0) if k_sel < 0 else (ln == k_sel)
+        c = Zn[sel] - m[ln[sel]]
+        return torch.from_numpy(c.T @ c)
+
+    def fit_map(self, Z, label, species_names, **kw):
+        return map_fit.fit_map(self, Z, label, species_names, **kw)
+
+    def map_score(self, Z, fit, want_scores=False, tau="fit"):
+        Zn = Z.numpy().astype(np.float32)
+        a, lp = fit.constants()
+        n, K = Zn.shape[0], len(fit.species)
+        scores = np.zeros((n, K))
+        for k in range(K):
+            diff = (Zn - fit.means[k][None]).astype(np.float32)
+            quad = np.einsum("nd,de,ne->n", diff, fit.precision[k].astype(np.float32), diff).astype(np.float64)
+            scores[:, k] = -0.5 * (quad + a[k]) + lp[k]
+        best = scores.max(axis=1) if K else np.full(n, -np.inf)
+        pred = scores.argmax(axis=1).astype(np.int32)
+        t = fit.tau if tau == "fit" else tau
+        if t is not None:
+            pred = np.where(best < float(t), -1, pred).astype(np.int32)
+        return torch.from_numpy(pred), torch.from_numpy(best), (torch.from_numpy(scores) if want_scores else None)
+
+
+def oracle_encode_wavs(encoder, wav_paths, device=None, *, duration=5.0, return_failed=False, **mel):
+    rows, failed = [], []
+    for p in wav_paths:
+        try:
+            rows.append(api._fix_length(api.load_wav(p, mel.get("sr", 48000)), mel.get("sr", 48000), duration))
+        except Exception:
+            failed.append(p)
+    Z = hp.encode_batch(encoder, np.stack(rows), **mel) if rows else np.zeros((0, 128), np.float32)
+    return (Z, failed) if return_failed else Z
+
+
+@pytest.fixture(scope="module")
+def project(tmp_path_factory):
+    """The temp project of oracle/make_golden_pipeline_map.py: raw synthetic tree -> normalised PCM_16 chunks (oracle)."""
+    from amphibian_vae_latent_detector_b200 import synth
+    from oracle import librosa_port as lp
+    pm = json.loads((GOLD.parent / "pipeline" / "meta.json").read_text())
+    root = tmp_path_factory.mktemp("mapproj")
+    lse = root / "latent_space_exploration"
+    (root / "downloaded_models").mkdir()
+    mdir = root / "models" / "bird_net_vae_audio_splitted_encoder_v0"
+    mdir.mkdir(parents=True)
+    (mdir / "model.pt").write_bytes(b"")
+    (mdir / "bird_net_vae_audio_splitted.yaml").write_text("encoder: {}\n")
+    for split, n, seed, every in (("train_chunks", pm["n_train"], pm["seed_train"], 17), ("val_chunks", pm["n_val"], pm["seed_val"], 11)):
+        synth.write_wav_tree(lse / "raw" / split, pm["species"], n, pm["length"], seed=seed, special_every=every)
+        for wav in sorted((lse / "raw" / split).rglob("*.wav")):                  # 00:41-57 with the oracle's normaliser
+            y, _ok = hp.rms_normalize(api.load_wav(wav))
+            out = lse / split / wav.parent.name / wav.name
+            out.parent.mkdir(parents=True, exist_ok=True)
+            lp.write_wav(out, np.asarray(y, np.float32), 48000)                   # written even when gated (00:54-57)
+    return root, lse, pm
+
+
+@pytest.fixture()
+def host_only(monkeypatch, standin_encoder):
+    monkeypatch.setattr(api, "encode_wavs_to_latents", oracle_encode_wavs)
+    monkeypatch.setattr(api, "_engine", lambda *a, **k: OracleEngine())
+    monkeypatch.setattr(api, "load_encoder", lambda *a, **k: standin_encoder)
+    monkeypatch.setattr(api, "_dev_rows", lambda Z: torch.from_numpy(np.ascontiguousarray(Z, dtype=np.float32)))
+
+
+def _read_csv(path):
+    with open(path, newline="", encoding="utf-8") as f:
+        return list(csv.DictReader(f))
+
+
+def check_case_against_reference(root, lse, case, capsys, *, tol, score_tol, cov_tol=None, prec_tol=None):
+    """Run main_08b + main_10b + main_09n for ``case`` in project ``root`` and compare with tests/golden/pipeline_map/<case>.
+    Shared with the GPU test (looser tolerances there: latents differ by <= 1e-3)."""
+    meta = json.loads((GOLD / "meta.json").read_text())["cases"][case]
+    here = lse
+    cfg_path = root / "config.json"
+    cfg_path.write_text(json.dumps({"species": json.loads((GOLD / "meta.json").read_text())["species"], "chunk_seconds": 3.0},
+                                   indent=2), encoding="utf-8")
+    cache = root / "latent_space_exploration" / "cache_npz"
+    if cache.exists():
+        for f in cache.glob("*.npz"):
+            f.unlink()
+    cli.main_08b(["--config", str(cfg_path), "--root", str(lse / "train_chunks"), "--device", "cpu"] + meta["flags"], here=here)
+    cli.main_10b(["--root", str(lse / "val_chunks"), "--config", str(cfg_path), "--device", "cpu"], here=here)
+    log = capsys.readouterr().out
+    got = json.loads(cfg_path.read_text(encoding="utf-8"))
+    ref = json.loads((GOLD / case / "config_used.json").read_text(encoding="utf-8"))
+    params = np.load(GOLD / case / "params.npz")
+    assert cfg_path.with_suffix(".json.bak").exists()
+    assert list(got) == list(ref)                                                  # species, chunk_seconds, map_detector
+    g, r = got["map_detector"], ref["map_detector"]
+    assert list(g) == list(r)
+    names = list(r["means"])
+    for k in ("model", "cov_type", "cov_structure", "priors"):
+        assert g[k] == r[k]
+    for key in ("means", "cov", "precision"):
+        assert list(g[key]) == names
+        a = np.stack([np.array(g[key][sp]) for sp in names])
+        b = params[key].astype(np.float64)
+        assert a.shape == b.shape
+        lim = {"cov": cov_tol, "precision": prec_tol}.get(key) or tol
+        assert np.max(np.abs(a - b)) <= lim * np.max(np.abs(b)), key
+    for sp in names:
+        assert abs(g["logdet_cov"][sp] - r["logdet_cov"][sp]) <= max(score_tol, tol * abs(r["logdet_cov"][sp]))
+    if r["tau"] is None:
+        assert g["tau"] is None
+    else:
+        assert abs(g["tau"] - r["tau"]) <= max(score_tol, tol * abs(r["tau"]))
+    mg, mr = g["meta_fit"], r["meta_fit"]
+    assert list(mg) == list(mr)
+    assert {k: v for k, v in mg.items() if k not in ("per_species", "chunks_dir", "score_true_global_summary")} == \
+           {k: v for k, v in mr.items() if k not in ("per_species", "chunks_dir", "score_true_global_summary")}
+    assert mg["chunks_dir"] == str(lse / "train_chunks")
+    for k, v in mr["score_true_global_summary"].items():
+        assert abs(mg["score_true_global_summary"][k] - v) <= max(score_tol, tol * abs(v))
+    assert list(mg["per_species"]) == list(mr["per_species"])
+    for sp in names:
+        pg, pr = mg["per_species"][sp], mr["per_species"][sp]
+        assert list(pg) == list(pr)
+        assert (pg["N"], pg["failed"], pg["used"]) == (pr["N"], pr["failed"], pr["used"])
+        assert pg["prior"] == pytest.approx(pr["prior"], rel=1e-12)
+        for k, v in pr["score_true_summary"].items():
+            assert abs(pg["score_true_summary"][k] - v) <= max(score_tol, tol * abs(v))
+    # 10b artefacts
+    out = root / "outputs" / "detection_benchmark_map"
+    rg, rr = _read_csv(out / "results.csv"), _read_csv(GOLD / case / "results.csv")
+    assert list(rg[0]) == list(rr[0]) == ["file", "true_species", "pred_species", "detected", "correct", "best_score"]
+    assert [Path(x["file"]).name for x in rg] == [Path(x["file"]).name for x in rr]
+    flips = 0
+    for a, b in zip(rg, rr):
+        sa, sb = float(a["best_score"]), float(b["best_score"])
+        assert abs(sa - sb) <= max(score_tol, tol * abs(sb))
+        if a["pred_species"] != b["pred_species"]:
+            flips += 1
+    # a prediction may only differ where the reference's own margins are inside the tolerance; count them via the scores
+    assert flips <= (0 if score_tol < 1e-2 else 3)
+    if flips == 0:
+        assert (out / "summary.txt").read_text(encoding="utf-8") == (GOLD / case / "summary.txt").read_text(encoding="utf-8")
+    ref_log = (GOLD / case / "run.log").read_text(encoding="utf-8")
+    for line in ("🔎 BENCHMARK DETECTION ON FOLDER — MAP", "✅ MAP detector fit listo. (NO_DETECT se decide con tau en 09n/10b.)",
+                 "⏱️ chunk_seconds usados: 3.0"):
+        assert line in log and line in ref_log
+    for ln in ref_log.splitlines():                                                # every "encoded" / cache line of the fit
+        if ln.startswith("🧪") or ln.startswith("   ↳ guardado cache"):
+            assert ln in log, ln
+    # 09n on one file per species: exit code 0 / 2 and the printed score
+    for rel, (det, name, best) in meta["detect_species_map"].items():
+        with pytest.raises(SystemExit) as ex:
+            cli.main_09n(["--wav", str(lse / rel), "--config", str(cfg_path)], here=here)
+        line = capsys.readouterr().out.strip().splitlines()[-1]
+        score = float(line.rsplit("best_score=", 1)[1])
+        assert abs(score - best) <= max(score_tol, tol * abs(best))
+        if flips == 0:
+            assert ex.value.code == (0 if det else 2)
+            assert line.startswith(f"✅ DETECTADO (MAP): {name} |" if det else "❌ NO_DETECT (MAP) |")
+    return got
+
+
+@pytest.mark.parametrize("case", ["lda_diag_tau", "qda_full_uniform"])
+def test_map_scripts_host_logic_matches_reference_artifacts(project, host_only, capsys, case):
+    root, lse, _ = project
+    check_case_against_reference(root, lse, case, capsys, tol=2e-5, score_tol=2e-3)
+
+
+def test_fit_map_cache_is_reused(project, host_only, capsys):
+    """08b --cache: second run loads cache_npz/Z_<root>_<species>.npz (08b:196-204) and reproduces the fit exactly."""
+    root, lse, _ = project
+    cfg_path = root / "config_cache.json"
+    cfg_path.write_text(json.dumps({"species": json.loads((GOLD / "meta.json").read_text())["species"], "chunk_seconds": 3.0}))
+    argv = ["--config", str(cfg_path), "--root", str(lse / "train_chunks"), "--cov-structure", "diag", "--shrink", "0.3",
+            "--max-per-class", "8", "--cache"]
+    for f in (root / "latent_space_exploration" / "cache_npz").glob("*.npz"):
+        f.unlink()
+    cli.main_08b(argv, here=lse)
+    first, log1 = json.loads(cfg_path.read_text())["map_detector"], capsys.readouterr().out
+    cli.main_08b(argv, here=lse)
+    second, log2 = json.loads(cfg_path.read_text())["map_detector"], capsys.readouterr().out
+    assert "🧊" not in log1 and log2.count("🧊") == 4
+    assert first["means"] == second["means"] and first["logdet_cov"] == second["logdet_cov"]
+    z = np.load(next((root / "latent_space_exploration" / "cache_npz").glob("*.npz")))
+    assert sorted(z.files) == ["Z", "failed", "root"] and z["Z"].shape == (8, 128)
+
+
+def test_flag_validation_and_missing_files(tmp_path, host_only):
+    (tmp_path / "downloaded_models").mkdir()
+    (tmp_path / "latent_space_exploration").mkdir()
+    (tmp_path / "config.json").write_text(json.dumps({"species": ["a"]}))
+    (tmp_path / "latent_space_exploration" / "train_chunks").mkdir()
+    here = tmp_path / "latent_space_exploration"
+    with pytest.raises(SystemExit, match="--shrink debe estar en"):
+        cli.main_08b(["--root", "train_chunks", "--shrink", "1.5"], here=here)
+    with pytest.raises(SystemExit, match="--set-tau-q debe estar en"):
+        cli.main_08b(["--root", "train_chunks", "--set-tau-q", "1.0"], here=here)
+    with pytest.raises(FileNotFoundError, match="No encontré encoder .pt en"):      # core:64-69, models/ not downloaded_models/
+        cli.main_08b(["--root", "train_chunks"], here=here)
+    with pytest.raises(SystemExit, match="No existe chunks_dir"):
+        cli.main_08b(["--root", "nowhere"], here=here)
+    with pytest.raises(FileNotFoundError, match="No existe WAV"):
+        cli.main_09n(["--wav", str(tmp_path / "missing.wav")], here=here)
+    with pytest.raises(FileNotFoundError, match="No existe root"):
+        cli.main_10b(["--root", str(tmp_path / "nope")], here=here)
+    (tmp_path / "config.json").write_text(json.dumps({"species": "a"}))
+    with pytest.raises(SystemExit, match="debe tener un campo 'species'"):
+        cli.main_08b(["--root", "train_chunks"], here=here)
