@@ -47,13 +47,19 @@ def window_starts(n_samples: int, window_len: int, hop_len: int) -> np.ndarray:
 
 def open_pcm16_mono(path, sr: int) -> np.ndarray:
     """Mono PCM_16 WAV -> int16 sample array, memory-mapped (nothing is read until it is sliced).  Raises ``ValueError``
-    for any other sample format / channel count (the caller then decodes as ``librosa.load`` would)."""
+    for any other sample format / channel count (the caller then decodes as ``librosa.load`` would).
+
+    A day of 48 kHz PCM_16 audio is 8.3 GB, beyond the 32-bit sizes of RIFF, so the 64-bit forms recorders and libsndfile
+    write are accepted too: ``RF64`` / ``BW64`` files (true data size in the ``ds64`` chunk, the 32-bit field holds
+    0xFFFFFFFF) and plain ``RIFF`` files whose data size field is the 0xFFFFFFFF / 0 placeholder of a streamed write --
+    both mean "to the end of the file"."""
     import struct
     with open(path, "rb") as f:
         head = f.read(12)
-        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+        if len(head) < 12 or head[:4] not in (b"RIFF", b"RF64", b"BW64") or head[8:12] != b"WAVE":
             raise RuntimeError(f"{path}: not a RIFF/WAVE file")
         fmt = None
+        data_size64 = None
         while True:
             hdr = f.read(8)
             if len(hdr) < 8:
@@ -62,6 +68,10 @@ def open_pcm16_mono(path, sr: int) -> np.ndarray:
             if name == b"fmt ":
                 fmt = struct.unpack("<HHIIHH", f.read(16))
                 f.seek(size - 16 + (size & 1), 1)
+            elif name == b"ds64":
+                body = f.read(size + (size & 1))
+                if len(body) >= 16:
+                    data_size64 = struct.unpack("<Q", body[8:16])[0]                 # riffSize, dataSize, sampleCount, ...
             elif name == b"data":
                 offset = f.tell()
                 break
@@ -74,7 +84,10 @@ def open_pcm16_mono(path, sr: int) -> np.ndarray:
         raise RuntimeError(f"{path}: sample rate {rate} != {sr}; resampling is not implemented on this path")
     if tag != 1 or nch != 1 or bits != 16:
         raise ValueError("not mono PCM_16")
-    n = min(size, Path(path).stat().st_size - offset) // 2
+    remaining = Path(path).stat().st_size - offset
+    if size == 0xFFFFFFFF or (size == 0 and remaining > 0):
+        size = data_size64 if data_size64 else remaining
+    n = min(size, remaining) // 2
     if n == 0:
         return np.zeros(0, dtype="<i2")
     return np.memmap(str(path), dtype="<i2", mode="r", offset=offset, shape=(n,))

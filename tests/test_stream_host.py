@@ -64,3 +64,45 @@ def test_slabs_cover_the_recording(hop, slab):
             assert np.array_equal(row[:m], x[s:s + m]) and not row[m:].any()
             seen.append(int(s))
     assert seen == stream.window_starts(x.shape[0], L, hop).tolist()
+
+
+def _rf64(path, n_samples, tail, *, magic=b"RF64", data_field=0xFFFFFFFF, with_ds64=True):
+    """A sparse 64-bit WAV: header, ``n_samples`` zero samples (a hole in the file), the last ``len(tail)`` of them = tail."""
+    data_bytes = 2 * n_samples
+    ds64 = b"ds64" + struct.pack("<IQQQI", 28, 4 + 36 + 24 + data_bytes, data_bytes, n_samples, 0) if with_ds64 else b""
+    head = magic + struct.pack("<I", 0xFFFFFFFF) + b"WAVE" + ds64 + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 48000, 96000, 2, 16) \
+        + b"data" + struct.pack("<I", data_field)
+    with open(path, "wb") as f:
+        f.write(head)
+        f.truncate(len(head) + data_bytes)
+        f.seek(len(head) + data_bytes - tail.nbytes)
+        f.write(tail.tobytes())
+    return len(head)
+
+
+@pytest.mark.parametrize("kind", ["rf64", "bw64", "riff_placeholder", "riff_zero"])
+def test_open_day_long_recordings_beyond_4_gib(tmp_path, kind):
+    """24 h at 48 kHz = 4 147 200 000 samples = 8.3 GB of PCM_16: RIFF's 32-bit sizes cannot hold it (BASELINE configs[4])."""
+    n = 24 * 3600 * 48000
+    tail = np.arange(-500, 500).astype("<i2")
+    path = tmp_path / f"{kind}.wav"
+    kw = {"rf64": {}, "bw64": {"magic": b"BW64"}, "riff_placeholder": {"magic": b"RIFF", "with_ds64": False},
+          "riff_zero": {"magic": b"RIFF", "with_ds64": False, "data_field": 0}}[kind]
+    _rf64(path, n, tail, **kw)
+    if path.stat().st_blocks * 512 > 64 << 20:
+        pytest.skip("file system without sparse files")
+    m = stream.open_pcm16_mono(path, 48000)
+    assert m.shape == (n,)
+    assert np.array_equal(m[-1000:], tail) and not m[:4096].any() and not m[n // 2:n // 2 + 4096].any()
+    starts = stream.window_starts(n, 144000, 144000)
+    assert starts.shape == (28800,) and int(starts[-1]) + 144000 == n              # 28 800 windows of 3 s
+
+
+def test_open_rf64_data_size_shorter_than_file(tmp_path):
+    """ds64 holds the true payload size: trailing chunks after the data are not read as samples."""
+    x = np.arange(-100, 100).astype("<i2")
+    ds64 = b"ds64" + struct.pack("<IQQQI", 28, 0, x.nbytes, x.shape[0], 0)
+    body = b"WAVE" + ds64 + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 48000, 96000, 2, 16) + b"data" + \
+        struct.pack("<I", 0xFFFFFFFF) + x.tobytes() + b"LIST" + struct.pack("<I", 4) + b"tail"
+    (tmp_path / "c.wav").write_bytes(b"RF64" + struct.pack("<I", 0xFFFFFFFF) + body)
+    assert np.array_equal(stream.open_pcm16_mono(tmp_path / "c.wav", 48000), x)
