@@ -19,7 +19,7 @@ Reference functions behind each method (paths relative to ``latent_space_explora
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

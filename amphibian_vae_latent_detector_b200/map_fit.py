@@ -9,7 +9,7 @@ slogdet, inverse) is the reference's own numpy sequence in the reference's own d
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -17,7 +17,6 @@ independent implementation in tests/test_oracle_pinning.py.
 """
 from __future__ import annotations
 
-import struct
 import wave
 from pathlib import Path
 from typing import Callable, Optional, Tuple, Union
