@@ -12,8 +12,8 @@ error behaviour -- executed by the CUDA library.  Paths r
     DetectorSession                                     10_benchmark_folder_detection.py:113-199
 
 plus batched additions (``*_batch`` / ``predict_many``) that feed many files per GPU pass.  File I/O is
-PCM WAV via the standard library (the reference's librosa.load / soundfile.write on 16-bit mono/stereo
-files); resampling is not implemented (the reference's datasets are already 48 kHz) and raises.
+WAV via the standard library (the reference's librosa.load on PCM_16 / 24 / 32 / U8 / IEEE-float files of any
+channel count, soundfile.write as PCM_16); resampling is not implemented (the reference's datasets are already 48 kHz) and raises.
 Everything numeric runs on the GPU: ``device`` arguments are accepted for signature compatibility, and
 "cpu" is mapped to ``cuda:0`` -- there is no CPU implementation to fall back to.
 """
@@ -77,16 +77,64 @@ def _engine_with_encoder(encoder, chunk_len, device, *, max_batch: int = 64, **m
 # ----------------------------------------------------------------------------------------------------------
 # WAV I/O (librosa.load(sr=sr, mono=True) on PCM files; soundfile.write(float data) = PCM_16)
 # ----------------------------------------------------------------------------------------------------------
+def _read_ieee_float_wav(path):
+    """RIFF/WAVE with format tag 3 (IEEE float; also the EXTENSIBLE form), which the standard library's ``wave`` rejects:
+    -> (channels, bytes per sample, rate, raw payload)."""
+    import struct
+    with open(path, "rb") as f:
+        head = f.read(12)
+        if len(head) < 12 or head[:4] != b"RIFF" or head[8:12] != b"WAVE":
+            raise RuntimeError(f"{path}: not a RIFF/WAVE file")
+        fmt = None
+        while True:
+            hdr = f.read(8)
+            if len(hdr) < 8:
+                raise RuntimeError(f"{path}: no data chunk")
+            name, size = hdr[:4], struct.unpack("<I", hdr[4:])[0]
+            if name == b"fmt ":
+                body = f.read(size + (size & 1))
+                fmt = struct.unpack("<HHIIHH", body[:16])
+                if fmt[0] == 0xFFFE and len(body) >= 26:                          # EXTENSIBLE: the real tag leads the GUID
+                    fmt = (struct.unpack("<H", body[24:26])[0],) + fmt[1:]
+            elif name == b"data":
+                raw = f.read(size)
+                break
+            else:
+                f.seek(size + (size & 1), 1)
+    if fmt is None or fmt[0] != 3 or fmt[5] not in (32, 64):
+        raise RuntimeError(f"{path}: unsupported WAV format tag {None if fmt is None else fmt[0]}")
+    return fmt[1], fmt[5] // 8, fmt[2], raw
+
+
 def load_wav(path, sr: int = 48000) -> np.ndarray:
-    with wave.open(str(path), "rb") as w:
-        nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
-        raw = w.readframes(n)
+    """``librosa.load(path, sr=sr, mono=True)`` for WAV files: float32 samples exactly as libsndfile converts them
+    (PCM_16 / 2^15, PCM_24 / 2^23, PCM_32 / 2^31, PCM_U8 (u - 128) / 2^7, IEEE float as stored), channels averaged.
+    The sample rate must already be ``sr``: resampling is not implemented and raises."""
+    is_float = False
+    try:
+        with wave.open(str(path), "rb") as w:
+            nch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+            raw = w.readframes(n)
+    except wave.Error as e:
+        if "unknown format" not in str(e) and "unknown extended format" not in str(e):
+            raise
+        nch, width, rate, raw = _read_ieee_float_wav(path)
+        is_float = True
     if rate != sr:
         raise RuntimeError(f"{path}: sample rate {rate} != {sr}; resampling is not implemented on this path")
-    if width == 2:
+    if is_float:
+        x = np.frombuffer(raw, dtype="<f4" if width == 4 else "<f8").astype(np.float32)
+    elif width == 2:
         x = np.frombuffer(raw, dtype="<i2").astype(np.float32) * np.float32(1.0 / 32768.0)
     elif width == 4:
         x = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif width == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = (b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16))
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)                               # sign-extend 24 -> 32 bits
+        x = v.astype(np.float32) * np.float32(1.0 / 8388608.0)                     # exact: 24-bit integers fit a float32
+    elif width == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - np.float32(128.0)) * np.float32(1.0 / 128.0)
     else:
         raise RuntimeError(f"{path}: unsupported sample width {width}")
     if nch > 1:
