@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 files=("$@")
 if [ ${#files[@]} -eq 0 ]; then
-  files=(tests/test_gpu_gemm.py tests/test_gpu_rms.py tests/test_gpu_radial.py tests/test_gpu_features.py tests/test_gpu_encoder.py tests/test_gpu_e2e.py tests/test_gpu_reference_api.py tests/test_gpu_map.py tests/test_gpu_pipeline.py tests/test_gpu_stream.py tests/test_gpu_grid_c4.py tests/test_gpu_edge_cases.py)
+  files=(tests/test_gpu_gemm.py tests/test_gpu_rms.py tests/test_gpu_radial.py tests/test_gpu_features.py tests/test_gpu_encoder.py tests/test_gpu_e2e.py tests/test_gpu_reference_api.py tests/test_gpu_map.py tests/test_gpu_pipeline.py tests/test_gpu_stream.py tests/test_gpu_grid_c4.py tests/test_gpu_edge_cases.py tests/test_gpu_zmap_cli.py)
 fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
