@@ -6,8 +6,8 @@ The semantics defined for a long WAV are therefore the ones that reproduce that 
 recording is cut into windows of ``chunk_seconds`` (hop = window unless ``hop_seconds`` is given), the last partial
 window is zero-padded on the right as ``wav_to_mel`` pads a short file, and every window goes through exactly what one
 chunk file goes through -- ``rms_normalize`` + the PCM_16 write/read of ``process_folder`` (00:29-57), log-mel, encoder
-mean, radial decision (09:416-436) -- so window ``i`` of the stream gives the same answer as the chunk file holding the
-same samples.
+mean, radial decision (09:416-436) or, 09n / 10b style, Gaussian-MAP decision (``detect_long_wav_map``) -- so window ``i``
+of the stream gives the same answer as the chunk file holding the same samples.
 
 Data path: PCM_16 samples are sliced straight out of the (memory-mapped) WAV payload into pinned host slabs by a
 filler thread while the previous slab is inside ``avld_encode_detect_host_pcm16`` (which itself double-buffers
@@ -36,6 +36,17 @@ class WindowResult:
     species: Optional[str]
     best_distance: float
     normalised: bool          # False = the window was below the rms_min gate (00:32-34) and passed through unscaled
+
+
+@dataclass
+class MapWindowResult:
+    """One window decided by the Gaussian-MAP detector (09n:114-140): ``best_score`` is the largest class score, reported
+    for rejected windows too."""
+    start_s: float
+    detected: bool
+    species: Optional[str]
+    best_score: float
+    normalised: bool
 
 
 def window_starts(n_samples: int, window_len: int, hop_len: int) -> np.ndarray:
@@ -232,3 +243,80 @@ def _detect_float_stream(y: np.ndarray, encoder, centroids, thresholds, *, sr, w
         for s, p, b, o in zip(piece, pred, best, ok):
             out.append(WindowResult(float(s) / sr, bool(p >= 0), species[p] if p >= 0 else None, float(b), bool(o)))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The same windows decided 09n / 10b style (BASELINE.json configs[4]): Gaussian-MAP score, argmax, tau
+# ----------------------------------------------------------------------------------------------------------
+def _map_windows(slabs, eng, fit, sr: int) -> List[MapWindowResult]:
+    """``slabs`` yields ``(starts, host slab [m, window_len])``; the encode half of the fused host call produces the
+    latent means (its radial half runs against a single dummy centroid and is ignored), ``avld_map_score`` decides."""
+    D = eng.latent_dim
+    zero, far, prio = np.zeros((1, D), np.float32), np.array([np.inf]), np.zeros(1, np.int32)
+    out: List[MapWindowResult] = []
+    for starts, slab in slabs:
+        _, _, ok, mu = eng.encode_detect_host(slab, zero, far, prio, pcm16=True, want_mu=True)
+        if fit is None:                                                            # no usable class (09n:142-143)
+            out += [MapWindowResult(float(s) / sr, False, None, -float("inf"), bool(o)) for s, o in zip(starts, ok)]
+            continue
+        pred, best, _ = eng.map_score(torch.from_numpy(mu).to(eng.device), fit)
+        for s, p, b, o in zip(starts, pred.cpu().numpy(), best.cpu().numpy(), ok):
+            out.append(MapWindowResult(float(s) / sr, bool(p >= 0), fit.species[p] if p >= 0 else None, float(b), bool(o)))
+    return out
+
+
+def detect_pcm16_stream_map(pcm: np.ndarray, encoder: torch.nn.Module, means: Dict[str, np.ndarray],
+                            precisions: Dict[str, np.ndarray], logdets: Dict[str, float], priors: Dict[str, float],
+                            tau: Optional[float], *, sr: int = 48000, window_seconds: float = 5.0,
+                            hop_seconds: Optional[float] = None, slab_windows: int = 2048, device=0, n_mels: int = 64,
+                            fmin: float = 150.0, fmax: float = 15000.0, hop_length: int = 384, n_fft: int = 2048,
+                            target_frames: int = 192) -> List[MapWindowResult]:
+    """``pcm`` int16 [n_samples] (array or memmap) -> one :class:`MapWindowResult` per window; the parameters are those
+    ``read_map_detector_params`` / ``get_priors_from_map_meta`` return (core:326-420)."""
+    window_len = int(sr * window_seconds)
+    hop_len = window_len if hop_seconds is None else int(sr * hop_seconds)
+    if hop_len <= 0:
+        raise ValueError("hop_seconds must be positive")
+    mel_kw = dict(sr=sr, n_mels=n_mels, fmin=fmin, fmax=fmax, hop_length=hop_length, n_fft=n_fft, target_frames=target_frames)
+    n_win = window_starts(pcm.shape[0], window_len, hop_len).shape[0]
+    eng = api._engine_with_encoder(encoder, window_len, device, max_batch=64 if n_win <= 256 else 1024, **mel_kw)
+    fit = api._map_fit_from_params(means, precisions, logdets, priors, tau, eng.latent_dim)
+    return _map_windows(iter_slabs(pcm, window_len, hop_len, slab_windows), eng, fit, sr)
+
+
+def detect_long_wav_map(wav_path, *, config_path, encoder: torch.nn.Module, window_seconds: Optional[float] = None,
+                        hop_seconds: Optional[float] = None, sr: int = 48000, slab_windows: int = 4096, device=0,
+                        **mel_kw) -> List[MapWindowResult]:
+    """Windows of ``map_detector.meta_fit.chunk_seconds`` (core:358-370) over a long WAV, decided with the config's
+    Gaussian-MAP detector as ``09n_evaluate_wav_detection.py`` decides one chunk file."""
+    cfg = api.load_json(Path(config_path))
+    means, precisions, logdets, tau = api.read_map_detector_params(cfg)
+    species = sorted(set(means) & set(precisions) & set(logdets))
+    if not species:
+        raise RuntimeError("map_detector inconsistente: no hay intersección entre means/precision/logdet_cov.")     # 09n:93-94
+    priors = api.get_priors_from_map_meta(cfg, species)
+    win = float(api.get_chunk_seconds_for_map(cfg) if window_seconds is None else window_seconds)
+    try:
+        pcm = open_pcm16_mono(wav_path, sr)
+    except ValueError:                       # other sample formats / channel counts: decoded as librosa.load would
+        y = api.load_wav(wav_path, sr)
+        window_len = int(sr * win)
+        hop_len = window_len if hop_seconds is None else int(sr * hop_seconds)
+        kw = dict(sr=sr, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048, target_frames=192)
+        kw.update(mel_kw)
+        eng = api._engine_with_encoder(encoder, window_len, device, **kw)
+        fit = api._map_fit_from_params(means, precisions, logdets, priors, tau, eng.latent_dim)
+        starts = window_starts(y.shape[0], window_len, hop_len)
+
+        def float_slabs():
+            for i in range(0, starts.shape[0], slab_windows):
+                piece = starts[i:i + slab_windows]
+                slab = np.zeros((piece.shape[0], window_len), dtype=np.float32)
+                for j, st in enumerate(piece):
+                    m = min(window_len, y.shape[0] - int(st))
+                    slab[j, :m] = y[st:st + m]
+                yield piece, slab
+
+        return _map_windows(float_slabs(), eng, fit, sr)
+    return detect_pcm16_stream_map(pcm, encoder, means, precisions, logdets, priors, tau, sr=sr, window_seconds=win,
+                                   hop_seconds=hop_seconds, slab_windows=slab_windows, device=device, **mel_kw)

@@ -45,3 +45,52 @@ def test_map_scripts_match_reference_artifacts(project, standin_encoder, monkeyp
     monkeypatch.setattr(api, "load_encoder", lambda *a, **k: standin_encoder)  # the thesis checkpoint is not public
     cfg = check_case_against_reference(root, lse, case, capsys, tol=2e-3, cov_tol=1e-2, prec_tol=3e-2, score_tol=2.0)
     assert Path(cfg["map_detector"]["meta_fit"]["chunks_dir"]).name == "train_chunks"
+
+
+def test_stream_map_window_equals_chunk_file_workflow(tmp_path, standin_encoder):
+    """BASELINE configs[4], 09n / 10b style: window i of ``stream.detect_long_wav_map`` == ``process_folder`` (00) on a chunk file
+    holding the same samples, then ``MapDetectorSession.predict_many`` (10b) -- same kernels, only the batch differs."""
+    import wave
+
+    import numpy as np
+    import torch
+
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    from amphibian_vae_latent_detector_b200 import stream, synth
+    params = np.load(GOLD / "lda_diag_tau" / "params.npz")
+    ref = json.loads((GOLD / "lda_diag_tau" / "config_used.json").read_text(encoding="utf-8"))
+    md = ref["map_detector"]
+    names = list(md["means"])
+    for key in ("means", "precision"):                                           # the reference-made MAP parameters
+        md[key] = {sp: params[key][i].tolist() for i, sp in enumerate(names)}
+    md.pop("cov")
+    (tmp_path / "config.json").write_text(json.dumps(ref))
+    L, n_full, tail = 144000, 7, 61000
+    x, _ = synth.make_chunks(n_full + 1, L, seed=91, special_every=4)
+    pcm = torch.clamp(torch.round(x * 32767.0), -32768, 32767).to(torch.int16).numpy()
+
+    def write(path, samples):
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(1)
+            w.setsampwidth(2)
+            w.setframerate(48000)
+            w.writeframes(samples.astype("<i2").tobytes())
+
+    write(tmp_path / "long.wav", np.concatenate([pcm[:n_full].reshape(-1), pcm[n_full, :tail]]))
+    for i in range(n_full):
+        write(tmp_path / "raw" / "sp" / f"w{i:02d}.wav", pcm[i])
+    pad = np.zeros(L, np.int16)
+    pad[:tail] = pcm[n_full, :tail]
+    write(tmp_path / "raw" / "sp" / f"w{n_full:02d}.wav", pad)
+    api.process_folder(tmp_path / "raw", tmp_path / "norm")
+    sess = api.MapDetectorSession(tmp_path, tmp_path / "config.json", tmp_path / "x.pt", tmp_path / "x.yaml", "cuda")
+    sess.set_params(api.load_json(tmp_path / "config.json"))
+    sess.encoder = standin_encoder
+    by_file = sess.predict_many(sorted((tmp_path / "norm" / "sp").glob("*.wav")))
+    res = stream.detect_long_wav_map(tmp_path / "long.wav", config_path=tmp_path / "config.json", encoder=standin_encoder,
+                                     slab_windows=3)
+    assert [w.start_s for w in res] == [3.0 * i for i in range(n_full + 1)]
+    for w, (det, sp, best) in zip(res, by_file):
+        assert (w.detected, w.species) == (det, sp)
+        assert abs(w.best_score - best) <= 1e-5 * abs(best)
