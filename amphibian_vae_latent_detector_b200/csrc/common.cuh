@@ -221,6 +221,8 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold(avld_ctx* c, int n, cudaStream_t st);
 int launch_fold2(avld_ctx* c, int n, cudaStream_t st);
 int launch_stft_mel_fold2(avld_ctx* c, int n, cudaStream_t st);
+bool dftf4_supported(const avld_ctx* c);                               // dftf4.cu: experimental, AVLD_DFT_DUAL=1
+int launch_stft_mel_fold2_dual(avld_ctx* c, int n, cudaStream_t st);
 bool dftg_supported(const avld_ctx* c);
 int launch_stft_mel_gen(avld_ctx* c, const float* x, const int16_t* x16, int n, cudaStream_t st);
 int launch_stft_mel_pair(avld_ctx* c, int n, cudaStream_t st);

@@ -46,6 +46,7 @@ int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
     // PCM_16-quantised input only) lets the GEMM build it from a shared-memory span of samples instead (dftg.cu)
     if (c->cur_quantize && dftg_supported(c)) return launch_stft_mel_gen(c, c->cur_x, c->cur_x16, n, st);
     AVLD_TRY(launch_fold2(c, n, st));
+    if (dftf4_supported(c)) return launch_stft_mel_fold2_dual(c, n, st);   // opt-in (AVLD_DFT_DUAL=1), not yet run on hardware
     return launch_stft_mel_fold2(c, n, st);
   }
   if (c->dft_fold) {

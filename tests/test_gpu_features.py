@@ -1,5 +1,7 @@
 """GPU: log-mel features (map_detector_core.py:219-237, librosa 0.9.2 semantics) and latents against
 the reference-made fixtures and the numpy oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -176,3 +178,24 @@ def test_prequantised_operand_source_is_bit_identical(monkeypatch, standin_encod
     assert np.array_equal(np.isnan(a), np.isnan(b))
     assert np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
     assert np.isnan(a[5]).all() and np.isnan(a[6]).all() and np.isnan(a[7]).all() and not np.isnan(a[[0, 1, 2, 3, 4, 8, 9]]).any()
+
+
+@pytest.mark.skipif(os.environ.get("AVLD_TEST_DUAL", "0") in ("", "0"),
+                    reason="dftf4.cu (AVLD_DFT_DUAL=1) was written after round 1's GPU budget was spent and has not run on a "
+                           "B200 yet; set AVLD_TEST_DUAL=1 to bring it up")
+def test_dual_tile_kernel_matches_default(monkeypatch):
+    """AVLD_DFT_DUAL=1 (dftf4.cu: both tiles of the odd bin class per pass over its A columns): the accumulation order of
+    every output element is that of dftf3.cu, so the features must be bit-identical -- ragged batch, gate / clip chunks,
+    3 s and 5 s geometry."""
+    from amphibian_vae_latent_detector_b200 import synth
+    from amphibian_vae_latent_detector_b200.engine import Engine
+    for chunk_len, n, mb in ((144000, 37, 16), (240000, 7, 4)):
+        x, _ = synth.make_chunks(n, chunk_len, seed=31, special_every=9)
+        eng = Engine(0, chunk_len=chunk_len, max_batch=mb)
+        base, ok0, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+        monkeypatch.setenv("AVLD_DFT_DUAL", "1")
+        dual, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+        monkeypatch.delenv("AVLD_DFT_DUAL")
+        assert torch.equal(ok0, ok1)
+        assert torch.equal(dual, base)
+        eng.close()
