@@ -460,7 +460,8 @@ def main():
                                     "kind": "port", "stages_chunks_per_s": cpu_stages,
                                     "sample": f"{nc} chunks of the same workload, one chunk at a time (batch 1) as the "
                                               f"reference runs it: numpy float64 FFT + torch CPU encoder, "
-                                              f"{dt:.1f} s wall, host has {os.cpu_count()} logical cores"}
+                                              f"{dt:.1f} s wall, host has {os.cpu_count()} logical cores; one process, as the "
+                                              f"reference executes -- all cores at once (process pool): --impl reference"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
