@@ -20,6 +20,13 @@
 //   warps                0 = TMA producer (both CTAs), 1 = MMA issuer (leader), 2..9 = epilogue (both CTAs), as in dftf3
 // Accumulation order per output element is that of dftf3 (same K blocks, same three passes), the mel atomics see the same
 // values, so features are expected to be bit-identical to the default path.
+//
+// AVLD_DFT_DUAL=2 additionally shares B between the two CTA pairs of a 4-CTA cluster (template parameter kPairs = 2): the
+// pairs work on neighbouring frame pairs in step, every CTA loads only a quarter of a B tile (40 rows) and TMA multicast
+// delivers it to the CTA of the same parity in the other pair as well, so each SM pulls half of its B bytes from L2; a B
+// slot is free again once BOTH issuers have committed (b_empty counts kPairs commits, multicast to the whole cluster).
+// The instruction form is the one of CUTLASS' SM100_TMA_2SM_LOAD_MULTICAST (cta_group::2 + .multicast::cluster, barrier
+// address masked to the pair leader of every destination).  Same status: compiles, protocol modelled, never run.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -76,7 +83,20 @@ __device__ __forceinline__ int region_of(int g, int t, int part) {
 }
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// multicast TMA load of a CTA pair member: the box lands at the same offset in every CTA of `mask`, the bytes are counted
+// on the barrier at this offset of each destination's pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                                    uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+// kPairs CTA pairs per cluster (launched with a runtime cluster dimension of 2 * kPairs); tmB_* have 80-row boxes for
+// kPairs = 1 and 40-row boxes for kPairs = 2
+template <int kPairs>
+__global__ void __launch_bounds__(kThreads, 1)
 dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Dftf4Params P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
@@ -95,10 +115,19 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();                    // rank in the cluster
+  const uint32_t rank = crank & 1u;                            // rank in the CTA pair
+  const uint32_t cpair = crank >> 1;                           // which pair of the cluster
+  const uint32_t lead = crank & ~1u;                           // cluster rank of this pair's leader
   const bool leader = rank == 0;
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * cpair));
+  const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * kPairs)) - 1u);
   const int n_clusters = static_cast<int>(ncluster_id_x());
   const int cluster = static_cast<int>(cluster_id_x());
+  // frame pairs: the cluster takes kPairs neighbouring ones per round; a pair past the end still walks the schedule (its A
+  // rows are out of range = zero fill, its epilogue rows are invalid) because the B slots are shared with the other pair
+  const int first_fp = cluster * kPairs + static_cast<int>(cpair), fp_step = n_clusters * kPairs;
+  const int num_rounds = (P.num_pairs + kPairs - 1) / kPairs;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -111,7 +140,7 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int s = 0; s < kSB; ++s) {
       mbar_init(&b_full[s], 2);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], kPairs);      // one multicast commit per issuer of the cluster
     }
     for (int r = 0; r < kRegions; ++r) {
       mbar_init(&r_full[r], 1);
@@ -134,7 +163,7 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     uint32_t pa = 0, pb = 0;
     // L2 prefetch of this CTA's A rows, PF K blocks ahead of the loads
     constexpr int PF = 8;
-    int pf_pair = cluster, pf_g = 0, pf_kb = 0;
+    int pf_pair = first_fp, pf_g = 0, pf_kb = 0;
     auto pf_step = [&]() {
       if (pf_pair < P.num_pairs) {
         const int y = pf_pair * 2 * kBM + static_cast<int>(rank) * kBM;
@@ -146,12 +175,13 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         __syncwarp();
         if (++pf_kb == 2 * P.group[pf_g].kbp) {
           pf_kb = 0;
-          if (++pf_g == P.num_groups) { pf_g = 0; pf_pair += n_clusters; }
+          if (++pf_g == P.num_groups) { pf_g = 0; pf_pair += fp_step; }
         }
       }
     };
     for (int i = 0; i < PF; ++i) pf_step();
-    for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+    for (int round = cluster; round < num_rounds; round += n_clusters) {
+      const int pair = round * kPairs + static_cast<int>(cpair);
       const int ay = pair * 2 * kBM + static_cast<int>(rank) * kBM;
       for (int g = 0; g < P.num_groups; ++g) {
         const int a_col0 = P.group[g].a_col0, kbp = P.group[g].kbp, item0 = P.group[g].item0, tiles = P.group[g].tiles;
@@ -161,7 +191,7 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait(&a_empty[sa], pa ^ 1u, 100 + sa);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * kASlot);
-            else mbar_arrive_cluster(&a_full[sa], 0);
+            else mbar_arrive_cluster(&a_full[sa], lead);
             uint8_t* da = ring_a + sa * kASlot;
             tma_load_2d_pair(da, &tmA_hi, &a_full[sa], a_col0 + kb * kBK, ay);
             tma_load_2d_pair(da + kAHalf, &tmA_lo, &a_full[sa], a_col0 + kb * kBK, ay);
@@ -174,10 +204,21 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             mbar_wait(&b_empty[sb], pb ^ 1u, 110 + sb);
             if (elect_one()) {
               if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * kBSlot);
-              else mbar_arrive_cluster(&b_full[sb], 0);
+              else mbar_arrive_cluster(&b_full[sb], lead);
               uint8_t* db = ring_b + sb * kBSlot;
-              tma_load_2d_pair(db, &tmB_hi, &b_full[sb], bx, by);
-              tma_load_2d_pair(db + kBHalf, &tmB_lo, &b_full[sb], bx, by);
+              if (kPairs == 1) {
+                tma_load_2d_pair(db, &tmB_hi, &b_full[sb], bx, by);
+                tma_load_2d_pair(db + kBHalf, &tmB_lo, &b_full[sb], bx, by);
+              } else {                     // this CTA's share of the 80 rows, delivered to the same-parity CTA of every pair
+                constexpr int kShare = (kBN / 2) / kPairs;
+                const int sy = by + static_cast<int>(cpair) * kShare;
+                uint8_t* ds = db + static_cast<int>(cpair) * kShare * kSwz;
+                uint16_t mc = 0;
+#pragma unroll
+                for (int q = 0; q < kPairs; ++q) mc |= static_cast<uint16_t>(1u << (2 * q + static_cast<int>(rank)));
+                tma_load_2d_pair_mc(ds, &tmB_hi, &b_full[sb], bx, sy, mc);
+                tma_load_2d_pair_mc(ds + kBHalf, &tmB_lo, &b_full[sb], bx, sy, mc);
+              }
             }
             __syncwarp();
             if (++sb == kSB) { sb = 0; pb ^= 1u; }
@@ -192,7 +233,7 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       uint32_t used = 0;                       // bit r = parity of the completed uses of TMEM region r
-      for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+      for (int round = cluster; round < num_rounds; round += n_clusters) {
         for (int g = 0; g < P.num_groups; ++g) {
           const int kbp = P.group[g].kbp, tiles = P.group[g].tiles;
           for (int part = 0; part < 2; ++part) {
@@ -220,14 +261,14 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                     umma_f16_pair(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
                     umma_f16_pair(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
                   }
-                  umma_commit_pair(&b_empty[sb], 0x3);                       // B slot reusable in both CTAs
-                  if (kb == kbp - 1) umma_commit_pair(&r_full[r], 0x3);      // accumulator complete in both CTAs
+                  umma_commit_pair(&b_empty[sb], all_mask);                  // this pair is done with the B slot (all CTAs hear it)
+                  if (kb == kbp - 1) umma_commit_pair(&r_full[r], pair_mask);   // accumulator complete in both CTAs
                 }
                 __syncwarp();
                 if (kb == kbp - 1) used ^= 1u << r;
                 if (++sb == kSB) { sb = 0; pb ^= 1u; }
               }
-              if (elect_one()) umma_commit_pair(&a_empty[sa], 0x3);          // A slot reusable in both CTAs
+              if (elect_one()) umma_commit_pair(&a_empty[sa], pair_mask);    // A slot reusable in both CTAs
               __syncwarp();
               if (++sa == kSA) { sa = 0; pa ^= 1u; }
             }
@@ -247,11 +288,12 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         if (leader) mbar_arrive(&r_empty[r]);
-        else mbar_arrive_cluster(&r_empty[r], 0);
+        else mbar_arrive_cluster(&r_empty[r], lead);
       }
       used ^= 1u << r;
     };
-    for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
+    for (int round = cluster; round < num_rounds; round += n_clusters) {
+      const int pair = round * kPairs + static_cast<int>(cpair);
       const long long gr = static_cast<long long>(pair) * 2 * kBM + static_cast<long long>(rank) * kBM + row;
       const bool valid = gr < P.M_total;
       const float s2 = valid ? P.inv2[gr / P.F] : 0.f;
@@ -321,16 +363,52 @@ dftf4_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
 // Opt-in, and only for the item pattern the TMEM schedule above is written for: two tiles of one class, then two
 // single-tile classes (the three-level fold at n_fft = 2048 with the reference's mel band).
-bool dftf4_supported(const avld_ctx* c) {
+// AVLD_DFT_DUAL = 1: CTA pairs on their own; 2: B shared by multicast between the two pairs of a 4-CTA cluster.
+static int dftf4_mode(const avld_ctx* c) {
   const char* e = getenv("AVLD_DFT_DUAL");                        // read per pass, like AVLD_DFT_GEN: A/B in one process
-  const bool on = e != nullptr && atoi(e) != 0;
-  if (!on || !c->dft_fold2 || c->f2_levels != 3 || c->f2_items != 4) return false;
+  const int mode = e != nullptr ? atoi(e) : 0;
+  if (mode < 1 || mode > 2 || !c->dft_fold2 || c->f2_levels != 3 || c->f2_items != 4) return 0;
   const auto* it = c->f2_item;
-  return it[0].a_col0 == it[1].a_col0 && it[0].cls == it[1].cls && it[0].kbp == it[1].kbp && it[2].cls != it[0].cls &&
-         it[3].cls != it[2].cls && it[3].cls != it[0].cls && it[0].kbp >= 1 && it[2].kbp >= 1 && it[3].kbp >= 1;
+  const bool ok = it[0].a_col0 == it[1].a_col0 && it[0].cls == it[1].cls && it[0].kbp == it[1].kbp && it[2].cls != it[0].cls &&
+                  it[3].cls != it[2].cls && it[3].cls != it[0].cls && it[0].kbp >= 1 && it[2].kbp >= 1 && it[3].kbp >= 1;
+  if (!ok) return 0;
+  if (mode == 2 && c->sm_count % 4 != 0) return 1;
+  return mode;
+}
+
+bool dftf4_supported(const avld_ctx* c) { return dftf4_mode(c) != 0; }
+
+template <int kPairs>
+static int launch_dual(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const Dftf4Params& P, int sm_count, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    AVLD_CUDA(cudaFuncSetAttribute(dftf4_kernel<kPairs>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AVLD_CUDA(cudaFuncSetAttribute(dftf4_kernel<kPairs>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  constexpr int kCluster = 2 * kPairs;
+  const int rounds = (P.num_pairs + kPairs - 1) / kPairs;
+  const int grid = kCluster * std::min(rounds, sm_count / kCluster);
+  if (grid < kCluster) return AVLD_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  AVLD_CUDA(cudaLaunchKernelEx(&cfg, dftf4_kernel<kPairs>, a_hi, a_lo, b_hi, b_lo, P));
+  return AVLD_OK;
 }
 
 int launch_stft_mel_fold2_dual(avld_ctx* c, int n, cudaStream_t st) {
+  const int mode = dftf4_mode(c);
   Dftf4Params P{};
   const long long rows = static_cast<long long>(n) * c->F;
   const int m_tiles = static_cast<int>((rows + kBM - 1) / kBM);
@@ -352,20 +430,23 @@ int launch_stft_mel_fold2_dual(avld_ctx* c, int n, cudaStream_t st) {
   P.plane_stride = c->melpow_plane;
   P.F = c->F;
   P.n_mels = c->M;
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(dftf4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
+  // 40-row boxes of the DFT matrix for the multicast variant: encoded on first use only, so that the default path's
+  // context creation is untouched by this experiment
+  static const avld_ctx* tm_owner = nullptr;
+  static CUtensorMap tm_q_hi, tm_q_lo;
+  if (mode == 2 && tm_owner != c) {
+    const int Q = c->p.n_fft / 4;
+    const uint64_t rows3 = static_cast<uint64_t>(c->f2_items) * 2 * kBN;
+    AVLD_TRY(encode_tmap_2d(&tm_q_hi, c->d_B3hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kBN / 4, 128));
+    AVLD_TRY(encode_tmap_2d(&tm_q_lo, c->d_B3lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kBN / 4, 128));
+    tm_owner = c;
   }
   if (c->planes_dirty)     // only after a pass that failed between the GEMM and logmel_post_kernel (see dftf3.cu)
     AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(c->melpow_plane) * c->f2_classes * sizeof(float), st));
   c->planes_dirty = true;
-  const int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
-  if (grid < 2) return AVLD_OK;
   LaunchScope ls(c, ST_STFT_MEL, st);
-  dftf4_kernel<<<grid, kThreads, kSmemBytes, st>>>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B3_hi, c->tm_B3_lo, P);
-  AVLD_CUDA(cudaGetLastError());
-  return AVLD_OK;
+  if (mode == 2) return launch_dual<2>(c->tm_A2_hi, c->tm_A2_lo, tm_q_hi, tm_q_lo, P, c->sm_count, st);
+  return launch_dual<1>(c->tm_A2_hi, c->tm_A2_lo, c->tm_B3_hi, c->tm_B3_lo, P, c->sm_count, st);
 }
 
 }  // namespace avld

@@ -193,9 +193,10 @@ def test_dual_tile_kernel_matches_default(monkeypatch):
         x, _ = synth.make_chunks(n, chunk_len, seed=31, special_every=9)
         eng = Engine(0, chunk_len=chunk_len, max_batch=mb)
         base, ok0, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-        monkeypatch.setenv("AVLD_DFT_DUAL", "1")
-        dual, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-        monkeypatch.delenv("AVLD_DFT_DUAL")
-        assert torch.equal(ok0, ok1)
-        assert torch.equal(dual, base)
+        for mode in os.environ.get("AVLD_TEST_DUAL_MODES", "1,2").split(","):     # 1: CTA pairs, 2: + B multicast (4-CTA clusters)
+            monkeypatch.setenv("AVLD_DFT_DUAL", mode)
+            dual, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
+            monkeypatch.delenv("AVLD_DFT_DUAL")
+            assert torch.equal(ok0, ok1), mode
+            assert torch.equal(dual, base), mode
         eng.close()
