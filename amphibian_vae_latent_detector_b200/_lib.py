@@ -7,10 +7,12 @@ fails, an exception is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libavld.so"
+# AVLD_LIB_PATH selects another build of the same library (tools/ point it at libavld_bringup.so); it is never a fallback
+LIB_PATH = Path(os.environ["AVLD_LIB_PATH"]).resolve() if os.environ.get("AVLD_LIB_PATH") else HERE / "libavld.so"
 
 OK = 0
 ERROR_NAMES = {-1: "AVLD_ERR_INVALID", -2: "AVLD_ERR_CUDA", -3: "AVLD_ERR_UNSUPPORTED", -4: "AVLD_ERR_STATE",

@@ -21,7 +21,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libavld.so"
 OBJ = HERE / "build"
 
-SOURCES = ["ctx.cu", "rms.cu", "gemm3.cu", "dftf2.cu", "fold2.cu", "dftf3.cu", "dftf4.cu", "dftg.cu", "logmel.cu", "convh.cu", "encoder.cu", "radial.cu", "map.cu", "api.cu"]
+SOURCES = ["ctx.cu", "rms.cu", "gemm3.cu", "fold3.cu", "dftf3.cu", "logmel.cu", "convh.cu", "encoder.cu", "radial.cu", "map.cu", "api.cu"]
 EXTRA_FLAGS = {"rms.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -41,15 +41,22 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> Path:
+    """``bringup=True`` builds ``libavld_bringup.so`` with -DAVLD_BRINGUP (kernel probes and cycle counters driven by
+    AVLD_DBG; used by tools/ only -- the product library has none of it compiled in)."""
+    global LIB, OBJ
     nvcc = _nvcc()
+    if bringup:
+        LIB, OBJ = HERE / "libavld_bringup.so", HERE / "build_bringup"
+    else:
+        LIB, OBJ = HERE / "libavld.so", HERE / "build"
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "avld.h", Path(__file__)]
     jobs = []
     for src in SOURCES:
         obj = OBJ / (src + ".o")
         if force or _stale(obj, [CSRC / src] + headers):
-            cmd = [nvcc, *COMMON, *EXTRA_FLAGS.get(src, []), "-c", str(CSRC / src), "-o", str(obj)]
+            cmd = [nvcc, *COMMON, *EXTRA_FLAGS.get(src, []), *(["-DAVLD_BRINGUP"] if bringup else []), "-c", str(CSRC / src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -77,5 +84,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--bringup", action="store_true", help="build libavld_bringup.so (-DAVLD_BRINGUP) for tools/")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, bringup=a.bringup))

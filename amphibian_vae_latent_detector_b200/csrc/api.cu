@@ -23,7 +23,7 @@ static int encode_pass(avld_ctx* c, const float* x, const int16_t* x16, float* m
 
 extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, int64_t n, float target_rms,
                            float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
@@ -39,7 +39,7 @@ extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, 
 
 extern "C" int avld_encode_pcm16(avld_ctx* c, const int16_t* pcm, float* mu, uint8_t* ok, int64_t n, float target_rms,
                                  float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(pcm && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
@@ -56,12 +56,11 @@ extern "C" int avld_encode_pcm16(avld_ctx* c, const int16_t* pcm, float* mu, uin
 static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_bytes, int64_t n, int quantize_pcm16,
                                    const float* centroid, const double* thr, const int32_t* priority_rank, int32_t K,
                                    int32_t* pred_host, float* best_host, float* mu_host, uint8_t* ok_host) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0 && K >= 1 && K <= 64, AVLD_ERR_INVALID, "bad n / K");
   AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
-  AVLD_CUDA(cudaSetDevice(c->device));
   const int D = c->latent_dim;
   const size_t xbytes = static_cast<size_t>(c->max_batch) * c->L * sizeof(float);
   for (int b = 0; b < 2; ++b)
@@ -191,7 +190,8 @@ extern "C" int avld_encode_detect_host_pcm16(avld_ctx* c, const int16_t* pcm_hos
 // ------------------------------------------------------------------------------------------------
 extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float* C, int64_t M, int32_t N, int32_t K,
                              int32_t mode, void* stream) {
-  AVLD_CHECK(c && A && B && C, AVLD_ERR_INVALID, "NULL argument");
+  AVLD_ENTER(c);
+  AVLD_CHECK(A && B && C, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(M >= 1 && N >= 16 && N % 16 == 0 && K >= 64 && K % 64 == 0, AVLD_ERR_INVALID, "need N %% 16 == 0 and K %% 64 == 0");
   AVLD_CHECK(mode == 0 || mode == 1, AVLD_ERR_INVALID, "mode must be 0 or 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -231,7 +231,7 @@ extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float*
     P.out_f32 = C;
     P.ldc = N;
     LaunchScope ls(c, ST_DENSE_GEMM, st);
-    rc = run_gemm3(bn, 128, EPI_PLAIN, ta_hi, ta_lo, tb_hi, tb_lo, P, c->sm_count, st);
+    rc = run_gemm3(c, bn, 128, EPI_PLAIN, ta_hi, ta_lo, tb_hi, tb_lo, P, st);
     if (rc) break;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {

@@ -329,15 +329,12 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 }
 
 template <int BN, int CBLK>
-static int launch_one(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                      ConvhParams P, int sm_count, cudaStream_t st) {
+static int launch_one(avld_ctx* c, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                      const CUtensorMap& w_lo, ConvhParams P, cudaStream_t st) {
+  const int sm_count = c->sm_count;
   using Cfg = ConvhCfg<BN, CBLK>;
-  static bool configured = false;
   auto kfn = convh_kernel<BN, CBLK>;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(kfn), Cfg::SMEM_BYTES));
   P.resident = (P.cblocks == 1 && Cfg::RES_BYTES <= 80 * 1024 && Cfg::HSTAGES_RES >= 2) ? 1 : 0;
   if (!P.resident && Cfg::WSTAGES_STR < 2) {
     set_error("convh: tile does not fit shared memory (BN=%d, CBLK=%d)", BN, CBLK);
@@ -362,8 +359,8 @@ bool convh_supported(int c_in, int c_out, int ksize, int w) {
   return ksize == 3 && (c_in == 32 || c_in % 64 == 0) && (c_out == 64 || c_out == 128) && (w % kTW == 0);
 }
 
-int launch_convh(const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
-                 __nv_bfloat16* out_lo, int sm_count, cudaStream_t st) {
+int launch_convh(avld_ctx* c, const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
+                 __nv_bfloat16* out_lo, cudaStream_t st) {
   ConvhParams P{};
   P.tiles_w = L.in_w / kTW;
   P.tiles_h = (L.in_h + kTH - 1) / kTH;
@@ -376,10 +373,10 @@ int launch_convh(const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& 
   P.dbg = dbg_env;
   P.out_hi = out_hi;
   P.out_lo = out_lo;
-  if (L.c_out == 64 && L.cblk == 32) return launch_one<64, 32>(a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, sm_count, st);
-  if (L.c_out == 64 && L.cblk == 64) return launch_one<64, 64>(a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, sm_count, st);
-  if (L.c_out == 128 && L.cblk == 32) return launch_one<128, 32>(a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, sm_count, st);
-  if (L.c_out == 128 && L.cblk == 64) return launch_one<128, 64>(a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, sm_count, st);
+  if (L.c_out == 64 && L.cblk == 32) return launch_one<64, 32>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
+  if (L.c_out == 64 && L.cblk == 64) return launch_one<64, 64>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
+  if (L.c_out == 128 && L.cblk == 32) return launch_one<128, 32>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
+  if (L.c_out == 128 && L.cblk == 64) return launch_one<128, 64>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
   set_error("convh: unsupported shape C_out=%d cblk=%d", L.c_out, L.cblk);
   return AVLD_ERR_UNSUPPORTED;
 }

@@ -46,6 +46,14 @@ LaunchScope::~LaunchScope() {
   if (stop) cudaEventRecord(stop, st);
 }
 
+int ensure_dyn_smem(avld_ctx* c, const void* kernel, int bytes) {
+  for (const void* k : c->smem_configured)
+    if (k == kernel) return AVLD_OK;
+  AVLD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  c->smem_configured.push_back(kernel);
+  return AVLD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA descriptors
 // ------------------------------------------------------------------------------------------------
@@ -266,16 +274,15 @@ static int build_ctx(avld_ctx* c) {
   const avld_params& p = c->p;
   AVLD_CHECK(p.sr > 0 && p.n_fft >= 64 && p.hop > 0 && p.n_mels > 0 && p.target_frames > 0 && p.chunk_len > 0,
              AVLD_ERR_INVALID, "non-positive feature parameter");
-  AVLD_CHECK(p.n_fft % 64 == 0, AVLD_ERR_UNSUPPORTED, "n_fft must be a multiple of 64 (got %d)", p.n_fft);
-  AVLD_CHECK(p.hop % 64 == 0, AVLD_ERR_UNSUPPORTED, "hop_length must be a multiple of 64 (got %d)", p.hop);
+  AVLD_CHECK(p.n_fft % 512 == 0, AVLD_ERR_UNSUPPORTED,
+             "n_fft must be a multiple of 512 for the folded STFT GEMM (got %d)", p.n_fft);
+  AVLD_CHECK(p.hop % 8 == 0, AVLD_ERR_UNSUPPORTED, "hop_length must be a multiple of 8 (got %d)", p.hop);
   AVLD_CHECK(p.n_mels <= 256, AVLD_ERR_UNSUPPORTED, "n_mels > 256");
   AVLD_CHECK(p.amin > 0.f && p.top_db >= 0.f, AVLD_ERR_INVALID, "amin must be > 0 and top_db >= 0");
   AVLD_CHECK(p.max_batch >= 1, AVLD_ERR_INVALID, "max_batch must be >= 1");
+  AVLD_CHECK(c->sm_count % 2 == 0, AVLD_ERR_UNSUPPORTED, "the STFT GEMM runs on CTA pairs: odd SM count %d", c->sm_count);
   c->L = p.chunk_len;
   c->F = 1 + p.chunk_len / p.hop;
-  c->R = (p.chunk_len + p.n_fft + p.hop - 1) / p.hop;
-  c->hpb = p.hop / 64;
-  c->kblocks = p.n_fft / 64;
   c->T = p.target_frames;
   c->M = p.n_mels;
   c->max_batch = p.max_batch;
@@ -315,251 +322,125 @@ static int build_ctx(avld_ctx* c) {
   std::vector<float> w0, w1;
   int bin_lo, bin_hi;
   AVLD_TRY(mel_taps_host(p, first, w0, w1, &bin_lo, &bin_hi));
-  c->bin_lo = bin_lo;
-  const int nbins = bin_hi - bin_lo + 1;
-  {
-    const char* mode = getenv("AVLD_DFT_MODE");          // "direct" selects the un-folded K = n_fft GEMM (A/B comparisons)
-    c->dft_fold = !(mode != nullptr && strcmp(mode, "direct") == 0) && (p.n_fft % 128 == 0);
-    c->dft_pair = !(mode != nullptr && strcmp(mode, "fold1") == 0);
-    // default: the twice-folded kernel; "fold" keeps the once-folded CTA-pair kernel (A/B comparisons)
-    const bool two = mode != nullptr && strcmp(mode, "fold2") == 0;
-    c->dft_fold2 = c->dft_fold && (mode == nullptr || two) && (p.n_fft % 512 == 0) && (c->sm_count % 2 == 0);
-    c->f2_levels = two ? 2 : 3;
-    if (c->dft_fold2) {
-      // the folded kernel keeps one 16-byte tap record per accumulator column of every work item in shared memory and
-      // has room for 8 items of 160 bins; other geometries (many more FFT bins) use the once-folded kernel
-      int items = 0;
-      const int mods[3][2] = {{2, 1}, {c->f2_levels == 3 ? 4 : 2, 0}, {4, 2}};
-      for (int ci = 0; ci < (c->f2_levels == 3 ? 3 : 2); ++ci) {
-        int nb = 0;
-        for (int b = bin_lo; b <= bin_hi; ++b) nb += (b % mods[ci][0]) == mods[ci][1];
-        items += (nb + 159) / 160;
-      }
-      if (items > 8 || static_cast<size_t>(items) * 160 * sizeof(MelTap) > 12288 - 512) c->dft_fold2 = 0;
-    }
-  }
-  c->n_tiles2 = (nbins + 255) / 256;
-  c->last_tile_bins = (nbins - (c->n_tiles2 - 1) * 256) <= 128 ? 128 : 256;
-  c->nbins_pad = c->dft_fold ? c->n_tiles2 * 256 : (nbins + 127) / 128 * 128;
-  c->n_tiles_n = c->nbins_pad / 128;
-  c->ncols = 2 * c->nbins_pad;
-  AVLD_CHECK(static_cast<size_t>(c->nbins_pad) * sizeof(MelTap) <= 14000, AVLD_ERR_UNSUPPORTED, "too many FFT bins");
-  std::vector<MelTap> taps(c->nbins_pad);
-  int run_first = 0;
-  for (int i = 0; i < c->nbins_pad; ++i) {
-    const int b = bin_lo + i;
-    if (b <= bin_hi && first[b] >= 0) {
-      run_first = first[b];
-      taps[i] = {first[b], w0[b], w1[b], 0};
-    } else {
-      taps[i] = {run_first, 0.f, 0.f, 0};
-    }
-  }
-  AVLD_TRY(dev_alloc(&c->d_taps, taps.size()));
-  AVLD_CUDA(cudaMemcpy(c->d_taps, taps.data(), taps.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
 
-  // ---- windowed DFT matrix B[col][k]; N tile t holds Re of bins [128t, 128t+128) then Im of the same bins
-  if (c->dft_fold) {
-    const int nf = p.n_fft, half = nf / 2;
-    const double bscale = std::ldexp(1.0, c->dft_scale_log2);
-    const size_t rows2 = static_cast<size_t>(c->n_tiles2) * 512;
-    std::vector<__half> hi(rows2 * half), lo(rows2 * half);
-    for (size_t r = 0; r < rows2; ++r) {
-      const int tile = static_cast<int>(r / 512), part = static_cast<int>((r % 512) / 256), j = static_cast<int>(r % 256);
-      const int bin = bin_lo + tile * 256 + j;
-      for (int col = 0; col < half; ++col) {
-        const int k = col + 1;                                   // taps 1 .. N/2
-        double v = 0.0;
-        if (bin <= bin_hi) {
-          const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf);   // scipy get_window('hann', n, fftbins=True)
-          const long long ph = (static_cast<long long>(k) * bin) % nf;
-          const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
-          v = bscale * w * (part == 0 ? std::cos(ang) : -std::sin(ang));
-        }
-        const __half h = __float2half_rn(static_cast<float>(v));
-        hi[r * half + col] = h;
-        lo[r * half + col] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
-      }
+  // ---- folded operands: three bin classes, each covered by work items of 160 bins; item rows of the DFT matrix B3 =
+  // 160 cos rows then 160 sin rows, Q = N/4 taps wide (the classes = 0 / 2 mod 4 use the first N/8), no window (it is
+  // applied to the frames by fold3_kernel), scaled by 2^dft_scale_log2 to keep the lo parts out of the fp16 subnormals
+  const int nf = p.n_fft, half = nf / 2, Q = nf / 4, kItem = 160;
+  const double bscale = std::ldexp(1.0, c->dft_scale_log2);
+  struct ClassDef { int mod, rem, a_col0, K, edge_im; };
+  const ClassDef classes[3] = {{2, 1, 0, Q, 1},                 // odd bins: K = N/4, edge O[N/4] sin(pi b / 2) -> Im
+                               {4, 0, half, Q / 2, 0},          // b = 0 mod 4: K = N/8, edge P[N/8] cos(pi b / 4) -> Re
+                               {4, 2, half + Q, Q / 2, 1}};     // b = 2 mod 4: K = N/8, edge R[N/8] sin(pi b / 4) -> Im
+  c->f2_classes = 3;
+  std::vector<std::vector<int>> item_bins;
+  c->f2_items = 0;
+  for (int ci = 0; ci < 3; ++ci) {
+    std::vector<int> bins;
+    for (int b = bin_lo; b <= bin_hi; ++b)
+      if (b % classes[ci].mod == classes[ci].rem) bins.push_back(b);
+    for (size_t o = 0; o < bins.size(); o += kItem) {
+      AVLD_CHECK(c->f2_items < avld_ctx::kMaxItems, AVLD_ERR_UNSUPPORTED,
+                 "too many FFT bins carry mel weight for the STFT kernel (%d bins, limit %d)", bin_hi - bin_lo + 1,
+                 avld_ctx::kMaxItems * kItem);
+      c->f2_item[c->f2_items++] = {classes[ci].a_col0, classes[ci].K / 64, ci, classes[ci].edge_im};
+      item_bins.emplace_back(bins.begin() + o, bins.begin() + std::min(bins.size(), o + kItem));
     }
-    AVLD_TRY(dev_alloc(&c->d_B2hi, hi.size()));
-    AVLD_TRY(dev_alloc(&c->d_B2lo, lo.size()));
-    AVLD_CUDA(cudaMemcpy(c->d_B2hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
-    AVLD_CUDA(cudaMemcpy(c->d_B2lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
-    {
-      const char* bk = getenv("AVLD_FOLD_BK");
-      c->fold_bk = (bk != nullptr && atoi(bk) == 32) ? 32 : 64;
-    }
-    const uint32_t fbk = static_cast<uint32_t>(c->fold_bk), fsw = fbk * 2;
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 256, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_hi, c->d_B2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 128, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B2h_lo, c->d_B2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, half, rows2, static_cast<uint64_t>(half) * 2, fbk, 128, fsw));
-    const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 256;
-    AVLD_TRY(dev_alloc(&c->d_A2hi, frames * nf));
-    AVLD_TRY(dev_alloc(&c->d_A2lo, frames * nf));
-    AVLD_CUDA(cudaMemset(c->d_A2hi, 0, frames * nf * 2));
-    AVLD_CUDA(cudaMemset(c->d_A2lo, 0, frames * nf * 2));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, fbk, 128, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, fbk, 128, fsw));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A2pf_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 256, 128, 0));
-    AVLD_TRY(dev_alloc(&c->d_chunk_par, c->max_batch));
-    if (c->dft_fold2) {
-      // ---- folded operands: bin classes, each covered by work items of 160 bins; item rows = 160 cos then 160 sin
-      const int Q = nf / 4, kItem = 160;
-      struct ClassDef { int mod, rem, a_col0, K, edge_im; };
-      std::vector<ClassDef> classes;
-      if (c->f2_levels == 3) {
-        classes = {{2, 1, 0, Q, 1},                       // odd bins: K = N/4, edge O[N/4] sin(pi b / 2) -> Im
-                   {4, 0, nf / 2, Q / 2, 0},              // b = 0 mod 4: K = N/8, edge P[N/8] cos(pi b / 4) -> Re
-                   {4, 2, nf / 2 + Q, Q / 2, 1}};         // b = 2 mod 4: K = N/8, edge R[N/8] sin(pi b / 4) -> Im
-      } else {
-        classes = {{2, 0, 0, Q, 0},                       // even bins: edge E[N/4] cos(pi b / 2) -> Re
-                   {2, 1, nf / 2, Q, 1}};                 // odd bins:  edge O[N/4] sin(pi b / 2) -> Im
-      }
-      c->f2_classes = static_cast<int>(classes.size());
-      struct ItemBins { std::vector<int> bins; };
-      std::vector<ItemBins> item_bins;
-      c->f2_items = 0;
-      for (size_t ci = 0; ci < classes.size(); ++ci) {
-        std::vector<int> bins;
-        for (int b = bin_lo; b <= bin_hi; ++b)
-          if (b % classes[ci].mod == classes[ci].rem) bins.push_back(b);
-        for (size_t o = 0; o < bins.size(); o += kItem) {
-          AVLD_CHECK(c->f2_items < 8, AVLD_ERR_UNSUPPORTED, "too many FFT bins for the folded STFT kernel");
-          c->f2_item[c->f2_items++] = {classes[ci].a_col0, classes[ci].K / 64, static_cast<int>(ci), classes[ci].edge_im};
-          item_bins.push_back({std::vector<int>(bins.begin() + o, bins.begin() + std::min(bins.size(), o + kItem))});
-        }
-      }
-      const size_t rows3 = static_cast<size_t>(c->f2_items) * 2 * kItem;
-      std::vector<__half> h3(rows3 * Q), l3(rows3 * Q);
-      std::vector<MelTap> taps3(static_cast<size_t>(c->f2_items) * kItem);
-      for (int it = 0; it < c->f2_items; ++it) {
-        const ClassDef& cd = classes[c->f2_item[it].cls];
-        const std::vector<int>& bins = item_bins[it].bins;
-        int run = 0;
-        for (size_t u = 0; u < bins.size(); ++u)             // `first` must be monotone from the item's first column on
-          if (first[bins[u]] >= 0) { run = first[bins[u]]; break; }
-        for (int j = 0; j < kItem; ++j) {
-          const bool have = j < static_cast<int>(bins.size());
-          const int bin = have ? bins[j] : -1;
-          // epilogue taps: mel filter pair of the bin and the coefficient of the class's self-paired tap:
-          // cos(pi b / 2), sin(pi b / 2), cos(pi b / 4) or sin(pi b / 4) at the class's bins, all +-1
-          MelTap tp{run, 0.f, 0.f, 0};
-          if (have && first[bin] >= 0) {
-            run = first[bin];
-            const double ang = M_PI * bin / (cd.K == Q ? 2.0 : 4.0);
-            const double cf = cd.edge_im ? std::sin(ang) : std::cos(ang);
-            const float coef = static_cast<float>(bscale * std::round(cf));
-            int32_t bits;
-            memcpy(&bits, &coef, 4);
-            tp = {first[bin], w0[bin], w1[bin], bits};
-          }
-          taps3[static_cast<size_t>(it) * kItem + j] = tp;
-          for (int part = 0; part < 2; ++part) {
-            const size_t r = (static_cast<size_t>(it) * 2 + part) * kItem + j;
-            for (int k = 0; k < Q; ++k) {
-              double v = 0.0;
-              if (have && k < cd.K) {
-                const long long ph = (static_cast<long long>(k) * bin) % nf;
-                const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
-                v = bscale * (part == 0 ? std::cos(ang) : std::sin(ang));
-              }
-              const __half h = __float2half_rn(static_cast<float>(v));
-              h3[r * Q + k] = h;
-              l3[r * Q + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
-            }
-          }
-        }
-      }
-      AVLD_TRY(dev_alloc(&c->d_B3hi, h3.size()));
-      AVLD_TRY(dev_alloc(&c->d_B3lo, l3.size()));
-      AVLD_CUDA(cudaMemcpy(c->d_B3hi, h3.data(), h3.size() * 2, cudaMemcpyHostToDevice));
-      AVLD_CUDA(cudaMemcpy(c->d_B3lo, l3.data(), l3.size() * 2, cudaMemcpyHostToDevice));
-      AVLD_TRY(encode_tmap_2d(&c->tm_B3_hi, c->d_B3hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
-      AVLD_TRY(encode_tmap_2d(&c->tm_B3_lo, c->d_B3lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
-      AVLD_TRY(dev_alloc(&c->d_taps3, taps3.size()));
-      AVLD_CUDA(cudaMemcpy(c->d_taps3, taps3.data(), taps3.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
-      // periodic Hann [half + 1], then (three-level fold) the same values regrouped per 8-tap block kb of fold3_kernel as
-      // nine float4 planes [9][E / 8]: w[k] (2), w[H-k] (2), w[Q-k] (2), w[Q+k] (2) for k = 8 kb + 0..7, and (w[Q-k], w[Q+k]) at
-      // k = 8 kb + 8 -- one coalesced 16-byte load per plane instead of 34 strided scalar loads per thread
-      const int wt_off = (half + 1 + 3) & ~3, wt_blocks = nf / 64;
-      std::vector<float> win(c->f2_levels == 3 ? wt_off + 9 * wt_blocks * 4 : half + 1, 0.f);
-      for (int k = 0; k <= half; ++k) win[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf));
-      if (c->f2_levels == 3) {
-        const int Q4 = nf / 4;
-        for (int kb = 0; kb < wt_blocks; ++kb) {
-          auto cell = [&](int plane, int j) -> float& { return win[wt_off + (plane * wt_blocks + kb) * 4 + j]; };
-          for (int q = 0; q < 8; ++q) {
-            const int k = kb * 8 + q;
-            cell(0 + q / 4, q % 4) = win[k];
-            cell(2 + q / 4, q % 4) = win[half - k];
-            cell(4 + q / 4, q % 4) = win[Q4 - k];
-            cell(6 + q / 4, q % 4) = win[Q4 + k];
-          }
-          cell(8, 0) = win[Q4 - (kb * 8 + 8)];
-          cell(8, 1) = win[Q4 + (kb * 8 + 8)];
-        }
-      }
-      AVLD_TRY(dev_alloc(&c->d_win, win.size()));
-      AVLD_CUDA(cudaMemcpy(c->d_win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
-      if (c->f2_levels == 3 && std::getenv("AVLD_NO_Q16") == nullptr)
-        AVLD_TRY(dev_alloc(&c->d_q16, static_cast<size_t>(p.max_batch) * c->L + 64));
-      AVLD_TRY(dev_alloc(&c->d_edge, frames));
-      AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float4)));
-      if (fbk != 64) {   // the fold2 kernel loads 64-tap boxes of A
-        AVLD_TRY(encode_tmap_2d(&c->tm_A2_hi, c->d_A2hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
-        AVLD_TRY(encode_tmap_2d(&c->tm_A2_lo, c->d_A2lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, frames, static_cast<uint64_t>(nf) * 2, 64, 128, 128));
-      }
-    }
-  } else {
-    const int nf = p.n_fft;
-    std::vector<double> win(nf), ct(nf), stab(nf);
-    for (int k = 0; k < nf; ++k) {
-      win[k] = 0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf);  // scipy get_window('hann', n, fftbins=True)
-      ct[k] = std::cos(2.0 * M_PI * k / nf);
-      stab[k] = std::sin(2.0 * M_PI * k / nf);
-    }
-    std::vector<__half> hi(static_cast<size_t>(c->ncols) * nf);
-    std::vector<__half> lo(hi.size());
-    const double bscale = std::ldexp(1.0, c->dft_scale_log2);   // keeps the lo parts out of the fp16 subnormals
-    for (int col = 0; col < c->ncols; ++col) {
-      const int tile = col / 256, part = (col % 256) / 128, j = col % 128;
-      const int bin = bin_lo + tile * 128 + j;
-      for (int k = 0; k < nf; ++k) {
-        double v = 0.0;
-        if (bin <= nf / 2) {
-          const int ph = static_cast<int>((static_cast<long long>(k) * bin) % nf);
-          v = bscale * win[k] * (part == 0 ? ct[ph] : -stab[ph]);
-        }
-        const float vf = static_cast<float>(v);
-        const __half h = __float2half_rn(vf);
-        hi[static_cast<size_t>(col) * nf + k] = h;
-        lo[static_cast<size_t>(col) * nf + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
-      }
-    }
-    AVLD_TRY(dev_alloc(&c->d_Bhi, hi.size()));
-    AVLD_TRY(dev_alloc(&c->d_Blo, lo.size()));
-    AVLD_CUDA(cudaMemcpy(c->d_Bhi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
-    AVLD_CUDA(cudaMemcpy(c->d_Blo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B_hi, c->d_Bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
-    AVLD_TRY(encode_tmap_2d(&c->tm_B_lo, c->d_Blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, nf, c->ncols, static_cast<uint64_t>(nf) * 2, 64, 256, 128));
   }
+  const size_t rows3 = static_cast<size_t>(c->f2_items) * 2 * kItem;
+  std::vector<__half> h3(rows3 * Q), l3(rows3 * Q);
+  std::vector<MelTap> taps3(static_cast<size_t>(c->f2_items) * kItem);
+  for (int it = 0; it < c->f2_items; ++it) {
+    const ClassDef& cd = classes[c->f2_item[it].cls];
+    const std::vector<int>& bins = item_bins[it];
+    int run = 0;
+    for (size_t u = 0; u < bins.size(); ++u)             // `first` must be monotone from the item's first column on
+      if (first[bins[u]] >= 0) { run = first[bins[u]]; break; }
+    for (int j = 0; j < kItem; ++j) {
+      const bool have = j < static_cast<int>(bins.size());
+      const int bin = have ? bins[j] : -1;
+      // epilogue taps: mel filter pair of the bin and the coefficient of the class's self-paired tap:
+      // cos(pi b / 2), sin(pi b / 2), cos(pi b / 4) or sin(pi b / 4) at the class's bins, all +-1
+      MelTap tp{run, 0.f, 0.f, 0};
+      if (have && first[bin] >= 0) {
+        run = first[bin];
+        const double ang = M_PI * bin / (cd.K == Q ? 2.0 : 4.0);
+        const double cf = cd.edge_im ? std::sin(ang) : std::cos(ang);
+        const float coef = static_cast<float>(bscale * std::round(cf));
+        int32_t bits;
+        memcpy(&bits, &coef, 4);
+        tp = {first[bin], w0[bin], w1[bin], bits};
+      }
+      taps3[static_cast<size_t>(it) * kItem + j] = tp;
+      for (int part = 0; part < 2; ++part) {
+        const size_t r = (static_cast<size_t>(it) * 2 + part) * kItem + j;
+        for (int k = 0; k < Q; ++k) {
+          double v = 0.0;
+          if (have && k < cd.K) {
+            const long long ph = (static_cast<long long>(k) * bin) % nf;
+            const double ang = 2.0 * M_PI * static_cast<double>(ph) / nf;
+            v = bscale * (part == 0 ? std::cos(ang) : std::sin(ang));
+          }
+          const __half h = __float2half_rn(static_cast<float>(v));
+          h3[r * Q + k] = h;
+          l3[r * Q + k] = __float2half_rn(static_cast<float>(v - static_cast<double>(__half2float(h))));
+        }
+      }
+    }
+  }
+  AVLD_TRY(dev_alloc(&c->d_B3hi, h3.size()));
+  AVLD_TRY(dev_alloc(&c->d_B3lo, l3.size()));
+  AVLD_CUDA(cudaMemcpy(c->d_B3hi, h3.data(), h3.size() * 2, cudaMemcpyHostToDevice));
+  AVLD_CUDA(cudaMemcpy(c->d_B3lo, l3.data(), l3.size() * 2, cudaMemcpyHostToDevice));
+  AVLD_TRY(encode_tmap_2d(&c->tm_B3_hi, c->d_B3hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
+  AVLD_TRY(encode_tmap_2d(&c->tm_B3_lo, c->d_B3lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, Q, rows3, static_cast<uint64_t>(Q) * 2, 64, kItem / 2, 128));
+  AVLD_TRY(dev_alloc(&c->d_taps3, taps3.size()));
+  AVLD_CUDA(cudaMemcpy(c->d_taps3, taps3.data(), taps3.size() * sizeof(MelTap), cudaMemcpyHostToDevice));
+
+  // ---- folded frames A3, tile-major (fold3.cu): [tile of 128 frames][K block][hi | lo][128][64] fp16; one (tile, K block)
+  // = 256 rows of 128 bytes = one 32 KB box of the tensor map below
+  c->a3_kblocks = nf / 64;
+  const size_t frames = static_cast<size_t>(c->max_batch) * c->F + 256;
+  c->a3_tiles = (frames + 127) / 128;
+  const size_t a3_rows = c->a3_tiles * c->a3_kblocks * 256;
+  AVLD_CHECK(a3_rows < (1ull << 31), AVLD_ERR_UNSUPPORTED, "max_batch too large for the folded operand's tensor map");
+  AVLD_TRY(dev_alloc(&c->d_A3, a3_rows * 64));
+  AVLD_CUDA(cudaMemset(c->d_A3, 0, a3_rows * 64 * 2));
+  AVLD_TRY(encode_tmap_2d(&c->tm_A3, c->d_A3, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 64, a3_rows, 128, 64, 256, 128));
+  AVLD_TRY(dev_alloc(&c->d_chunk_par, c->max_batch));
+  // periodic Hann [half + 1], then the same values regrouped per 8-tap block kb of fold3_kernel as nine float4 planes
+  // [9][E / 8]: w[k] (2), w[H-k] (2), w[Q-k] (2), w[Q+k] (2) for k = 8 kb + 0..7, and (w[Q-k], w[Q+k]) at k = 8 kb + 8 --
+  // one coalesced 16-byte load per plane instead of 34 strided scalar loads per thread
+  {
+    const int wt_off = (half + 1 + 3) & ~3, wt_blocks = nf / 64;
+    std::vector<float> win(wt_off + 9 * wt_blocks * 4, 0.f);
+    for (int k = 0; k <= half; ++k) win[k] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * M_PI * k / nf));   // scipy get_window('hann', n, fftbins=True)
+    for (int kb = 0; kb < wt_blocks; ++kb) {
+      auto cell = [&](int plane, int j) -> float& { return win[wt_off + (plane * wt_blocks + kb) * 4 + j]; };
+      for (int q = 0; q < 8; ++q) {
+        const int k = kb * 8 + q;
+        cell(0 + q / 4, q % 4) = win[k];
+        cell(2 + q / 4, q % 4) = win[half - k];
+        cell(4 + q / 4, q % 4) = win[Q - k];
+        cell(6 + q / 4, q % 4) = win[Q + k];
+      }
+      cell(8, 0) = win[Q - (kb * 8 + 8)];
+      cell(8, 1) = win[Q + (kb * 8 + 8)];
+    }
+    AVLD_TRY(dev_alloc(&c->d_win, win.size()));
+    AVLD_CUDA(cudaMemcpy(c->d_win, win.data(), win.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // AVLD_NO_Q16 (read here, once): PCM_16 round-trip passes then re-normalise every sample inside fold3_kernel instead of
+  // reading prep_kernel's integers -- the same bits by construction, kept selectable so that a test can prove it
+  if (std::getenv("AVLD_NO_Q16") == nullptr) AVLD_TRY(dev_alloc(&c->d_q16, static_cast<size_t>(p.max_batch) * c->L + 64));
+  AVLD_TRY(dev_alloc(&c->d_edge, frames));
+  AVLD_CUDA(cudaMemset(c->d_edge, 0, frames * sizeof(float4)));
 
   // ---- per-pass scratch
-  if (!c->dft_fold) {
-    const size_t rows = static_cast<size_t>(c->max_batch) * c->R + 136;
-    AVLD_TRY(dev_alloc(&c->d_Ahi, rows * p.hop));
-    AVLD_TRY(dev_alloc(&c->d_Alo, rows * p.hop));
-    AVLD_CUDA(cudaMemset(c->d_Ahi, 0, rows * p.hop * 2));
-    AVLD_CUDA(cudaMemset(c->d_Alo, 0, rows * p.hop * 2));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A_hi, c->d_Ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
-    AVLD_TRY(encode_tmap_2d(&c->tm_A_lo, c->d_Alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.hop, rows, static_cast<uint64_t>(p.hop) * 2, 64, 128, 128));
-  }
   AVLD_TRY(dev_alloc(&c->d_inv2, c->max_batch));
-  c->melpow_plane = static_cast<long long>(c->max_batch) * c->R * c->M;
-  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 3 : 1)));
-  AVLD_CUDA(cudaMemset(c->d_melpow, 0, static_cast<size_t>(c->melpow_plane) * (c->dft_fold2 ? 3 : 1) * sizeof(float)));
+  c->melpow_plane = static_cast<long long>(frames) * c->M;
+  AVLD_TRY(dev_alloc(&c->d_melpow, static_cast<size_t>(c->melpow_plane) * c->f2_classes));
+  AVLD_CUDA(cudaMemset(c->d_melpow, 0, static_cast<size_t>(c->melpow_plane) * c->f2_classes * sizeof(float)));
   AVLD_TRY(dev_alloc(&c->d_feat, static_cast<size_t>(c->max_batch) * c->T * c->M));
   AVLD_TRY(dev_alloc(&c->d_ok, c->max_batch));
   AVLD_TRY(dev_alloc(&c->d_rms, c->max_batch));
@@ -606,10 +487,10 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_taps, c->d_Bhi, c->d_Blo, c->d_Ahi,
-                  c->d_Alo, c->d_chunk_par, c->d_A2hi, c->d_A2lo, c->d_B2hi, c->d_B2lo, c->d_B3hi, c->d_B3lo, c->d_taps3, c->d_edge, c->d_q16, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok, c->d_rms, c->d_act_hi[0],
-                  c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr,
-                  c->d_prio, c->d_pred, c->d_best, c->d_hist};
+  void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_chunk_par, c->d_A3, c->d_B3hi, c->d_B3lo,
+                  c->d_taps3, c->d_edge, c->d_q16, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok,
+                  c->d_rms, c->d_act_hi[0], c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1],
+                  c->d_cent, c->d_thr, c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& l : c->layers) {
@@ -634,14 +515,13 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
 }
 
 extern "C" int avld_profile_enable(avld_ctx* c, int on) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   c->profiling = on != 0;
   return AVLD_OK;
 }
 
 extern "C" int avld_profile_collect(avld_ctx* c, double* ms, int64_t* timed_launches, uint64_t* launches, int reset) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
-  AVLD_CUDA(cudaSetDevice(c->device));
+  AVLD_ENTER(c);
   for (int i = 0; i < ST_COUNT; ++i) {
     if (ms) ms[i] = 0.0;
     if (timed_launches) timed_launches[i] = 0;
@@ -664,14 +544,14 @@ extern "C" int avld_profile_collect(avld_ctx* c, double* ms, int64_t* timed_laun
 
 extern "C" int avld_stage_count(void) { return ST_COUNT; }
 extern "C" const char* avld_stage_name(int stage) {
-  static const char* names[ST_COUNT] = {"prep_kernel", "gemm3_kernel<DFT>", "logmel_post_kernel", "conv_direct_kernel",
-                                        "gemm3_kernel<CONV>", "gemm3_kernel<PLAIN>", "radii_kernel", "decide_kernel",
-                                        "centroid_kernel", "select_hist_kernel", "split_kernel", "fold_kernel", "map_kernels"};
+  static const char* names[ST_COUNT] = {"prep_kernel", "dftf3_kernel", "logmel_post_kernel", "conv1_kernel", "convh_kernel",
+                                        "gemm3_kernel", "radii_kernel", "decide_kernel", "centroid_kernel", "select_hist_kernel",
+                                        "split_kernel", "fold3_kernel", "map_kernels"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 
 extern "C" int avld_ctx_dft_info(const avld_ctx* c, const char** mode, double* algorithmic, double* issued) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   const double F = c->F, N = c->p.n_fft;
   int first_bin = 0, bins = 0;
   {
@@ -684,25 +564,17 @@ extern "C" int avld_ctx_dft_info(const avld_ctx* c, const char** mode, double* a
   }
   (void)first_bin;
   if (algorithmic) *algorithmic = 2.0 * F * N * 2.0 * bins;
-  const char* m = "direct";
+  // items x (cos + sin) x K x 160 columns, three split-precision passes
+  const char* m = "fold3";
   double iss = 0.0;
-  if (c->dft_fold2) {            // items x (cos + sin) x K x 160 columns, three passes
-    m = c->f2_levels == 3 ? "fold3" : "fold2";
-    for (int it = 0; it < c->f2_items; ++it) iss += 3.0 * 2.0 * F * 2.0 * (c->f2_item[it].kbp * 64.0) * 160.0;
-  } else if (c->dft_fold) {      // per 256-bin tile: K = N/2 for Re and for Im, three passes
-    m = c->dft_pair ? "fold" : "fold1";
-    const double cols = (c->n_tiles2 - 1) * 256.0 + c->last_tile_bins;
-    iss = 3.0 * 2.0 * F * (N / 2) * 2.0 * cols;
-  } else {                       // junk rows between chunks are multiplied too (R rows per chunk)
-    iss = 3.0 * 2.0 * c->R * N * c->ncols;
-  }
+  for (int it = 0; it < c->f2_items; ++it) iss += 3.0 * 2.0 * F * 2.0 * (c->f2_item[it].kbp * 64.0) * 160.0;
   if (mode) *mode = m;
   if (issued) *issued = iss;
   return AVLD_OK;
 }
 
 extern "C" int avld_ctx_info(const avld_ctx* c, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n_frames) *n_frames = c->F;
   if (latent_dim) *latent_dim = c->latent_dim;
   if (sm_count) *sm_count = c->sm_count;

@@ -278,7 +278,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       AVLD_CUDA(cudaGetLastError());
     } else if (L.kind == 3) {
       LaunchScope ls(c, ST_CONV_GEMM, st);
-      AVLD_TRY(launch_convh(L, c->tm_act_hi[li], c->tm_act_lo[li], n, out_hi, out_lo, c->sm_count, st));
+      AVLD_TRY(launch_convh(c, L, c->tm_act_hi[li], c->tm_act_lo[li], n, out_hi, out_lo, st));
     } else if (L.kind == 0) {
       Gemm3Params P{};
       const int H = L.in_h, W = L.in_w;  // same-size convolution
@@ -297,7 +297,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       P.out_lo = out_lo;
       P.H = H; P.W = W; P.Cout = L.c_out; P.pool = L.pool;
       LaunchScope ls(c, ST_CONV_GEMM, st);
-      AVLD_TRY(run_gemm3(L.bn, L.swz, EPI_CONV, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
+      AVLD_TRY(run_gemm3(c, L.bn, L.swz, EPI_CONV, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, st));
     } else {
       Gemm3Params P{};
       P.num_m_tiles = (n + 127) / 128;
@@ -318,7 +318,7 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
         P.out_lo = out_lo;
       }
       LaunchScope ls(c, ST_DENSE_GEMM, st);
-      AVLD_TRY(run_gemm3(L.bn, 128, EPI_PLAIN, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, c->sm_count, st));
+      AVLD_TRY(run_gemm3(c, L.bn, 128, EPI_PLAIN, c->tm_act_hi[li], c->tm_act_lo[li], L.tm_w_hi, L.tm_w_lo, P, st));
     }
   }
   return AVLD_OK;
@@ -329,9 +329,9 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
 using namespace avld;
 
 extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t n_layers) {
-  AVLD_CHECK(c && layers && n_layers > 0, AVLD_ERR_INVALID, "NULL / empty layer list");
+  AVLD_ENTER(c);
+  AVLD_CHECK(layers && n_layers > 0, AVLD_ERR_INVALID, "NULL / empty layer list");
   AVLD_CHECK(c->layers.empty(), AVLD_ERR_STATE, "an encoder is already loaded into this context");
-  AVLD_CUDA(cudaSetDevice(c->device));
   std::vector<LayerDev> out;
   int h = c->T, w = c->M, ch = 1;
   bool flat = false;
@@ -456,7 +456,7 @@ extern "C" int avld_encoder_load(avld_ctx* c, const avld_layer* layers, int32_t 
 }
 
 extern "C" int avld_encoder_forward(avld_ctx* c, const float* feat, float* mu, int64_t n, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(feat && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");

@@ -1,28 +1,27 @@
-// fold2.cu -- operand preparation of the twice-folded STFT ("fold2", see common.cuh): raw chunk -> windowed, two-stage
-// folded fp16 hi/lo rows.  With u[k] = w[k] xs[f*hop + k] (w = periodic Hann, xs = normalised, clipped, PCM_16-quantised,
-// power-of-two-scaled, reflect-padded audio), N = n_fft, H = N/2, Q = N/4 and, for k = 1 .. Q-1,
-//   a = u[k], b = u[N-k], c = u[H-k], d = u[H+k]:
-//   even bins:  Re X[b] = sum_k (a+b+c+d) cos(2 pi k b / N) + edge_e cos(pi b / 2),  -Im X[b] = sum_k ((a-b)-(c-d)) sin(.)
-//   odd  bins:  Re X[b] = sum_k (a+b-c-d) cos(.),  -Im X[b] = sum_k ((a-b)+(c-d)) sin(.) + edge_o sin(pi b / 2)
-//   k = 0 column: cos parts u[0] +- u[H], sin parts 0;   edge_e = u[Q] + u[N-Q],  edge_o = u[Q] - u[N-Q].
-// (time-reversal symmetry of a real DFT, applied twice; w[N-k] = w[k], w[H-k] = w[H+k].)  Row layout of A3 (N columns):
-//   [ even: cos part (Q) | sin part (Q) | odd: cos part (Q) | sin part (Q) ].
-// One thread = 8 consecutive k of one frame: four runs of 8 samples (two ascending, two descending), 64 B + 64 B out.
-// The window is applied here in fp32 (the products are no longer exact integers; the hi/lo split keeps 22 bits).
+// fold3.cu -- operand preparation of the three-times folded STFT: raw chunk -> windowed, folded fp16 hi/lo tiles.
+// With u[k] = w[k] xs[f*hop + k] (w = periodic Hann, xs = normalised, clipped, PCM_16-quantised, power-of-two-scaled,
+// reflect-padded audio; replaces the frame / window / rfft front of librosa.stft, map_detector_core.py:219-228), N = n_fft,
+// H = N/2, Q = N/4, E = N/8, the time-reversal symmetry of a real DFT is applied up to three times: the odd
+// bins keep Q taps per cos / sin part, the bins = 0 and = 2 mod 4 keep E taps each.
+//
+// Operand layout ("A3", tile-major): [frame tile of 128 rows][64-tap K block of the N columns][hi | lo][128 rows][64 taps]
+// fp16, columns = [ odd: cos (Q) | sin (Q) | b = 0 mod 4: cos (E) | sin (E) | b = 2 mod 4: cos (E) | sin (E) ].  One
+// (tile, K block) is 32 KB of contiguous memory = exactly one TMA box of the GEMM (dftf3.cu): a row-major [frame][N]
+// matrix made every box 128 row segments of 128 bytes with a 4 KB pitch, which the GEMM could only stream at about half
+// the DRAM rate (profiles/r02a_dft_probes.txt).
 #include <cstdlib>
 #include "common.cuh"
 #include "sample.cuh"
 
 namespace avld {
 
-struct Fold2Params {
+struct Fold3Params {
   const float* x;       // [n][L] or NULL
   const int16_t* x16;   // [n][L] PCM_16 or NULL
   const uint16_t* q16;  // [n][L] normalised PCM_16 + 32768 written by prep_kernel, or NULL (fold3_kernel<2> reads it instead of x)
   const float4* chunk_par;
   const float* win;     // [H + 1] periodic Hann, win[k] = 0.5 - 0.5 cos(2 pi k / N)
-  __half* a_hi;         // [n*F][N]
-  __half* a_lo;
+  __half* a3;           // tile-major folded operand, see the header
   float4* edge;         // [n*F] one self-paired tap per bin class (indexed by class), see the kernels
   int F, hop, n_fft, L, quantize;
   int vec_ok;
@@ -61,105 +60,29 @@ __device__ __forceinline__ void load8(const float* xf, const int16_t* xi, int sr
   }
 }
 
-__device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t at, const float (&v)[8]) {
+// 8 consecutive taps (col % 8 == 0) of one frame row into the tile-major operand: row_base = offset of (tile, K block 0,
+// hi, row), one K block = 2 * 128 * 64 halves, lo = hi + 128 * 64
+__device__ __forceinline__ void split_store(__half* a3, size_t row_base, int col, const float (&v)[8]) {
   __align__(16) __half h[8], l[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     h[q] = __float2half_rn(v[q]);
     l[q] = __float2half_rn(v[q] - __half2float(h[q]));
   }
-  *reinterpret_cast<uint4*>(hi + at) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(lo + at) = *reinterpret_cast<const uint4*>(l);
+  __half* dst = a3 + row_base + static_cast<size_t>(col >> 6) * (2 * 128 * 64) + (col & 63);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(dst + 128 * 64) = *reinterpret_cast<const uint4*>(l);
 }
 
 }  // namespace
 
-template <bool PCM>
-__global__ void __launch_bounds__(256) fold2_kernel(const Fold2Params P) {
-  const int N = P.n_fft, H = N >> 1, Q = N >> 2, per_frame = Q >> 3;
-  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < P.total;
-       t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = t / per_frame;                 // global frame index = chunk * F + f
-    const int k0 = static_cast<int>(t - row * per_frame) << 3;
-    const long long chunk = row / P.F;
-    const int f = static_cast<int>(row - chunk * P.F);
-    const float4 par = P.chunk_par[chunk];
-    const float scale = par.x, pow2 = par.y;
-    const int scaled = par.z != 0.f;
-    const float* xf = PCM ? nullptr : P.x + chunk * P.L;
-    const int16_t* xi = PCM ? P.x16 + chunk * P.L : nullptr;
-    const int pf = f * P.hop;                            // padded index of the frame's tap 0
-    // xa[q] = xs[pf + k0 + q], xd[q] = xs[pf + H + k0 + q], xb[q] = xs[pf + N - k0 - q], xc[q] = xs[pf + H - k0 - q]
-    float xa[8], xb[8], xc[8], xd[8];
-    const int s0 = pf - H;                               // source index of tap 0 when nothing is reflected
-    if (P.vec_ok && s0 - 8 >= 0 && s0 + N + 8 <= P.L) {
-      float rb[8], rc[8];
-      load8<PCM>(xf, xi, s0 + k0, xa);
-      load8<PCM>(xf, xi, s0 + H + k0, xd);
-      load8<PCM>(xf, xi, s0 + N - k0 - 8, rb);           // taps N-k0-8 .. N-k0-1
-      load8<PCM>(xf, xi, s0 + H - k0 - 8, rc);           // taps H-k0-8 .. H-k0-1
-      xb[0] = raw_sample<PCM>(xf, xi, s0 + N - k0);
-      xc[0] = raw_sample<PCM>(xf, xi, s0 + H - k0);
-#pragma unroll
-      for (int q = 1; q < 8; ++q) {
-        xb[q] = rb[8 - q];
-        xc[q] = rc[8 - q];
-      }
-    } else {
-      // the first / last frames touch the reflect padding (and the last tap N of the last frame does not exist)
-      const int plen = P.L + N;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int ia = pf + k0 + q, id = pf + H + k0 + q, ib = pf + N - k0 - q, ic = pf + H - k0 - q;
-        xa[q] = raw_sample<PCM>(xf, xi, reflect_src(ia, H, P.L));
-        xd[q] = raw_sample<PCM>(xf, xi, reflect_src(id, H, P.L));
-        xb[q] = ib < plen ? raw_sample<PCM>(xf, xi, reflect_src(ib, H, P.L)) : 0.f;
-        xc[q] = raw_sample<PCM>(xf, xi, reflect_src(ic, H, P.L));
-      }
-    }
-    float c0[8], s0v[8], c1[8], s1v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k = k0 + q;
-      const float wk = P.win[k], wh = P.win[H - k];
-      float a = finish_sample(xa[q], scale, scaled, P.quantize) * pow2;
-      float b = finish_sample(xb[q], scale, scaled, P.quantize) * pow2;
-      float c = finish_sample(xc[q], scale, scaled, P.quantize) * pow2;
-      float d = finish_sample(xd[q], scale, scaled, P.quantize) * pow2;
-      if (k == 0) {                                      // u[0] and u[H] pair with nothing
-        b = 0.f;
-        d = 0.f;
-      }
-      const float ep = wk * (a + b), em = wh * (c + d);  // a + b and c + d are exact (integers times a power of two)
-      const float op = wk * (a - b), om = wh * (c - d);
-      c0[q] = ep + em;
-      c1[q] = ep - em;
-      s0v[q] = k == 0 ? 0.f : op - om;
-      s1v[q] = k == 0 ? 0.f : op + om;
-    }
-    const size_t base = static_cast<size_t>(row) * N + k0;
-    split_store(P.a_hi, P.a_lo, base, c0);
-    split_store(P.a_hi, P.a_lo, base + Q, s0v);
-    split_store(P.a_hi, P.a_lo, base + H, c1);
-    split_store(P.a_hi, P.a_lo, base + H + Q, s1v);
-    if (k0 == 0) {
-      const float wq = P.win[Q];
-      const float p = finish_sample(raw_sample<PCM>(xf, xi, reflect_src(pf + Q, H, P.L)), scale, scaled, P.quantize) * pow2;
-      const float m = finish_sample(raw_sample<PCM>(xf, xi, reflect_src(pf + N - Q, H, P.L)), scale, scaled, P.quantize) * pow2;
-      P.edge[row] = make_float4(wq * (p + m), wq * (p - m), 0.f, 0.f);     // class 0 = even bins, class 1 = odd bins
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// fold3_kernel: as fold2_kernel, with one more fold for the even bins (their cos / sin kernels are again symmetric
-// about k = N/8 once restricted to b = 0 or 2 mod 4; the odd bins' symmetry is spent).  With Q = N/4, E = N/8 and, for
+// fold3_kernel.  With Q = N/4, E = N/8 and, for
 // k = 1 .. E-1,  u1 = u[k], u2 = u[N-k], u3 = u[2Q-k], u4 = u[2Q+k], u5 = u[Q-k], u6 = u[3Q+k], u7 = u[Q+k], u8 = u[3Q-k]:
 //   P = u1+u2+u3+u4, P' = u5+u6+u7+u8, R = (u1-u2)-(u3-u4), R' = (u5-u6)-(u7-u8)
 //   b = 0 mod 4:  Re X = sum_k (P + P') cos(2 pi k b / N) + edge cos(pi b / 4),    -Im X = sum_k (R - R') sin(.)
 //   b = 2 mod 4:  Re X = sum_k (P - P') cos(.),                                   -Im X = sum_k (R + R') sin(.) + edge sin(pi b / 4)
 //   odd b (k < Q): Re X = sum_k ((u1+u2)-(u3+u4)) cos(.),  -Im X = sum_k ((u1-u2)+(u3-u4)) sin(.) + edge sin(pi b / 2)
-// Row layout of A3: [ odd: cos (Q) | sin (Q) | b = 0 mod 4: cos (E) | sin (E) | b = 2 mod 4: cos (E) | sin (E) ].
 // One thread = 8 consecutive k < E of one frame: eight runs of the chunk (the four of the second half also give the odd
 // class at k' = Q - k, which lands on an aligned block when shifted by one tap), 256 B out.
 // ------------------------------------------------------------------------------------------------
@@ -212,9 +135,9 @@ struct Samples {
 }  // namespace
 
 // NFFT = 0: n_fft at run time; otherwise a compile-time n_fft (every row offset becomes an immediate).  Thread indices are
-// 32-bit (launch_fold2 checks total < 2^31): the 64-bit divisions of the generic form were ~10 % of the instructions.
+// 32-bit (launch_fold3 checks total < 2^31): the 64-bit divisions of the generic form were ~10 % of the instructions.
 template <int SRC, int MINB, int NFFT>
-__global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold2Params P) {
+__global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold3Params P) {
   const int N = NFFT ? NFFT : P.n_fft, H = N >> 1, Q = N >> 2, E = N >> 3, per_frame = E >> 3;
   const unsigned total = static_cast<unsigned>(P.total), F = static_cast<unsigned>(P.F);
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -320,15 +243,15 @@ __global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold2Params P) {
         s2v[q] = z ? 0.f : Rk + Rm;
       }
     }
-    const size_t base = static_cast<size_t>(row) * N;
-    split_store(P.a_hi, P.a_lo, base + k0, oc);
-    split_store(P.a_hi, P.a_lo, base + Q + k0, os);
-    split_store(P.a_hi, P.a_lo, base + (Q - k0 - 8), oc2);
-    split_store(P.a_hi, P.a_lo, base + Q + (Q - k0 - 8), os2);
-    split_store(P.a_hi, P.a_lo, base + H + k0, c0);
-    split_store(P.a_hi, P.a_lo, base + H + E + k0, s0v);
-    split_store(P.a_hi, P.a_lo, base + H + Q + k0, c2);
-    split_store(P.a_hi, P.a_lo, base + H + Q + E + k0, s2v);
+    const size_t base = (static_cast<size_t>(row >> 7) * (N >> 6) * 256 + (row & 127)) * 64;
+    split_store(P.a3, base, k0, oc);
+    split_store(P.a3, base, Q + k0, os);
+    split_store(P.a3, base, Q - k0 - 8, oc2);
+    split_store(P.a3, base, Q + (Q - k0 - 8), os2);
+    split_store(P.a3, base, H + k0, c0);
+    split_store(P.a3, base, H + E + k0, s0v);
+    split_store(P.a3, base, H + Q + k0, c2);
+    split_store(P.a3, base, H + Q + E + k0, s2v);
     if (k0 == 0) {
       auto xs = [&](int tap) -> float {
         const float r = X.raw(reflect_src(pf + tap, H, P.L));
@@ -344,16 +267,15 @@ __global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold2Params P) {
   }
 }
 
-int launch_fold2(avld_ctx* c, int n, cudaStream_t st) {
+int launch_fold3(avld_ctx* c, int n, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
-  Fold2Params P{};
+  Fold3Params P{};
   P.x = c->cur_x;
   P.x16 = c->cur_x16;
   P.q16 = c->cur_q16;
   P.chunk_par = c->d_chunk_par;
   P.win = c->d_win;
-  P.a_hi = c->d_A2hi;
-  P.a_lo = c->d_A2lo;
+  P.a3 = c->d_A3;
   P.edge = c->d_edge;
   P.F = c->F;
   P.hop = c->p.hop;
@@ -362,31 +284,23 @@ int launch_fold2(avld_ctx* c, int n, cudaStream_t st) {
   P.quantize = c->cur_quantize;
   P.vec_ok = (c->L % 8 == 0) && (c->p.hop % 8 == 0) && (reinterpret_cast<uintptr_t>(P.x) % 16 == 0) &&
              (reinterpret_cast<uintptr_t>(P.x16) % 16 == 0);
-  const bool three = c->f2_levels == 3;
-  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / (three ? 64 : 32));
-  const long long blocks = (P.total + 255) / 256;
-  const long long cap = static_cast<long long>(c->sm_count) * 32;
-  const int grid = static_cast<int>(blocks < cap ? blocks : cap);
+  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / 64);
+  AVLD_CHECK(P.total < (1ll << 31), AVLD_ERR_UNSUPPORTED, "fold3: more than 2^31 operand threads in one pass");
+  // ~145 registers per thread: 128-thread blocks keep three to four blocks per SM resident
+  const long long b3 = (P.total + 127) / 128, cap = static_cast<long long>(c->sm_count) * 64;
+  const int g3 = static_cast<int>(b3 < cap ? b3 : cap);
+  const bool n2k = c->p.n_fft == 2048;
   {
     LaunchScope ls(c, ST_FOLD, st);
-    if (three) {      // ~145 registers per thread: 128-thread blocks keep three blocks per SM resident
-      const long long b3 = (P.total + 127) / 128;
-      const int g3 = static_cast<int>(b3 < 2 * cap ? b3 : 2 * cap);
-      AVLD_CHECK(P.total < (1ll << 31), AVLD_ERR_UNSUPPORTED, "fold3: more than 2^31 operand threads in one pass");
-      const bool n2k = c->p.n_fft == 2048;
-      if (P.q16 != nullptr) {
-        if (n2k) fold3_kernel<2, 4, 2048><<<g3, 128, 0, st>>>(P);
-        else fold3_kernel<2, 4, 0><<<g3, 128, 0, st>>>(P);
-      } else if (P.x16 != nullptr) {
-        if (n2k) fold3_kernel<1, 3, 2048><<<g3, 128, 0, st>>>(P);
-        else fold3_kernel<1, 3, 0><<<g3, 128, 0, st>>>(P);
-      } else {
-        if (n2k) fold3_kernel<0, 3, 2048><<<g3, 128, 0, st>>>(P);
-        else fold3_kernel<0, 3, 0><<<g3, 128, 0, st>>>(P);
-      }
+    if (P.q16 != nullptr) {
+      if (n2k) fold3_kernel<2, 4, 2048><<<g3, 128, 0, st>>>(P);
+      else fold3_kernel<2, 4, 0><<<g3, 128, 0, st>>>(P);
+    } else if (P.x16 != nullptr) {
+      if (n2k) fold3_kernel<1, 3, 2048><<<g3, 128, 0, st>>>(P);
+      else fold3_kernel<1, 3, 0><<<g3, 128, 0, st>>>(P);
     } else {
-      if (P.x16 != nullptr) fold2_kernel<true><<<grid, 256, 0, st>>>(P);
-      else fold2_kernel<false><<<grid, 256, 0, st>>>(P);
+      if (n2k) fold3_kernel<0, 3, 2048><<<g3, 128, 0, st>>>(P);
+      else fold3_kernel<0, 3, 0><<<g3, 128, 0, st>>>(P);
     }
   }
   AVLD_CUDA(cudaGetLastError());

@@ -5,28 +5,25 @@
 namespace avld {
 
 template <int EPI>
-static int by_shape(int bn, int swz, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                    const CUtensorMap& b_lo, const Gemm3Params& P, int sms, cudaStream_t st) {
+static int by_shape(avld_ctx* c, int bn, int swz, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                    const CUtensorMap& b_lo, const Gemm3Params& P, cudaStream_t st) {
   if (swz == 128) {
-    if (bn == 64) return launch_gemm3<64, 128, EPI>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-    if (bn == 128) return launch_gemm3<128, 128, EPI>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-    if (bn == 256) return launch_gemm3<256, 128, EPI>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
+    if (bn == 64) return launch_gemm3<64, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);
+    if (bn == 128) return launch_gemm3<128, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);
+    if (bn == 256) return launch_gemm3<256, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);
   } else if (swz == 64 && EPI == EPI_CONV) {
-    if (bn == 64) return launch_gemm3<64, 64, EPI_CONV>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-    if (bn == 128) return launch_gemm3<128, 64, EPI_CONV>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-    if (bn == 256) return launch_gemm3<256, 64, EPI_CONV>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
+    if (bn == 64) return launch_gemm3<64, 64, EPI_CONV>(c, a_hi, a_lo, b_hi, b_lo, P, st);
+    if (bn == 128) return launch_gemm3<128, 64, EPI_CONV>(c, a_hi, a_lo, b_hi, b_lo, P, st);
+    if (bn == 256) return launch_gemm3<256, 64, EPI_CONV>(c, a_hi, a_lo, b_hi, b_lo, P, st);
   }
   set_error("run_gemm3: no kernel for BN=%d swizzle=%d epilogue=%d", bn, swz, EPI);
   return AVLD_ERR_UNSUPPORTED;
 }
 
-int run_gemm3(int bn, int swz, int epi, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-              const CUtensorMap& b_lo, const Gemm3Params& P, int sms, cudaStream_t st) {
-  if (epi == EPI_PLAIN) return by_shape<EPI_PLAIN>(bn, swz, a_hi, a_lo, b_hi, b_lo, P, sms, st);
-  if (epi == EPI_CONV) return by_shape<EPI_CONV>(bn, swz, a_hi, a_lo, b_hi, b_lo, P, sms, st);
-  if (epi == EPI_DFT && bn == 256 && swz == 128) return launch_gemm3<256, 128, EPI_DFT>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-  if (epi == EPI_DFTF && bn == 256 && swz == 128) return launch_gemm3<256, 128, EPI_DFTF>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
-  if (epi == EPI_DFTF && bn == 256 && swz == 64) return launch_gemm3<256, 64, EPI_DFTF>(a_hi, a_lo, b_hi, b_lo, P, sms, st);
+int run_gemm3(avld_ctx* c, int bn, int swz, int epi, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+              const CUtensorMap& b_lo, const Gemm3Params& P, cudaStream_t st) {
+  if (epi == EPI_PLAIN) return by_shape<EPI_PLAIN>(c, bn, swz, a_hi, a_lo, b_hi, b_lo, P, st);
+  if (epi == EPI_CONV) return by_shape<EPI_CONV>(c, bn, swz, a_hi, a_lo, b_hi, b_lo, P, st);
   set_error("run_gemm3: no kernel for BN=%d swizzle=%d epilogue=%d", bn, swz, epi);
   return AVLD_ERR_UNSUPPORTED;
 }

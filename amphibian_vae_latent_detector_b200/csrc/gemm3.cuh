@@ -1,5 +1,5 @@
-// gemm3.cuh -- split-precision GEMM core on tcgen05 / TMEM (sm_100a), shared by the STFT
-// (windowed DFT as a GEMM), the encoder's implicit-GEMM convolutions and its dense layers.
+// gemm3.cuh -- split-precision GEMM core on tcgen05 / TMEM (sm_100a) for the encoder's dense layers and the
+// implicit-GEMM convolutions that convh.cu does not cover (the STFT has its own CTA-pair kernel, dftf3.cu).
 //
 //   D[128 x BN] (fp32, TMEM) += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo       per 16-wide K step
 //
@@ -12,10 +12,8 @@
 //   warp 0 / lane 0 : TMA producer  -- A (hi, lo) and B (hi, lo) boxes into a STAGES-deep smem ring
 //   warp 1 / lane 0 : MMA issuer    -- tcgen05.mma, tcgen05.commit frees smem slots / publishes TMEM
 //   warps 2..5      : epilogue      -- tcgen05.ld from a double-buffered TMEM accumulator
-// A tiles are addressed three ways (a_mode):
+// A tiles are addressed two ways (a_mode):
 //   0  plain row-major [M, K]                      box (k0, m0)
-//   1  audio rows [n_rows, hop] (frame g, tap k lives at row g + k / hop, column k % hop: the STFT's
-//      im2col is free -- frames are overlapping windows, so no frame matrix is ever materialised)
 //   2  NHWC activations [N, H, W, C]: one box per filter tap, shifted by (kh - pad, kw - pad);
 //      TMA out-of-bounds zero fill *is* the convolution's zero padding
 #pragma once
@@ -24,20 +22,14 @@
 
 namespace avld {
 
-enum { EPI_PLAIN = 0, EPI_DFT = 1, EPI_CONV = 2, EPI_DFTF = 3 };
-// EPI_DFTF = folded STFT: per 256-bin N tile the first half of the K blocks (E | cos) accumulates the real parts
-// into TMEM columns [0, 256), the second half (O | -sin) the imaginary parts into [256, 512): one 512-column
-// accumulator, single buffered (the epilogue of a tile is not overlapped with the next tile's MMAs).
+enum { EPI_PLAIN = 0, EPI_CONV = 2 };
 
 struct Gemm3Params {
   int num_m_tiles, num_n_tiles, num_k_blocks;
   int dbg_shift, dbg_baseoff;   // bring-up probe: A descriptor start shifted by dbg_shift rows, descriptor base-offset field
   int split_n;  // 1: a work item is one (m tile, n tile) pair (dense layers with few m tiles); 0: one m tile, all n tiles
   uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
-  uint32_t idesc_last;                    // EPI_DFTF: descriptor of the last N tile when it holds only last_bins bins
-  int last_bins;
   int a_mode;
-  int hpb;  // a_mode 1: 64-sample blocks per hop
   // a_mode 2 geometry
   int tiles_w, tiles_h, tw, th, ksize, cblocks, cblk, pad;
   // common epilogue
@@ -49,21 +41,13 @@ struct Gemm3Params {
   int ldc;
   __nv_bfloat16* out_hi;    // PLAIN/CONV: split output for the next tensor-core layer
   __nv_bfloat16* out_lo;
-  // DFT epilogue
-  const void* a_hi_ptr;     // EPI_DFTF: base pointers / row pitch (bytes) of the A operand, for the L2-prefetch warp
-  const void* a_lo_ptr;
-  long long a_pitch;
-  const float* inv2;        // per chunk 2^(-2 s)
-  const MelTap* taps;       // [nbins_pad]
-  float* melpow;            // [rows][n_mels]
-  int R, F, n_mels, nbins_pad;
   // CONV epilogue
   int H, W, Cout, pool;     // H, W: conv output size before pooling
 };
 
 // non-template dispatcher (all instantiations live in gemm3.cu)
-int run_gemm3(int bn, int swz, int epi, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-              const CUtensorMap& tmB_lo, const Gemm3Params& P, int sm_count, cudaStream_t st);
+int run_gemm3(avld_ctx* c, int bn, int swz, int epi, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo,
+              const CUtensorMap& tmB_hi, const CUtensorMap& tmB_lo, const Gemm3Params& P, cudaStream_t st);
 
 #ifdef AVLD_GEMM3_IMPL
 template <int BN, int SWZ>
@@ -82,9 +66,9 @@ struct Gemm3Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
 
-// threads per CTA: TMA warp + MMA warp + 4 epilogue warps (8 for the folded STFT, whose epilogue is not overlapped)
+// threads per CTA: TMA warp + MMA warp + 4 epilogue warps
 template <int EPI>
-struct Gemm3Threads { static constexpr int value = (EPI == EPI_DFTF) ? 352 : 192; };   // DFTF: + 4 epilogue warps + 1 L2-prefetch warp
+struct Gemm3Threads { static constexpr int value = 192; };
 
 template <int BN, int SWZ, int EPI>
 __global__ void __launch_bounds__(Gemm3Threads<EPI>::value, 1)
@@ -94,8 +78,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
   using Cfg = Gemm3Cfg<BN, SWZ>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr bool FOLD = (EPI == EPI_DFTF);
-  constexpr int NACC = FOLD ? 1 : 2;            // TMEM accumulator buffers
+  constexpr int NACC = 2;                       // TMEM accumulator buffers
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS, not generic LD)
@@ -105,8 +88,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   uint64_t* tmem_full = empty_bar + STAGES;                          // [2]
   uint64_t* tmem_empty = tmem_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);            // EPI_DFT only (<= 12 KB)
-  float* s_bias = reinterpret_cast<float*>(tail + 512);              // other epilogues: bias[N_total], zero padded
+  float* s_bias = reinterpret_cast<float*>(tail + 512);              // bias[N_total], zero padded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,15 +104,13 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], FOLD ? 256 : 128);
+      mbar_init(&tmem_empty[a], 128);
     }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if (EPI == EPI_DFT || EPI == EPI_DFTF) {
-    for (int i = threadIdx.x; i < P.nbins_pad; i += blockDim.x) s_taps[i] = P.taps[i];
-  } else {
+  {
     const int nb = P.num_n_tiles * BN;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bias[i] = (P.bias != nullptr && i < P.N_total) ? P.bias[i] : 0.f;
   }
@@ -147,21 +127,6 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // FOLD: the A operand (folded frames) streams from HBM and is re-read once per N tile; a second iterator runs
-      // PF K blocks ahead of the loads and prefetches those boxes into L2
-      constexpr int PF = 512 / Cfg::BK;   // 8 blocks of 64 / 16 blocks of 32 taps ahead
-      [[maybe_unused]] int pf_item = blockIdx.x, pf_nt = 0, pf_kb = 0;
-      [[maybe_unused]] auto pf_step = [&]() {
-        if (pf_item < n_items) {
-          tma_prefetch_2d(&tmA_hi, pf_kb * Cfg::BK, pf_item * Cfg::BM);
-          tma_prefetch_2d(&tmA_lo, pf_kb * Cfg::BK, pf_item * Cfg::BM);
-          if (++pf_kb == nkb) {
-            pf_kb = 0;
-            if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_item += gridDim.x; }
-          }
-        }
-      };
-      (void)pf_step;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = P.split_n ? item / P.num_n_tiles : item;
         const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
@@ -185,11 +150,6 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             if (P.a_mode == 0) {
               tma_load_2d(sa_hi, &tmA_hi, &full_bar[stage], kb * Cfg::BK, mt * Cfg::BM);
               tma_load_2d(sa_lo, &tmA_lo, &full_bar[stage], kb * Cfg::BK, mt * Cfg::BM);
-            } else if (P.a_mode == 1) {
-              const int x = (kb % P.hpb) * Cfg::BK;
-              const int y = mt * Cfg::BM + kb / P.hpb;
-              tma_load_2d(sa_hi, &tmA_hi, &full_bar[stage], x, y);
-              tma_load_2d(sa_lo, &tmA_lo, &full_bar[stage], x, y);
             } else {
               const int tap = kb / P.cblocks;
               const int cb = kb - tap * P.cblocks;
@@ -197,15 +157,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               tma_load_4d(sa_hi, &tmA_hi, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
               tma_load_4d(sa_lo, &tmA_lo, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
             }
-            if (FOLD) {   // B2 rows: tile nt holds BN cos rows then BN (-sin) rows, each K/2 wide
-              const int hk = nkb >> 1;
-              const int bx = (kb < hk ? kb : kb - hk) * Cfg::BK, by = nt * 2 * BN + (kb < hk ? 0 : BN);
-              tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], bx, by);
-              tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], bx, by);
-            } else {
-              tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
-              tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
-            }
+            tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
+            tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -225,15 +178,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int sub = 0; sub < n_sub; ++sub) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
           tcgen05_fence_after();
-          const uint32_t d_tmem0 = tmem_base + static_cast<uint32_t>(acc * BN);
-          [[maybe_unused]] const bool last_tile = FOLD && (sub == n_sub - 1) && P.last_bins != BN;
-          const uint32_t id_hh = last_tile ? P.idesc_last : P.idesc_hh;
-          const uint32_t id_lh = last_tile ? P.idesc_last : P.idesc_lh;
-          const uint32_t id_hl = last_tile ? P.idesc_last : P.idesc_hl;
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+          const uint32_t id_hh = P.idesc_hh, id_lh = P.idesc_lh, id_hl = P.idesc_hl;
           for (int kb = 0; kb < nkb; ++kb) {
-            const int hk = nkb >> 1;
-            const uint32_t d_tmem = FOLD ? d_tmem0 + (kb < hk ? 0u : static_cast<uint32_t>(BN)) : d_tmem0;
-            const int kb_acc = FOLD ? (kb < hk ? kb : kb - hk) : kb;
+            const int kb_acc = kb;
             mbar_wait(&full_bar[stage], phase, 300 + stage);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -261,45 +209,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
       }
     }
-  } else if (FOLD && warp == 10) {
-    // ------------------------------------------------------------------ L2 prefetch warp (folded STFT only)
-    // The A operand (folded frames) streams from HBM and is re-read once per N tile.  This warp walks the producer's
-    // K-block sequence PFD blocks ahead, paced by the same "stage free" barriers, and pulls the rows of that block into
-    // L2 with plain prefetch instructions (LSU path): the TMA unit's row rate is the scarce resource of this kernel.
-    constexpr int PFD = 6;
-    int stage = 0;
-    uint32_t phase = 0;
-    int pf_item = blockIdx.x, pf_nt = 0, pf_kb = 0;
-    auto issue = [&]() {
-      if (pf_item < n_items) {
-        const long long row0 = static_cast<long long>(pf_item) * Cfg::BM;
-        const char* ph = static_cast<const char*>(P.a_hi_ptr) + row0 * P.a_pitch + static_cast<long long>(pf_kb) * SWZ;
-        const char* pl = static_cast<const char*>(P.a_lo_ptr) + row0 * P.a_pitch + static_cast<long long>(pf_kb) * SWZ;
-#pragma unroll
-        for (int q = 0; q < Cfg::BM / 32; ++q) {
-          const long long off = static_cast<long long>(lane + 32 * q) * P.a_pitch;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ph + off));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + off));
-        }
-        if (++pf_kb == nkb) {
-          pf_kb = 0;
-          if (++pf_nt == P.num_n_tiles) { pf_nt = 0; pf_item += gridDim.x; }
-        }
-      }
-    };
-    for (int i = 0; i < PFD; ++i) issue();
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      for (int nt = 0; nt < P.num_n_tiles; ++nt) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1u, 500 + stage);
-          __syncwarp();
-          issue();
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5; 2..9 for the folded STFT)
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
@@ -309,66 +220,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const int mt = P.split_n ? item / P.num_n_tiles : item;
       const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
       const int nt_end = P.split_n ? nt_begin + 1 : P.num_n_tiles;
-      // ---- per M-tile state
-      [[maybe_unused]] int cur = 0;
-      [[maybe_unused]] float acc0 = 0.f, acc1 = 0.f, s2 = 0.f;
-      [[maybe_unused]] bool valid = false;
-      [[maybe_unused]] long long g = 0;
-      if (EPI == EPI_DFT || EPI == EPI_DFTF) {
-        g = static_cast<long long>(mt) * Cfg::BM + row;
-        const long long c = g / P.R;                    // R = rows per chunk (direct: R incl. junk frames; folded: F)
-        const int f = static_cast<int>(g - c * P.R);
-        valid = (g < P.M_total) && (f < P.F);
-        s2 = valid ? P.inv2[c] : 0.f;
-      }
       for (int nt = nt_begin; nt < nt_end; ++nt) {
         mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
 
-        if (EPI == EPI_DFTF) {
-          // Folded STFT: [0, BN) = Re, [BN, 2 BN) = Im of the tile's BN bins.  Two warps per TMEM lane quarter, each
-          // taking half of the tile's bins; every mel output is accumulated with atomicAdd onto a zeroed buffer (a
-          // filter is narrower than half a tile, so it receives at most two partial sums: 0 + a + b is order independent).
-          const int half_id = (warp - 2) >> 2;
-          const int nb_tile = (nt == P.num_n_tiles - 1) ? P.last_bins : BN;
-          const int hbins = nb_tile >> 1;
-          const int b0 = half_id * hbins;
-          const MelTap* tile_taps = s_taps + nt * BN;
-          float* mrow = P.melpow + g * P.n_mels;
-          int mcur = tile_taps[b0].first;
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll 1
-          for (int c0 = b0; c0 < b0 + hbins; c0 += 16) {
-            uint32_t re[16], im[16];
-            tmem_ld16(t_acc + c0, re);
-            tmem_ld16(t_acc + BN + c0, im);
-            tmem_ld_wait();
-            float pw[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
-              pw[j] = (a * a + b * b) * s2;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const MelTap tp = tile_taps[c0 + j];
-              if (mcur < tp.first) {                 // warp-uniform (taps do not depend on the row), rare: 64 times per row
-#pragma unroll 1
-                while (mcur < tp.first) {
-                  if (valid && a0 != 0.f) atomicAdd(mrow + mcur, a0);
-                  a0 = a1;
-                  a1 = 0.f;
-                  ++mcur;
-                }
-              }
-              a0 = fmaf(tp.w0, pw[j], a0);
-              a1 = fmaf(tp.w1, pw[j], a1);
-            }
-          }
-          if (valid && a0 != 0.f && mcur < P.n_mels) atomicAdd(mrow + mcur, a0);
-          if (valid && a1 != 0.f && mcur + 1 < P.n_mels) atomicAdd(mrow + mcur + 1, a1);
-        } else if (EPI == EPI_PLAIN) {
+        if (EPI == EPI_PLAIN) {
           const long long m = static_cast<long long>(mt) * Cfg::BM + row;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -400,38 +257,6 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                   P.out_lo[m * P.ldc + n0 + j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi));
                 }
               }
-            }
-          }
-        } else if (EPI == EPI_DFT) {
-          // columns [0, BN/2) = Re, [BN/2, BN) = Im of the same BN/2 bins
-          constexpr int HB = BN / 2;
-#pragma unroll 1
-          for (int c0 = 0; c0 < HB; c0 += 16) {
-            uint32_t re[16], im[16];
-            tmem_ld16(t_acc + c0, re);
-            tmem_ld16(t_acc + HB + c0, im);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const MelTap tp = s_taps[nt * HB + c0 + j];
-              const float a = __uint_as_float(re[j]), b = __uint_as_float(im[j]);
-              const float pw = (a * a + b * b) * s2;
-              while (cur < tp.first) {               // warp-uniform: taps and cur do not depend on the row
-                if (valid) P.melpow[g * P.n_mels + cur] = acc0;
-                acc0 = acc1;
-                acc1 = 0.f;
-                ++cur;
-              }
-              acc0 = fmaf(tp.w0, pw, acc0);
-              acc1 = fmaf(tp.w1, pw, acc1);
-            }
-          }
-          if (nt == P.num_n_tiles - 1) {
-            while (cur < P.n_mels) {
-              if (valid) P.melpow[g * P.n_mels + cur] = acc0;
-              acc0 = acc1;
-              acc1 = 0.f;
-              ++cur;
             }
           }
         } else {
@@ -512,15 +337,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 }
 
 template <int BN, int SWZ, int EPI>
-int launch_gemm3(const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
-                 const CUtensorMap& tmB_lo, const Gemm3Params& P, int sm_count, cudaStream_t st) {
+int launch_gemm3(avld_ctx* c, const CUtensorMap& tmA_hi, const CUtensorMap& tmA_lo, const CUtensorMap& tmB_hi,
+                 const CUtensorMap& tmB_lo, const Gemm3Params& P, cudaStream_t st) {
+  const int sm_count = c->sm_count;
   using Cfg = Gemm3Cfg<BN, SWZ>;
-  static bool configured = false;
   auto kfn = gemm3_kernel<BN, SWZ, EPI>;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(kfn), Cfg::SMEM_BYTES));
   const int items = P.split_n ? P.num_m_tiles * P.num_n_tiles : P.num_m_tiles;
   int grid = items < sm_count ? items : sm_count;
   if (grid < 1) return AVLD_OK;

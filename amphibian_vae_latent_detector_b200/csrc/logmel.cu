@@ -2,84 +2,26 @@
 // z-score / centre crop (map_detector_core.py:219-237) and the [M,T] -> [T,M] transpose of
 // map_detector_core.py:267-268.
 //
-//   prep_kernel (rms.cu)            audio -> padded fp16/bf16 operand rows
-//   gemm3_kernel<256,128,EPI_DFT>   windowed DFT as a tcgen05 GEMM; epilogue = |X|^2, un-scale,
+//   prep_kernel (rms.cu)            audio -> per-chunk scale + normalised PCM_16 integers
+//   fold3_kernel (fold3.cu)         windowed, three-times folded frames (fp16 hi / lo tiles)
+//   dftf3_kernel (dftf3.cu)         folded DFT as a tcgen05 GEMM on CTA pairs; epilogue = |X|^2, un-scale,
 //                                   sparse slaney-mel accumulation (<= 2 taps per FFT bin)
 //   logmel_post_kernel              per chunk: ref = max, 10 log10, -top_db floor, mean/std over ALL
 //                                   F frames (statistics before the crop), z-score, crop/pad, store
 #include "common.cuh"
-#include "gemm3.cuh"
 
 namespace avld {
 
-static int launch_stft_mel_folded(avld_ctx* c, int n, cudaStream_t st) {
-  Gemm3Params P{};
-  const long long rows = static_cast<long long>(n) * c->F;          // only real frames: no junk rows between chunks
-  P.num_m_tiles = static_cast<int>((rows + 127) / 128);
-  P.num_n_tiles = c->n_tiles2;
-  P.num_k_blocks = c->p.n_fft / c->fold_bk;                         // first half: E | cos blocks, second half: O | -sin blocks
-  P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(0, 0, 128, 256);
-  P.idesc_last = avld_make_idesc(0, 0, 128, c->last_tile_bins);
-  P.last_bins = c->last_tile_bins;
-  P.a_mode = 0;
-  P.a_hi_ptr = c->d_A2hi;
-  P.a_lo_ptr = c->d_A2lo;
-  P.a_pitch = static_cast<long long>(c->p.n_fft) * 2;
-  P.M_total = rows;
-  P.N_total = c->ncols;
-  P.inv2 = c->d_inv2;
-  P.taps = c->d_taps;
-  P.melpow = c->d_melpow;
-  P.R = c->F;
-  P.F = c->F;
-  P.n_mels = c->M;
-  P.nbins_pad = c->nbins_pad;
-  // the epilogue accumulates mel outputs with atomicAdd
-  AVLD_CUDA(cudaMemsetAsync(c->d_melpow, 0, static_cast<size_t>(rows) * c->M * sizeof(float), st));
-  LaunchScope ls(c, ST_STFT_MEL, st);
-  return run_gemm3(256, c->fold_bk * 2, EPI_DFTF, c->tm_A2_hi, c->tm_A2_lo, c->tm_B2_hi, c->tm_B2_lo, P, c->sm_count, st);
-}
-
+// M2: folded operand (fold3.cu) -> CTA-pair GEMM with the |X|^2 / mel epilogue (dftf3.cu)
 int launch_stft_mel(avld_ctx* c, int n, cudaStream_t st) {
-  if (c->dft_fold2) {
-    // default: the operand is materialised by fold3_kernel and read back by dftf3_kernel; AVLD_DFT_GEN=1 (experimental,
-    // PCM_16-quantised input only) lets the GEMM build it from a shared-memory span of samples instead (dftg.cu)
-    if (c->cur_quantize && dftg_supported(c)) return launch_stft_mel_gen(c, c->cur_x, c->cur_x16, n, st);
-    AVLD_TRY(launch_fold2(c, n, st));
-    if (dftf4_supported(c)) return launch_stft_mel_fold2_dual(c, n, st);   // opt-in (AVLD_DFT_DUAL=1), not yet run on hardware
-    return launch_stft_mel_fold2(c, n, st);
-  }
-  if (c->dft_fold) {
-    AVLD_TRY(launch_fold(c, n, st));
-    if (c->dft_pair && c->sm_count % 2 == 0) return launch_stft_mel_pair(c, n, st);
-    return launch_stft_mel_folded(c, n, st);
-  }
-  Gemm3Params P{};
-  const long long rows = static_cast<long long>(n) * c->R;
-  P.num_m_tiles = static_cast<int>((rows + 127) / 128);
-  P.num_n_tiles = c->n_tiles_n;
-  P.num_k_blocks = c->kblocks;
-  // all four operands fp16 (kind::f16 rejects mixed fp16 / bf16 operands: "illegal instruction" on sm_100a)
-  P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(0, 0, 128, 256);
-  P.a_mode = 1;
-  P.hpb = c->hpb;
-  P.M_total = rows;
-  P.N_total = c->ncols;
-  P.inv2 = c->d_inv2;
-  P.taps = c->d_taps;
-  P.melpow = c->d_melpow;
-  P.R = c->R;
-  P.F = c->F;
-  P.n_mels = c->M;
-  P.nbins_pad = c->nbins_pad;
-  LaunchScope ls(c, ST_STFT_MEL, st);
-  return run_gemm3(256, 128, EPI_DFT, c->tm_A_hi, c->tm_A_lo, c->tm_B_hi, c->tm_B_lo, P, c->sm_count, st);
+  AVLD_TRY(launch_fold3(c, n, st));
+  return launch_dftf3(c, n, st);
 }
 
 struct PostParams {
-  float* melpow;        // [n*R][M]; fold2: the per-class planes are zeroed again right after they are read, so the
+  float* melpow;        // [planes][rows][M]; the per-class planes are zeroed again right after they are read, so the
                         // GEMM epilogue can accumulate into them on the next pass without a separate memset
-  long long plane2;     // fold2: stride between the per-class planes, added in a fixed order; 0 = single plane
+  long long plane2;     // stride between the per-class planes, added in a fixed order
   int n_planes;
   float* feat;          // [n][T][M]
   int R, F, M, T, crop_start, pad_left, frames_copy;
@@ -186,13 +128,9 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
 
 int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
-  PostParams P{c->d_melpow, c->dft_fold2 ? c->melpow_plane : 0, c->dft_fold2 ? c->f2_classes : 1, feat, c->dft_fold ? c->F : c->R, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
+  PostParams P{c->d_melpow, c->melpow_plane, c->f2_classes, feat, c->F, c->F, c->M, c->T, c->crop_start, c->pad_left, c->frames_copy, c->p.amin, c->p.top_db};
   const size_t smem = static_cast<size_t>(c->F) * c->M * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(logmel_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(logmel_post_kernel), 200 * 1024));
   { LaunchScope ls(c, ST_LOGMEL_POST, st); logmel_post_kernel<<<n, 512, smem, st>>>(P); }
   c->planes_dirty = false;
   AVLD_CUDA(cudaGetLastError());
@@ -218,7 +156,7 @@ static int features_pass(avld_ctx* c, const float* x, float* feat, uint8_t* ok, 
 }
 
 extern "C" int avld_logmel(avld_ctx* c, const float* y, float* feat, int64_t n, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(y && feat, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
@@ -227,7 +165,7 @@ extern "C" int avld_logmel(avld_ctx* c, const float* y, float* feat, int64_t n, 
 
 extern "C" int avld_normalize_logmel(avld_ctx* c, const float* x, float* feat, uint8_t* ok, float* rms, int64_t n,
                                      float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x && feat, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");

@@ -136,7 +136,7 @@ using namespace avld;
 extern "C" int avld_map_score(avld_ctx* c, const float* Z, const float* mean, const float* precision,
                               const double* a_const, const double* log_prior, double tau, int use_tau, int32_t* pred,
                               double* best, double* scores, int64_t n, int32_t K, int32_t D, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(Z && mean && precision && a_const && log_prior && pred && best, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && D >= 1 && D <= 32 * kMapMaxQ, AVLD_ERR_UNSUPPORTED, "need 1 <= D <= %d", 32 * kMapMaxQ);
@@ -152,7 +152,7 @@ extern "C" int avld_map_score(avld_ctx* c, const float* Z, const float* mean, co
 
 extern "C" int avld_cov_accumulate(avld_ctx* c, const float* Z, const int32_t* label, const float* mean, int32_t k_sel,
                                    double* out, int64_t n, int32_t K, int32_t D, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(Z && label && mean && out, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && D >= 1 && k_sel < K, AVLD_ERR_INVALID, "bad K / D / class");

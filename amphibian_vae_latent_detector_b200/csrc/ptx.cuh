@@ -197,6 +197,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "r"(cta)
       : "memory");
 }
+// The same without release semantics.  `mbarrier.arrive.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR
+// in front of the arrive (cuobjdump): the warp waits until every global access it has in flight -- e.g. the ~30 mel
+// reductions of an epilogue item -- is acknowledged by L2.  Where the arrival only says "I am done READING tensor memory"
+// (ordered by tcgen05.wait::ld) or "my TMA loads are issued" (the data is tracked by complete_tx), nothing has to be
+// released and the relaxed form is enough.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // TMA load of a CTA pair: the bytes are counted on the LEADER's mbarrier (same offset, rank bit cleared)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                                  int32_t c1) {

@@ -150,18 +150,14 @@ using namespace avld;
 
 extern "C" int avld_centroid_accumulate(avld_ctx* c, const float* Z, const int32_t* label, double* sum, int64_t* cnt,
                                         int64_t n, int32_t K, int32_t D, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(Z && label && sum && cnt, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && K <= 64 && D >= 1 && static_cast<size_t>(K) * D * 8 <= 96 * 1024, AVLD_ERR_UNSUPPORTED,
              "K must be in [1,64] and K*D*8 <= 96 KB");
   if (n <= 0) return AVLD_OK;
   const size_t smem = static_cast<size_t>(K) * D * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(centroid_kernel), 96 * 1024));
   const long long rows_per_block = std::max<long long>(64, (n + c->sm_count * 4 - 1) / (c->sm_count * 4));
   const int grid = static_cast<int>((n + rows_per_block - 1) / rows_per_block);
   { LaunchScope ls(c, ST_CENTROID, static_cast<cudaStream_t>(stream)); centroid_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, label, sum, reinterpret_cast<long long*>(cnt), n, K, D, rows_per_block); }
@@ -171,17 +167,13 @@ extern "C" int avld_centroid_accumulate(avld_ctx* c, const float* Z, const int32
 
 extern "C" int avld_radii(avld_ctx* c, const float* Z, const float* centroid, float* radii, int64_t n, int32_t K,
                           int32_t D, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(Z && centroid && radii, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1 && D >= 1 && static_cast<size_t>(K) * D * 4 <= 96 * 1024, AVLD_ERR_UNSUPPORTED, "K*D*4 must be <= 96 KB");
   if (n <= 0) return AVLD_OK;
   const size_t smem = static_cast<size_t>(K) * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(radii_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(radii_kernel), 96 * 1024));
   const long long want = (n + 7) / 8;
   const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(c->sm_count) * 8));
   { LaunchScope ls(c, ST_RADII, static_cast<cudaStream_t>(stream)); radii_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(Z, centroid, radii, n, K, D); }
@@ -191,7 +183,7 @@ extern "C" int avld_radii(avld_ctx* c, const float* Z, const float* centroid, fl
 
 extern "C" int avld_decide(avld_ctx* c, const float* radii, const double* thr, const int32_t* priority_rank,
                            int32_t* pred, float* best_d, int64_t n, int32_t K, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(radii && thr && priority_rank && pred && best_d, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(K >= 1, AVLD_ERR_INVALID, "K must be >= 1");
@@ -204,7 +196,8 @@ extern "C" int avld_decide(avld_ctx* c, const float* radii, const double* thr, c
 
 extern "C" int avld_order_stats(avld_ctx* c, const float* radii, const int32_t* label, int64_t n, int32_t K,
                                 const avld_rank_query* queries, int32_t n_q, float* out, void* stream) {
-  AVLD_CHECK(c && radii && label && queries && out, AVLD_ERR_INVALID, "NULL argument");   // an order statistic of
+  AVLD_ENTER(c);
+  AVLD_CHECK(radii && label && queries && out, AVLD_ERR_INVALID, "NULL argument");   // an order statistic of
   AVLD_CHECK(n > 0 && K >= 1 && n_q >= 1 && n_q <= 4096, AVLD_ERR_INVALID, "bad n / K / n_q");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   struct QState { uint32_t lo; int64_t rank; };
@@ -214,11 +207,7 @@ extern "C" int avld_order_stats(avld_ctx* c, const float* radii, const int32_t* 
                AVLD_ERR_INVALID, "query %d is malformed", q);
     qs[q] = {0u, queries[q].rank};
   }
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 * 4));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(select_hist_kernel), 8 * 2048 * 4));
   const uint32_t shifts[3] = {20u, 9u, 0u};
   std::vector<unsigned int> h_hist;
   for (int round = 0; round < 3; ++round) {

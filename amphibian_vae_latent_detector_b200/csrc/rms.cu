@@ -1,6 +1,6 @@
-// rms.cu -- R1/R2: bit-exact batched rms_normalize (00_normalize_dataset_rms.py:29-38) and the
-// operand preparation for the STFT GEMM (reflect padding of librosa.stft's center=True, per-chunk
-// power-of-two scaling, fp16-hi / bf16-lo split), fused in one kernel: one CTA per chunk.
+// rms.cu -- R1/R2: bit-exact batched rms_normalize (00_normalize_dataset_rms.py:29-38) and the per-chunk
+// parameters of the STFT operand (power-of-two scale, normalised PCM_16 integers), fused in one kernel:
+// one CTA per chunk.
 //
 // Bit-exactness: np.mean(y**2) on contiguous float32 walks numpy's pairwise-summation tree
 // (8 interleaved accumulators per <=128-element leaf, halves rounded down to a multiple of 8).
@@ -9,8 +9,8 @@
 // explicitly rounded __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn (no FMA contraction), following
 // numpy-2 float32 scalar semantics for `rms + eps` and `target / (...)`.
 //
-// Memory: phase 1 streams the chunk once (4*L bytes), phase 2 re-reads it (L2-resident: 148 CTAs x
-// 576 KB < 126 MB L2) and writes either y (4*L bytes) or the 16-bit operand pair (4*(L+n_fft) bytes).
+// Memory: phase 1 streams the chunk once (4*L bytes), phase 2 re-reads it and writes either y (4*L bytes,
+// avld_rms_normalize) or the normalised PCM_16 integers (2*L bytes, feature passes).
 #include "common.cuh"
 #include "sample.cuh"
 
@@ -20,10 +20,7 @@ struct PrepParams {
   const float* x;
   const int16_t* x16;     // alternative input: PCM_16 samples, decoded as s / 32768 (librosa.load of a 16-bit WAV)
   float* y;               // nullable
-  __half* a_hi;           // nullable (operand mode)
-  __half* a_lo;
-  float4* chunk_par;      // nullable (folded STFT): per chunk (scale, pow2, scaled flag, -) for fold_kernel, which
-                          // re-applies the normalisation on the fly instead of reading a materialised copy
+  float4* chunk_par;      // nullable (feature passes): per chunk (scale, pow2, scaled flag, -) for fold3_kernel
   float* inv2;
   uint16_t* q16;          // nullable: normalised, PCM_16-rounded samples + 32768 for fold3_kernel (quantize passes)
   uint8_t* ok;            // nullable
@@ -33,11 +30,11 @@ struct PrepParams {
   const PairNode* nodes;
   const int32_t* level_start;
   int n_leaves, n_nodes, n_levels;
-  int L, n_fft, hop, R;
+  int L, n_fft, hop;
   float target_rms, rms_min, eps;
   int normalize, quantize;
   int dft_scale_log2;
-  int headroom_log2;      // max |scaled sample| < 2^(headroom_log2 + 1): 14 (one fold: sums of two) or 13 (two folds)
+  int headroom_log2;      // max |scaled sample| < 2^(headroom_log2 + 1): 13 (sums of up to eight samples stay in fp16 range)
   int n;
 };
 
@@ -229,166 +226,6 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     }
     for (int i = (n8 << 3) + tid; i < P.L; i += blockDim.x) qc[i] = static_cast<uint16_t>(biased(xc(i)));
   }
-
-  // ---------------------------------------------------------------- phase 2b: GEMM operand rows
-  if (P.a_hi != nullptr) {
-    const float pow2 = s_pow2;
-    const int half = P.n_fft / 2;
-    const int total = P.R * P.hop;                       // multiple of 64
-    __half* __restrict__ ah = P.a_hi + static_cast<size_t>(c) * total;
-    __half* __restrict__ al = P.a_lo + static_cast<size_t>(c) * total;
-    for (int v8 = tid; v8 < (total >> 3); v8 += blockDim.x) {
-      const int p0 = v8 << 3;
-      __align__(16) __half hi[8];
-      __align__(16) __half lo[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int p = p0 + q;
-        int src = p - half;                              // np.pad(y, n_fft//2, mode="reflect")
-        if (src < 0) src = -src;
-        if (src >= P.L) src = 2 * (P.L - 1) - src;
-        float v = 0.f;
-        if (p < P.L + P.n_fft) v = finish_sample(xc(src), scale, scaled, P.quantize) * pow2;
-        const __half h = __float2half_rn(v);
-        hi[q] = h;
-        lo[q] = __float2half_rn(v - __half2float(h));
-      }
-      *reinterpret_cast<uint4*>(ah + p0) = *reinterpret_cast<const uint4*>(hi);
-      *reinterpret_cast<uint4*>(al + p0) = *reinterpret_cast<const uint4*>(lo);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fold_kernel: raw chunk -> even/odd folded fp16 hi/lo operand rows (see common.cuh, "folded STFT").
-//   xs[p] = finish(x[reflect(p - N/2)]) * pow2        (normalise, clip, PCM_16 round trip, power-of-two scale)
-//   E[f][j] = xs[f*hop + k] + xs[f*hop + N - k],  O[f][j] = xs[f*hop + k] - xs[f*hop + N - k],  k = j + 1
-//   (k = N/2: E = xs[f*hop + N/2], O = 0).  One thread = 8 consecutive taps of one frame.  The normalisation is
-//   re-applied on the fly (each sample ~10x, from L1/L2) instead of materialising xs: 1.2 MB less HBM traffic per chunk.
-// ------------------------------------------------------------------------------------------------
-struct FoldParams {
-  const float* x;       // [n][L] or NULL
-  const int16_t* x16;   // [n][L] PCM_16 or NULL
-  const float4* chunk_par;
-  __half* a_hi;         // [n*F][n_fft]
-  __half* a_lo;
-  int F, hop, n_fft, L, quantize;
-  int vec_ok;           // chunk rows are 16-byte aligned: interior frames may use vector loads
-  long long total;      // n * F * (n_fft/2/8) threads
-};
-
-template <bool PCM>
-__device__ __forceinline__ float fold_sample(const FoldParams& P, const float* xf, const int16_t* xi, int p, float scale,
-                                             int scaled, float pow2) {
-  int src = p - (P.n_fft >> 1);                         // np.pad(y, n_fft//2, mode="reflect")
-  if (src < 0) src = -src;
-  if (src >= P.L) src = 2 * (P.L - 1) - src;
-  const float v = PCM ? static_cast<float>(xi[src]) * (1.0f / 32768.0f) : xf[src];
-  return finish_sample(v, scale, scaled, P.quantize) * pow2;
-}
-
-template <bool PCM>
-__global__ void __launch_bounds__(256) fold_kernel(const FoldParams P) {
-  const int half = P.n_fft >> 1, per_frame = half >> 3;
-  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < P.total;
-       t += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = t / per_frame;                 // global frame index = chunk * F + f
-    const int j0 = static_cast<int>(t - row * per_frame) << 3;
-    const long long chunk = row / P.F;
-    const int f = static_cast<int>(row - chunk * P.F);
-    const float4 par = P.chunk_par[chunk];
-    const float scale = par.x, pow2 = par.y;
-    const int scaled = par.z != 0.f;
-    const float* xf = PCM ? nullptr : P.x + chunk * P.L;
-    const int16_t* xi = PCM ? P.x16 + chunk * P.L : nullptr;
-    const int pa = f * P.hop + j0;                        // padded index of tap j0 (a[q] is tap j0 + 1 + q)
-    const int pb = f * P.hop + P.n_fft - 8 - j0;          // b[q] is padded index pb + 7 - q
-    float a[8], b[8];
-    const int sa = pa - half, sb = pb - half;             // un-reflected source indices of the two runs
-    if (P.vec_ok && sa >= 0 && sa + 12 <= P.L && sb >= 0 && sb + 8 <= P.L) {
-      // interior: both runs are contiguous in the chunk and 16-byte aligned (hop % 64 == 0, j0 % 8 == 0)
-      float ra[12], rb[8];
-      if (PCM) {
-        const uint4 u0 = *reinterpret_cast<const uint4*>(xi + sa);                 // 8 samples
-        const uint2 u1 = *reinterpret_cast<const uint2*>(xi + sa + 8);             // 4 samples
-        const uint4 w0 = *reinterpret_cast<const uint4*>(xi + sb);
-        const uint32_t wa[6] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y};
-        const uint32_t wb[4] = {w0.x, w0.y, w0.z, w0.w};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          ra[2 * i] = static_cast<float>(static_cast<int16_t>(wa[i] & 0xffffu)) * (1.0f / 32768.0f);
-          ra[2 * i + 1] = static_cast<float>(static_cast<int16_t>(wa[i] >> 16)) * (1.0f / 32768.0f);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          rb[2 * i] = static_cast<float>(static_cast<int16_t>(wb[i] & 0xffffu)) * (1.0f / 32768.0f);
-          rb[2 * i + 1] = static_cast<float>(static_cast<int16_t>(wb[i] >> 16)) * (1.0f / 32768.0f);
-        }
-      } else {
-        const float4* xa = reinterpret_cast<const float4*>(xf + sa);
-        const float4 v0 = xa[0], v1 = xa[1], v2 = xa[2];
-        ra[0] = v0.x; ra[1] = v0.y; ra[2] = v0.z; ra[3] = v0.w; ra[4] = v1.x; ra[5] = v1.y; ra[6] = v1.z; ra[7] = v1.w;
-        ra[8] = v2.x; ra[9] = v2.y; ra[10] = v2.z; ra[11] = v2.w;
-        const float4* xb = reinterpret_cast<const float4*>(xf + sb);
-        const float4 w0 = xb[0], w1 = xb[1];
-        rb[0] = w0.x; rb[1] = w0.y; rb[2] = w0.z; rb[3] = w0.w; rb[4] = w1.x; rb[5] = w1.y; rb[6] = w1.z; rb[7] = w1.w;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        a[q] = finish_sample(ra[q + 1], scale, scaled, P.quantize) * pow2;
-        b[q] = finish_sample(rb[7 - q], scale, scaled, P.quantize) * pow2;
-      }
-    } else {
-      // the first / last frames touch the reflect padding
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        a[q] = fold_sample<PCM>(P, xf, xi, pa + 1 + q, scale, scaled, pow2);
-        b[q] = fold_sample<PCM>(P, xf, xi, pb + 7 - q, scale, scaled, pow2);
-      }
-    }
-    __align__(16) __half eh[8], el[8], oh[8], ol[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const bool mid = (j0 + q == half - 1);             // k = N/2 pairs with itself
-      const float e = mid ? a[q] : a[q] + b[q];
-      const float o = mid ? 0.f : a[q] - b[q];
-      eh[q] = __float2half_rn(e);
-      el[q] = __float2half_rn(e - __half2float(eh[q]));
-      oh[q] = __float2half_rn(o);
-      ol[q] = __float2half_rn(o - __half2float(oh[q]));
-    }
-    const size_t base = static_cast<size_t>(row) * P.n_fft + j0;
-    *reinterpret_cast<uint4*>(P.a_hi + base) = *reinterpret_cast<const uint4*>(eh);
-    *reinterpret_cast<uint4*>(P.a_lo + base) = *reinterpret_cast<const uint4*>(el);
-    *reinterpret_cast<uint4*>(P.a_hi + base + half) = *reinterpret_cast<const uint4*>(oh);
-    *reinterpret_cast<uint4*>(P.a_lo + base + half) = *reinterpret_cast<const uint4*>(ol);
-  }
-}
-
-int launch_fold(avld_ctx* c, int n, cudaStream_t st) {
-  if (n <= 0) return AVLD_OK;
-  FoldParams P{};
-  P.x = c->cur_x;
-  P.x16 = c->cur_x16;
-  P.chunk_par = c->d_chunk_par;
-  P.a_hi = c->d_A2hi;
-  P.a_lo = c->d_A2lo;
-  P.F = c->F;
-  P.hop = c->p.hop;
-  P.n_fft = c->p.n_fft;
-  P.L = c->L;
-  P.quantize = c->cur_quantize;
-  P.vec_ok = (c->L % 8 == 0) && (reinterpret_cast<uintptr_t>(P.x) % 16 == 0) && (reinterpret_cast<uintptr_t>(P.x16) % 16 == 0);
-  P.total = static_cast<long long>(n) * c->F * (c->p.n_fft / 16);
-  const long long blocks = (P.total + 255) / 256;
-  const int grid = static_cast<int>(blocks < static_cast<long long>(c->sm_count) * 32 ? blocks : static_cast<long long>(c->sm_count) * 32);
-  {
-    LaunchScope ls(c, ST_FOLD, st);
-    if (P.x16 != nullptr) fold_kernel<true><<<grid, 256, 0, st>>>(P);
-    else fold_kernel<false><<<grid, 256, 0, st>>>(P);
-  }
-  AVLD_CUDA(cudaGetLastError());
-  return AVLD_OK;
 }
 
 int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
@@ -398,15 +235,13 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.x = x;
   P.x16 = x16;
   P.y = y_out;
-  P.a_hi = (write_operand && !c->dft_fold) ? c->d_Ahi : nullptr;
-  P.a_lo = (write_operand && !c->dft_fold) ? c->d_Alo : nullptr;
-  P.chunk_par = (write_operand && c->dft_fold) ? c->d_chunk_par : nullptr;
-  if (write_operand) {      // operand source of this pass, consumed by launch_fold
+  P.chunk_par = write_operand ? c->d_chunk_par : nullptr;
+  if (write_operand) {      // operand source of this pass, consumed by launch_fold3
     c->cur_x = x;
     c->cur_x16 = x16;
     c->cur_quantize = quantize ? 1 : 0;
     // the uint4 stores of phase 2c need 16-byte aligned chunk rows
-    c->cur_q16 = (quantize && c->dft_fold2 && c->f2_levels == 3 && c->d_q16 && (c->L & 7) == 0) ? c->d_q16 : nullptr;
+    c->cur_q16 = (quantize && c->d_q16 && (c->L & 7) == 0) ? c->d_q16 : nullptr;
     P.q16 = c->d_q16 && c->cur_q16 ? c->d_q16 : nullptr;
   }
   P.inv2 = write_operand ? c->d_inv2 : nullptr;
@@ -422,20 +257,15 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.L = c->L;
   P.n_fft = c->p.n_fft;
   P.hop = c->p.hop;
-  P.R = c->R;
   P.target_rms = target_rms;
   P.rms_min = rms_min;
   P.eps = eps;
   P.normalize = normalize ? 1 : 0;
   P.quantize = quantize ? 1 : 0;
   P.dft_scale_log2 = c->dft_scale_log2;
-  P.headroom_log2 = c->dft_fold2 ? 13 : 14;
+  P.headroom_log2 = 13;
   const size_t smem = static_cast<size_t>(c->n_leaves + c->n_nodes + 1) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    AVLD_CUDA(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 164 * 1024));
-    configured = true;
-  }
+  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(prep_kernel), 164 * 1024));
   P.n = n;
   { LaunchScope ls(c, ST_PREP, st); prep_kernel<<<n, 512, smem, st>>>(P); }
   AVLD_CUDA(cudaGetLastError());
@@ -448,7 +278,7 @@ using namespace avld;
 
 extern "C" int avld_rms_normalize(avld_ctx* c, const float* x, float* y, uint8_t* ok, float* rms, int64_t n,
                                   float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream) {
-  AVLD_CHECK(c != nullptr, AVLD_ERR_INVALID, "ctx is NULL");
+  AVLD_ENTER(c);
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x && y, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");

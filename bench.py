@@ -72,7 +72,7 @@ def traffic_of(mode: str, chunks_per_launch: int):
         d = json.loads(p.read_text())
     except Exception:
         return None
-    kernel = {"fold3": "dftf3_kernel", "fold2": "dftf3_kernel", "fold": "dftf2_kernel"}.get(mode)   # bytes, per launch
+    kernel = "dftf3_kernel"   # bytes, per launch
     if d.get("kernel") != kernel or d.get("mode", "fold2") != mode or int(d.get("chunks_per_launch", 0)) != int(chunks_per_launch):
         return None
     return d["traffic_bytes"]
@@ -397,24 +397,20 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        dft = stages["gemm3_kernel<DFT>"]
+        dft = stages["dftf3_kernel"]
         chunks_timed = n * args.steps
         dft_tflops = DFT_FLOP_PER_CHUNK * chunks_timed / (dft["ms"] / 1e3) / 1e12 if dft["ms"] > 0 else None
         stage_ms = {k: round(v["ms"] / args.steps, 3) for k, v in stages.items() if v["timed_launches"]}
         kernel_ms = sum(stage_ms.values())
         hbm = {}
         prep = stages["prep_kernel"]
-        if prep["ms"] > 0:   # reads 4L, writes fp16 hi+lo operand rows incl. reflect padding: 4 * 381 * 384 bytes
-            hbm["prep_kernel"] = round((4 * CHUNK_LEN + 4 * 381 * 384) * chunks_timed / (prep["ms"] / 1e3) / 1e9, 1)
-        fold = stages.get("fold_kernel")
-        if fold and fold["ms"] > 0:   # reads the chunk once from HBM (re-reads hit L1/L2), writes the folded hi+lo rows
-            hbm["fold_kernel"] = round((4 * CHUNK_LEN + 4 * 376 * 2048) * chunks_timed / (fold["ms"] / 1e3) / 1e9, 1)
+        if prep["ms"] > 0:   # reads the float32 chunk (4 L), writes the normalised PCM_16 integers (2 L)
+            hbm["prep_kernel"] = round(6 * CHUNK_LEN * chunks_timed / (prep["ms"] / 1e3) / 1e9, 1)
+        fold = stages.get("fold3_kernel")
+        if fold and fold["ms"] > 0:   # reads the integers once (2 L; re-reads hit L1/L2), writes the folded hi+lo tiles
+            hbm["fold3_kernel"] = round((2 * CHUNK_LEN + 4 * 376 * 2048) * chunks_timed / (fold["ms"] / 1e3) / 1e9, 1)
         info = eng_info
-        kname = {"fold3": "dftf3_kernel (windowed DFT as GEMM, folded twice and a third time for the even bins, cta_group::2, + |X|^2 + mel)",
-                 "fold2": "dftf3_kernel (twice-folded windowed DFT as GEMM, cta_group::2, + |X|^2 + mel)",
-                 "fold": "dftf2_kernel (once-folded windowed DFT as GEMM, cta_group::2, + |X|^2 + mel)",
-                 "fold1": "gemm3_kernel<256,*,EPI_DFTF> (once-folded windowed DFT as GEMM + |X|^2 + mel)",
-                 "direct": "gemm3_kernel<256,128,EPI_DFT> (windowed DFT as GEMM + |X|^2 + mel)"}[info["mode"]]
+        kname = "dftf3_kernel (windowed DFT as GEMM, folded three times, cta_group::2, + |X|^2 + mel)"
         issued_tflops = (info["issued_flops_per_chunk"] * chunks_timed / (dft["ms"] / 1e3) / 1e12) if dft["ms"] > 0 else None
         roofline = {
             "bound": "tensor", "kernel": kname,
@@ -435,7 +431,7 @@ def main():
                     "tensor_pipe_frac (issued flops / peak) is the utilisation of the pipe; the kernel is L2->SM-feed bound",
             "dft_mode": info["mode"], "chunks_per_launch": args.max_batch,
             "avg_launch_ms": dft["ms"] / max(dft["timed_launches"], 1), "traffic": traffic_of(info["mode"], args.max_batch),
-            "share_of_kernel_time": (stage_ms.get("gemm3_kernel<DFT>", 0.0) / kernel_ms) if kernel_ms else None}
+            "share_of_kernel_time": (stage_ms.get("dftf3_kernel", 0.0) / kernel_ms) if kernel_ms else None}
         line = {
             "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

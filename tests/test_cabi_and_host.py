@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
     assert lib.avld_abi_version() == 1
     names = [lib.avld_stage_name(i).decode() for i in range(lib.avld_stage_count())]
-    assert "prep_kernel" in names and "gemm3_kernel<DFT>" in names
+    assert "prep_kernel" in names and "dftf3_kernel" in names and "fold3_kernel" in names
 
 
 def test_no_cpu_fallback():

@@ -95,16 +95,21 @@ def test_unsupported_geometry_fails_loudly():
     eng.close()
     with pytest.raises(ValueError):
         Engine(0, chunk_len=L, max_batch=4).logmel(torch.zeros(2, L))          # CPU tensor: no silent host path
-    # more FFT bins with mel weight than the kernels keep tap records for (875): refused at context creation
+    # more FFT bins with mel weight than the STFT kernel has work items for (12 x 160 bins per class split): refused at
+    # context creation, and so is an n_fft the folded GEMM cannot tile
     with pytest.raises(_lib.AvldError) as e:
-        Engine(0, chunk_len=L, max_batch=4, sr=32000, n_fft=2048, fmin=50.0, fmax=14000.0)
+        Engine(0, chunk_len=L, max_batch=4, sr=48000, n_fft=8192, fmin=0.0, fmax=24000.0)
     assert e.value.code == -3                       # AVLD_ERR_UNSUPPORTED
+    with pytest.raises(_lib.AvldError) as e:
+        Engine(0, chunk_len=L, max_batch=4, n_fft=1000, hop_length=250)
+    assert e.value.code == -3
 
 
 @pytest.mark.parametrize("kw", [
     dict(sr=48000, n_fft=1024, hop_length=256, n_mels=40, fmin=300.0, fmax=12000.0, target_frames=128),
     dict(sr=32000, n_fft=2048, hop_length=512, n_mels=64, fmin=50.0, fmax=11000.0, target_frames=96),
     dict(sr=48000, n_fft=2048, hop_length=384, n_mels=128, fmin=150.0, fmax=15000.0, target_frames=192),
+    dict(sr=32000, n_fft=2048, hop_length=512, n_mels=62, fmin=50.0, fmax=14000.0, target_frames=96),   # 7 work items; n_mels % 4 != 0: scalar reductions
 ])
 def test_other_feature_parameters_vs_oracle(kw):
     """The kernels are not specialised to the CLI defaults: other n_fft / hop / n_mels / band limits against the oracle."""

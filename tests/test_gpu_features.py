@@ -116,32 +116,6 @@ def test_feature_properties_full_batch(engine3s):
     assert rel(feat[2], feat[1]) < 1e-4
 
 
-def test_in_kernel_operand_generation_matches_default(monkeypatch):
-    """AVLD_DFT_GEN=1 (dftg.cu: the GEMM builds its folded operand from a shared-memory span of samples instead of reading
-    what fold3_kernel materialised): same features as the default path to fp32 rounding, for float32 and PCM_16 input,
-    ragged batch, chunks that hit the gate / clip, and the reference fixtures."""
-    from amphibian_vae_latent_detector_b200 import synth
-    from amphibian_vae_latent_detector_b200.engine import Engine
-    x, _ = synth.make_chunks(37, 144000, seed=31, special_every=9)
-    eng = Engine(0, chunk_len=144000, max_batch=16)
-    base, ok0, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-    monkeypatch.setenv("AVLD_DFT_GEN", "1")
-    gen, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-    assert torch.equal(ok0, ok1)
-    assert rel(gen.cpu().numpy(), base.cpu().numpy()) < 2e-5
-    for key in ("noise_3s", "tonal_3s", "hot_3s", "silent_3s"):
-        xg, d = _prep(key)
-        feat, _, _ = eng.normalize_logmel(torch.from_numpy(xg[None]).cuda(), pcm16=True)
-        assert rel(feat.cpu().numpy()[0], d["feat"].T) < FEAT_TOL, key
-    eng.close()
-    eng5 = Engine(0, chunk_len=240000, max_batch=4)                  # 5 s: 626 frames = 5 tiles per chunk, the last one short
-    for key in ("pulsed_5s", "tonal_5s"):
-        xg, d = _prep(key)
-        feat, _, _ = eng5.normalize_logmel(torch.from_numpy(np.stack([xg, xg, xg])).cuda(), pcm16=True)
-        assert rel(feat.cpu().numpy()[2], d["feat"].T) < FEAT_TOL, key
-    eng5.close()
-
-
 def test_prequantised_operand_source_is_bit_identical(monkeypatch, standin_encoder):
     """Default path: prep_kernel leaves the normalised PCM_16 integers (pcm16_of, four instructions) and fold3_kernel<2> reads
     them; AVLD_NO_Q16=1: fold3_kernel<0/1> re-normalises every sample on the fly (finish_sample).  Same bits out, for float32
@@ -178,25 +152,3 @@ def test_prequantised_operand_source_is_bit_identical(monkeypatch, standin_encod
     assert np.array_equal(np.isnan(a), np.isnan(b))
     assert np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
     assert np.isnan(a[5]).all() and np.isnan(a[6]).all() and np.isnan(a[7]).all() and not np.isnan(a[[0, 1, 2, 3, 4, 8, 9]]).any()
-
-
-@pytest.mark.skipif(os.environ.get("AVLD_TEST_DUAL", "0") in ("", "0"),
-                    reason="dftf4.cu (AVLD_DFT_DUAL=1) was written after round 1's GPU budget was spent and has not run on a "
-                           "B200 yet; set AVLD_TEST_DUAL=1 to bring it up")
-def test_dual_tile_kernel_matches_default(monkeypatch):
-    """AVLD_DFT_DUAL=1 (dftf4.cu: both tiles of the odd bin class per pass over its A columns): the accumulation order of
-    every output element is that of dftf3.cu, so the features must be bit-identical -- ragged batch, gate / clip chunks,
-    3 s and 5 s geometry."""
-    from amphibian_vae_latent_detector_b200 import synth
-    from amphibian_vae_latent_detector_b200.engine import Engine
-    for chunk_len, n, mb in ((144000, 37, 16), (240000, 7, 4)):
-        x, _ = synth.make_chunks(n, chunk_len, seed=31, special_every=9)
-        eng = Engine(0, chunk_len=chunk_len, max_batch=mb)
-        base, ok0, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-        for mode in os.environ.get("AVLD_TEST_DUAL_MODES", "1,2").split(","):     # 1: CTA pairs, 2: + B multicast (4-CTA clusters)
-            monkeypatch.setenv("AVLD_DFT_DUAL", mode)
-            dual, ok1, _ = eng.normalize_logmel(x.cuda(), pcm16=True)
-            monkeypatch.delenv("AVLD_DFT_DUAL")
-            assert torch.equal(ok0, ok1), mode
-            assert torch.equal(dual, base), mode
-        eng.close()
