@@ -12,10 +12,10 @@
 //                               half (80 rows) of the B tile
 //   warp 1 (leader only)        MMA issuer: tcgen05.mma.cta_group::2 (M 256, N 160), commits multicast to both CTAs
 //   warps 2..9    (both CTAs)   epilogue, once the item's Im is complete: Re and Im streamed from TMEM 16 columns at a time
-//                               (the next group's loads in flight under the current group's math); edge term and |X|^2
-//                               for the 16 columns without a branch, then the sparse slaney mel accumulation (band
-//                               transitions are warp uniform), un-scale, vector reductions (four mel bands per
-//                               red.global.add.v4.f32) into the class's plane.
+//                               (the next group's loads in flight under the current group's math); edge
+//                               term, |X|^2, sparse slaney mel accumulation (band changes are warp-uniform branches),
+//                               un-scale, vector reductions (four mel bands per red.global.add.v4.f32) into the class's
+//                               plane.
 // Bit-reproducible: a warp covers 80 consecutive bins of one class (160 FFT bins), a mel filter spans <= 67 FFT bins, so
 // every (frame, filter, class plane) cell receives at most two non-zero contributions (a + b is order independent; the
 // zeros that pad a group of four bands do not change a sum).
@@ -50,7 +50,7 @@ struct Dftf3Params {
   int F, n_mels;
   int dbg;                  // AVLD_BRINGUP builds only (always 0 otherwise): 1 = skip the epilogue math, 4 = no operand
                             // loads after the first pipeline fill (MMA issue rate alone), 8 / 16 = no A / no B loads after
-                            // the first fill, 32 = one MMA pass (hi x hi) instead of three, 64 = cycle counters into `prof`, 128 = no reductions
+                            // the first fill, 32 = one MMA pass (hi x hi) instead of three, 64 = cycle counters into `prof`
   unsigned long long* prof; // [grid][8] (bring-up)
 };
 
@@ -71,40 +71,46 @@ constexpr int kABytes = kBM * kSwz;              // one of hi / lo: 16 KB
 constexpr int kBBytes = (kBN / 2) * kSwz;        // this CTA's 80 rows: 10 KB
 constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;   // 52 KB
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;
-constexpr int kWarpCols = kBN / 2;               // 80 accumulator columns per epilogue warp
+constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter (16 warps of 40 columns measured the same time:
+                                                 // the epilogue is bound by its instruction count, not by latency)
+constexpr int kWarpCols = kBN / (kEpiWarps / 4); // 80 accumulator columns per epilogue warp
+constexpr int kGC = 16;                          // columns per tcgen05.ld in the column loop
 constexpr int kExtra = 512 + kEpiWarps * kWarpCols * static_cast<int>(sizeof(MelTap));   // barriers + per-warp tap records
 constexpr int kSmemBytes = kStages * kStageBytes + kExtra + 1024;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kGroups = kWarpCols / 16;          // 5 tcgen05.ld x16 per half
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+constexpr int kGroups = kWarpCols / kGC;         // 5 loads of Re and of Im per item and warp
 static_assert(kGroups % 2 == 1, "the epilogue's column loop handles pairs of groups plus one");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // four consecutive mel bands of one frame row in one L2 reduction
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   // no "memory" clobber: the kernel never reads the planes back, and a clobber would pin every shared-memory load of the
-  // epilogue behind the previous reduction (the compiler then serialises load -> math -> branch per column)
+  // epilogue behind the previous reduction
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
-// Mel accumulation of one frame row over an item's bins.  Bands are visited in ascending order (`first` is monotone within
-// an item, warp uniform); a finished band goes through a four-deep shift register and leaves as an aligned group of four.
+// Mel accumulation of one frame row (= one thread) over its warp's bins of an item.  Every bin feeds the bands `first` and
+// `first + 1` (slaney triangles overlap pairwise); `first` is warp uniform and monotone over the item's bins, so a running
+// pair (a0, a1) = partial sums of the bands (mcur, mcur + 1) is enough.  A finished band goes through a four-deep shift
+// register and leaves as an aligned group of four (VEC), or as a scalar reduction when n_mels is not a multiple of four.
+// Rows past the end of the batch (tail of the last tile) are not masked: their un-scale factor s2 is 0 and the operand rows
+// behind them hold finite stale values, so they add exact zeros to plane rows nobody reads in this pass.
 template <bool VEC>
 struct MelSink {
-  float* mrow;
-  float s2;
+  float* pcur;            // address of band `mcur` in this frame row of the class's plane
+  float s2;               // un-scale factor: a power of two, 0 (row past the batch) or NaN (poisoned chunk)
   int mcur, n_mels;
-  bool valid;
   float q0, q1, q2, q3;
   __device__ __forceinline__ void emit(float acc) {          // band `mcur` is complete
-    const float val = acc * s2;                              // s2 is a power of two (or NaN: poisoned chunk)
+    const float val = acc * s2;
     if (VEC) {
       q0 = q1; q1 = q2; q2 = q3; q3 = val;
-      if ((mcur & 3) == 3 && valid) red_add_v4(mrow + (mcur - 3), q0, q1, q2, q3);
-    } else if (valid && val != 0.f) {
-      atomicAdd(mrow + mcur, val);
+      if ((mcur & 3) == 3) red_add_v4(pcur - 3, q0, q1, q2, q3);
+    } else if (val != 0.f) {
+      atomicAdd(pcur, val);
     }
     ++mcur;
+    ++pcur;
   }
   __device__ __forceinline__ void finish(float a0, float a1) {
     if (mcur < n_mels) emit(a0);
@@ -114,40 +120,34 @@ struct MelSink {
   }
 };
 
-// One group of 16 accumulator columns (bins col0 .. col0 + 15 of the warp's 80): edge term and |X|^2 without a branch (16
-// independent chains), then the slaney mel accumulation -- every bin feeds the bands `first` and `first + 1`; `first` is
-// warp uniform and monotone, so a band change is a uniform branch.  The column loop of the epilogue is kept ROLLED around
-// this body (three copies in the kernel): fully unrolled, the epilogue was 80 KB of code whose taken branches over the
-// band-change blocks missed the instruction cache at every column (~180 cycles per column, measured).
+// kGC accumulator columns: edge term and |X|^2 (independent chains), then the mel accumulation; a band change is a warp-
+// uniform branch
 template <bool VEC>
-__device__ __forceinline__ void mel_group(const uint32_t (&re)[16], const uint32_t (&im)[16], const MelTap* taps, float e_re,
+__device__ __forceinline__ void mel_group(const uint32_t (&re)[kGC], const uint32_t (&im)[kGC], const MelTap* taps, float e_re,
                                           float e_im, MelSink<VEC>& sink, float& a0, float& a1) {
-  float pw[16];
+  MelTap tp[kGC];         // all tap records of the group first (independent 16-byte shared-memory loads)
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float coef = __int_as_float(taps[j].pad);
+  for (int j = 0; j < kGC; ++j) tp[j] = taps[j];
+  float pw[kGC];
+#pragma unroll
+  for (int j = 0; j < kGC; ++j) {
+    const float coef = __int_as_float(tp[j].pad);
     const float a = fmaf(e_re, coef, __uint_as_float(re[j]));
     const float b = fmaf(e_im, coef, __uint_as_float(im[j]));
     pw[j] = fmaf(a, a, b * b);
   }
 #pragma unroll
-  for (int j0 = 0; j0 < 16; j0 += 4) {
-    MelTap tp[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) tp[u] = taps[j0 + u];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (sink.mcur < tp[u].first) {
+  for (int j = 0; j < kGC; ++j) {
+    if (sink.mcur < tp[j].first) {
 #pragma unroll 1
-        do {
-          sink.emit(a0);
-          a0 = a1;
-          a1 = 0.f;
-        } while (sink.mcur < tp[u].first);
-      }
-      a0 = fmaf(tp[u].w0, pw[j0 + u], a0);
-      a1 = fmaf(tp[u].w1, pw[j0 + u], a1);
+      do {
+        sink.emit(a0);
+        a0 = a1;
+        a1 = 0.f;
+      } while (sink.mcur < tp[j].first);
     }
+    a0 = fmaf(tp[j].w0, pw[j], a0);
+    a1 = fmaf(tp[j].w1, pw[j], a1);
   }
 }
 }  // namespace
@@ -166,7 +166,7 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* re_empty = acc_full + 1;                          // [2]  Re_A / Re_B drained (leader)
   uint64_t* im_empty = re_empty + 2;                          // [1]  Im drained (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(im_empty + 1);
-  MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);     // [kEpiWarps][80]: each epilogue warp's bins of its current item
+  MelTap* s_taps = reinterpret_cast<MelTap*>(tail + 512);     // [kEpiWarps][kWarpCols]: each epilogue warp's bins of its current item
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -357,7 +357,7 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     };
     for (int pair = cluster; pair < P.num_pairs; pair += n_clusters) {
       const long long g = static_cast<long long>(pair) * 2 * kBM + static_cast<long long>(rank) * kBM + row;
-      const bool valid = g < P.M_total && !(dbg_of(P) & 128);      // 128: all the epilogue math, no reductions
+      const bool valid = g < P.M_total;
       const float s2 = valid ? P.inv2[g / P.F] : 0.f;
       const float4 edge = valid ? P.edge[g] : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int it = 0; it < P.num_items; ++it, ++n_item) {
@@ -366,9 +366,10 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float e_cls = cls == 0 ? edge.x : (cls == 1 ? edge.y : edge.z);
         const float e_re = P.item[it].edge_im ? 0.f : e_cls, e_im = P.item[it].edge_im ? e_cls : 0.f;
         const uint32_t t_re = t_acc + (n_item & 1u) * static_cast<uint32_t>(kReColB), t_im = t_acc + static_cast<uint32_t>(kImCol);
-        // this warp's 80 tap records of the item: fetched (L2) before the wait, parked in shared memory for the column loop
+        // this warp's tap records of the item: fetched (L2) before the wait, parked in shared memory for the column loop
         {
           const uint4* gt = reinterpret_cast<const uint4*>(P.taps + it * kBN + b0);
+          static_assert(kWarpCols > 64 && kWarpCols <= 96, "tap staging below assumes three rounds");
           const uint4 tr0 = __ldg(gt + lane), tr1 = __ldg(gt + 32 + lane);
           const uint4 tr2 = lane < kWarpCols - 64 ? __ldg(gt + 64 + lane) : make_uint4(0u, 0u, 0u, 0u);
           reinterpret_cast<uint4*>(my_taps)[lane] = tr0;
@@ -382,26 +383,34 @@ dftf3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           AVLD_PROF_ADD(prof_wait0, tw);
         }
         tcgen05_fence_after();
-        MelSink<VEC> sink{P.melpow + cls * P.plane_stride + g * P.n_mels, s2, my_taps[0].first, P.n_mels, valid, 0.f, 0.f, 0.f, 0.f};
+        const int m_first = my_taps[0].first;
+        MelSink<VEC> sink{P.melpow + cls * P.plane_stride + g * P.n_mels + m_first, s2, m_first, P.n_mels, 0.f, 0.f, 0.f, 0.f};
         float a0 = 0.f, a1 = 0.f;
-        uint32_t re0[16], im0[16], re1[16], im1[16];
+        // Column loop: groups of kGC columns, the next group's Re / Im travelling from TMEM under the current group's math
+        // (two register buffers, so the loop is rolled around a pair of groups plus one).  Fully unrolled -- 80 column
+        // bodies, each with a taken branch over its band-change block, 80 KB of code -- the eight epilogue warps ran at
+        // ~180 cycles per column, bound by instruction fetch; with three copies of the group body it is ~110, and what is
+        // left is the per-column uniform branch itself (BSSY / BRA / BSYNC, ~45 cycles with two warps per scheduler;
+        // profiles/r02b_dftf3_source_hotspots.txt).  A single copy in a loop of ten 8-column groups, 16 epilogue warps of
+        // 40 columns, or predicated band changes with scalar reductions measured no better (1.08 / 1.02 / 1.25 ms vs 1.01).
+        uint32_t re0[kGC], im0[kGC], re1[kGC], im1[kGC];
         tmem_ld16(t_re, re0);
         tmem_ld16(t_im, im0);
 #pragma unroll 1
-        for (int q = 0; q < kGroups - 1; q += 2) {      // groups q (buffer 0) and q + 1 (buffer 1); the next group travels
-          tmem_ld_wait();                               // while the current one is worked on
-          tmem_ld16(t_re + (q + 1) * 16, re1);
-          tmem_ld16(t_im + (q + 1) * 16, im1);
-          if (!skip) mel_group<VEC>(re0, im0, my_taps + q * 16, e_re, e_im, sink, a0, a1);
+        for (int q = 0; q < kGroups - 1; q += 2) {
           tmem_ld_wait();
-          tmem_ld16(t_re + (q + 2) * 16, re0);
-          tmem_ld16(t_im + (q + 2) * 16, im0);
-          if (!skip) mel_group<VEC>(re1, im1, my_taps + (q + 1) * 16, e_re, e_im, sink, a0, a1);
+          tmem_ld16(t_re + (q + 1) * kGC, re1);
+          tmem_ld16(t_im + (q + 1) * kGC, im1);
+          if (!skip) mel_group<VEC>(re0, im0, my_taps + q * kGC, e_re, e_im, sink, a0, a1);
+          tmem_ld_wait();
+          tmem_ld16(t_re + (q + 2) * kGC, re0);
+          tmem_ld16(t_im + (q + 2) * kGC, im0);
+          if (!skip) mel_group<VEC>(re1, im1, my_taps + (q + 1) * kGC, e_re, e_im, sink, a0, a1);
         }
         tmem_ld_wait();
         release(im_empty);                   // all of this warp's columns are in registers: the issuer may overwrite Im
         release(&re_empty[n_item & 1u]);     // (next sin part) and this Re buffer (the item after the next)
-        if (!skip) mel_group<VEC>(re0, im0, my_taps + (kGroups - 1) * 16, e_re, e_im, sink, a0, a1);
+        if (!skip) mel_group<VEC>(re0, im0, my_taps + (kGroups - 1) * kGC, e_re, e_im, sink, a0, a1);
         if (!skip) sink.finish(a0, a1);
         __syncwarp();                        // every lane is done with my_taps before the next item overwrites it
       }
@@ -441,7 +450,6 @@ int launch_dftf3(avld_ctx* c, int n, cudaStream_t st) {
   P.plane_stride = c->melpow_plane;
   P.F = c->F;
   P.n_mels = c->M;
-  const bool vec = (c->M % 4 == 0) && (c->melpow_plane % 4 == 0);
   P.dbg = 0;
   P.prof = nullptr;
 #ifdef AVLD_BRINGUP
@@ -465,6 +473,7 @@ int launch_dftf3(avld_ctx* c, int n, cudaStream_t st) {
   c->planes_dirty = true;
   const int grid = 2 * std::min(P.num_pairs, c->sm_count / 2);
   if (grid < 2) return AVLD_OK;
+  const bool vec = (c->M % 4 == 0) && (c->melpow_plane % 4 == 0);
   AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(dftf3_kernel<true>), kSmemBytes));
   AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(dftf3_kernel<false>), kSmemBytes));
   {

@@ -36,4 +36,3 @@ run noloads       AVLD_DBG=68
 run no_a          AVLD_DBG=72
 run no_b          AVLD_DBG=80
 run onepass       AVLD_DBG=96
-run no_red        AVLD_DBG=192
