@@ -49,6 +49,7 @@ _SIGNATURES = {
     "avld_ctx_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(_P)]),
     "avld_ctx_destroy": (None, [_P]),
     "avld_ctx_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "avld_ctx_set_normalization": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),
     "avld_ctx_dft_info": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "avld_profile_enable": (C.c_int, [_P, C.c_int]),
     "avld_profile_collect": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_int]),

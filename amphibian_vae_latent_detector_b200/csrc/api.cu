@@ -92,8 +92,9 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
   AVLD_CUDA(cudaMemcpyAsync(c->d_thr, thr, K * sizeof(double), cudaMemcpyHostToDevice, sc));
   AVLD_CUDA(cudaMemcpyAsync(c->d_prio, priority_rank, K * sizeof(int32_t), cudaMemcpyHostToDevice, sc));
 
-  // AVLD_HOST_TRACE=<file>: per-slab device timeline (copy start/end, compute start/end, ms since the first copy)
-  const char* trace_path = getenv("AVLD_HOST_TRACE");
+  // AVLD_HOST_TRACE=<file> (read once, at context creation): per-slab device timeline (copy start/end, compute start/end,
+  // ms since the first copy)
+  const char* trace_path = c->host_trace_path.empty() ? nullptr : c->host_trace_path.c_str();
   std::vector<cudaEvent_t> tev;
   auto mark = [&](cudaStream_t s) {
     if (!trace_path) return;
@@ -122,8 +123,8 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     }
     if (n >= 2 * mb) sizes.push_back(static_cast<int>(q));
   }
-  int64_t slab = 0, i = 0;
-  for (; slab < static_cast<int64_t>(sizes.size()); i += sizes[slab], ++slab) {
+  // one slab; any failure leaves copies / kernels in flight on both streams, so the caller drains them before returning
+  auto run_slab = [&](int64_t slab, int64_t i) -> int {
     const int m = sizes[slab];
     const int b = static_cast<int>(slab & 1);
     if (slab >= 2) AVLD_CUDA(cudaStreamWaitEvent(sx, c->ev_done[b], 0));   // buffer b free again
@@ -136,7 +137,8 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     mark(sc);
     AVLD_TRY(encode_pass(c, sample_bytes == 4 ? c->d_xbuf[b] : nullptr,
                          sample_bytes == 2 ? reinterpret_cast<const int16_t*>(c->d_xbuf[b]) : nullptr, c->d_mu, c->d_ok, m,
-                         0.05f, 1e-4f, 1e-8f, quantize_pcm16, sc));
+                         static_cast<float>(c->norm_target), static_cast<float>(c->norm_rms_min),
+                         static_cast<float>(c->norm_eps), quantize_pcm16, sc));
     AVLD_CUDA(cudaEventRecord(c->ev_done[b], sc));                         // x buffer consumed by the prep kernel
     AVLD_TRY(avld_radii(c, c->d_mu, c->d_cent, c->d_radii, m, K, D, sc));
     AVLD_TRY(avld_decide(c, c->d_radii, c->d_thr, c->d_prio, c->d_pred, c->d_best, m, K, sc));
@@ -147,9 +149,23 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     if (ok_host)
       AVLD_CUDA(cudaMemcpyAsync(s_ok + i, c->d_ok, static_cast<size_t>(m), cudaMemcpyDeviceToHost, sc));
     mark(sc);
+    return AVLD_OK;
+  };
+  int rc = AVLD_OK;
+  {
+    int64_t i = 0;
+    for (int64_t slab = 0; slab < static_cast<int64_t>(sizes.size()) && rc == AVLD_OK; i += sizes[slab], ++slab) rc = run_slab(slab, i);
   }
-  AVLD_CUDA(cudaStreamSynchronize(sc));
-  AVLD_CUDA(cudaStreamSynchronize(sx));
+  const cudaError_t e_sc = cudaStreamSynchronize(sc), e_sx = cudaStreamSynchronize(sx);
+  if (rc != AVLD_OK || e_sc != cudaSuccess || e_sx != cudaSuccess) {
+    // nothing of this call is in flight any more: the next call may reuse the slab buffers, d_cent and the staging area
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    if (rc == AVLD_OK) {
+      set_error("avld_encode_detect_host: %s", cudaGetErrorString(e_sc != cudaSuccess ? e_sc : e_sx));
+      rc = AVLD_ERR_CUDA;
+    }
+    return rc;
+  }
   if (trace_path && !tev.empty()) {
     if (FILE* f = fopen(trace_path, "w")) {
       fprintf(f, "slab copy_start copy_end compute_start compute_end (ms)\n");

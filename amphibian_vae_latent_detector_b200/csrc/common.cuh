@@ -79,6 +79,13 @@ struct avld_ctx {
   int sm_count = 0;
   int smem_optin = 0;
 
+  // R1 constants and scalar arithmetic of rms_normalize (avld_ctx_set_normalization).  scalar_f64 = 0: numpy >= 2 rules
+  // (`rms + eps` and `target / (...)` in float32, the gate against float32(rms_min)); 1: numpy 1.x value-based casting, what
+  // the reference's pinned numpy==1.26.4 executes (both scalar operations and the gate comparison in float64, the scale
+  // rounded to float32 once).  The per-call float parameters of the ABI are used in mode 0, these doubles in mode 1.
+  int scalar_f64 = 0;
+  double norm_target = 0.05, norm_rms_min = 1e-4, norm_eps = 1e-8;
+
   // derived feature geometry
   int L = 0, F = 0;            // samples and STFT frames per chunk
   int T = 0, M = 0;            // target_frames, n_mels
@@ -151,6 +158,7 @@ struct avld_ctx {
   int32_t* d_prio = nullptr;
   int32_t* d_pred = nullptr;
   float* d_best = nullptr;
+  std::string host_trace_path;     // AVLD_HOST_TRACE at context creation: per-slab timeline of the host path (tools/trace_run.py)
   void* h_stage = nullptr;         // pinned staging for results (a D2H into pageable memory would block the host
   size_t h_stage_bytes = 0;        // thread until the slab's kernels finish and serialise copy against compute)
 

@@ -473,6 +473,7 @@ extern "C" int avld_ctx_create(int device, const avld_params* params, avld_ctx**
   c->device = device;
   c->p = *params;
   c->sm_count = prop.multiProcessorCount;
+  if (const char* t = getenv("AVLD_HOST_TRACE")) c->host_trace_path = t;
   c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   const int r = build_ctx(c);
   if (r != AVLD_OK) {
@@ -512,6 +513,17 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   }
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   delete c;
+}
+
+extern "C" int avld_ctx_set_normalization(avld_ctx* c, int scalar_semantics, double target_rms, double rms_min, double eps) {
+  AVLD_ENTER(c);
+  AVLD_CHECK(scalar_semantics == 0 || scalar_semantics == 1, AVLD_ERR_INVALID, "scalar_semantics must be 0 (numpy 2) or 1 (numpy 1.x)");
+  AVLD_CHECK(target_rms > 0.0 && rms_min >= 0.0 && eps >= 0.0, AVLD_ERR_INVALID, "bad normalisation constants");
+  c->scalar_f64 = scalar_semantics;
+  c->norm_target = target_rms;
+  c->norm_rms_min = rms_min;
+  c->norm_eps = eps;
+  return AVLD_OK;
 }
 
 extern "C" int avld_profile_enable(avld_ctx* c, int on) {

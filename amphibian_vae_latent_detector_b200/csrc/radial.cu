@@ -91,10 +91,10 @@ __global__ void decide_kernel(const float* __restrict__ radii, const double* __r
     float bd = INFINITY;
     int sel = -1, sel_rank = 0x7fffffff;
     for (int k = 0; k < K; ++k) {
-      const double rk = thr[k];
-      if (rk != rk) continue;                                  // species without a threshold: skipped (09:418-419)
-      const float d = radii[i * K + k];
-      bd = fminf(bd, d);                                       // min(best_d, d): NaN d never lowers it
+      const double rk = thr[k];                                // NaN (e.g. a species fitted on no data): `d <= rk` is false,
+      const float d = radii[i * K + k];                        // but d still counts for best_d, as in 10:177-187.  A species
+      bd = fminf(bd, d);                                       // that is ABSENT from `thresholds` is dropped by the caller
+                                                               // (09:418-419).  min(best_d, d): NaN d never lowers it
       if (static_cast<double>(d) <= rk && prio[k] < sel_rank) {  // accept iff d <= rk; first in priority order wins
         sel = k;
         sel_rank = prio[k];

@@ -32,6 +32,8 @@ struct PrepParams {
   int n_leaves, n_nodes, n_levels;
   int L, n_fft, hop;
   float target_rms, rms_min, eps;
+  int scalar_f64;         // numpy 1.x scalar rules: gate, `rms + eps` and `target / (...)` in float64 (the three below)
+  double target_d, rms_min_d, eps_d;
   int normalize, quantize;
   int dft_scale_log2;
   int headroom_log2;      // max |scaled sample| < 2^(headroom_log2 + 1): 13 (sums of up to eight samples stay in fp16 range)
@@ -142,7 +144,15 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
     const float rms = __fsqrt_rn(mean);
     int scaled = 0;
     float scale = 1.0f;
-    if (P.normalize && !(rms < P.rms_min)) {           // silence gate: `if rms < rms_min: return y, False`
+    if (P.scalar_f64) {
+      // numpy 1.26.4 (the reference's pin): np.float32 (op) Python float is evaluated in float64; `y * scale` then casts the
+      // float64 scalar to the array's float32 -- one rounding (00_normalize_dataset_rms.py:30-36)
+      const double rd = static_cast<double>(rms);
+      if (P.normalize && !(rd < P.rms_min_d)) {
+        scaled = 1;
+        scale = __double2float_rn(__ddiv_rn(P.target_d, __dadd_rn(rd, P.eps_d)));
+      }
+    } else if (P.normalize && !(rms < P.rms_min)) {    // silence gate: `if rms < rms_min: return y, False`
       scaled = 1;
       scale = __fdiv_rn(P.target_rms, __fadd_rn(rms, P.eps));
     }
@@ -260,6 +270,14 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.target_rms = target_rms;
   P.rms_min = rms_min;
   P.eps = eps;
+  P.scalar_f64 = c->scalar_f64;
+  P.target_d = c->norm_target;
+  P.rms_min_d = c->norm_rms_min;
+  P.eps_d = c->norm_eps;
+  if (c->scalar_f64)      // the per-call floats must be the float32 images of the context's doubles
+    AVLD_CHECK(target_rms == static_cast<float>(c->norm_target) && rms_min == static_cast<float>(c->norm_rms_min) &&
+                   eps == static_cast<float>(c->norm_eps),
+               AVLD_ERR_INVALID, "numpy-1 scalar mode: target_rms / rms_min / eps differ from avld_ctx_set_normalization");
   P.normalize = normalize ? 1 : 0;
   P.quantize = quantize ? 1 : 0;
   P.dft_scale_log2 = c->dft_scale_log2;

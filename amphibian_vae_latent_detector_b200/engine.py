@@ -44,7 +44,11 @@ def _stream() -> int:
 class Engine:
     def __init__(self, device: int | torch.device = 0, *, chunk_len: int = 144000, max_batch: int = 256,
                  sr: int = 48000, n_fft: int = 2048, hop_length: int = 384, n_mels: int = 64, fmin: float = 150.0,
-                 fmax: float = 15000.0, target_frames: int = 192, amin: float = 1e-10, top_db: float = 80.0):
+                 fmax: float = 15000.0, target_frames: int = 192, amin: float = 1e-10, top_db: float = 80.0,
+                 scalar_semantics: str = "numpy2", target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8):
+        """``scalar_semantics``: how ``rms + eps`` and ``target_rms / (...)`` of rms_normalize (00:29-38) are rounded --
+        "numpy2" (float32, what numpy >= 2 does and the committed fixtures were made with) or "numpy1" (float64, what the
+        reference's pinned numpy==1.26.4 does).  ``target_rms / rms_min / eps`` are the constants of the fused host calls."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("amphibian_vae_latent_detector_b200 needs a CUDA device (sm_100a); there is no CPU path")
@@ -57,6 +61,11 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.avld_ctx_create(self.device.index, C.byref(self.params), C.byref(h)))
         self._h = h
+        if scalar_semantics not in ("numpy1", "numpy2"):
+            raise ValueError("scalar_semantics must be 'numpy1' or 'numpy2'")
+        self.scalar_semantics = scalar_semantics
+        self.norm = (float(target_rms), float(rms_min), float(eps))
+        _lib.check(self.lib.avld_ctx_set_normalization(self._h, 1 if scalar_semantics == "numpy1" else 0, *self.norm))
         nf, ld, sm = C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(self.lib.avld_ctx_info(self._h, C.byref(nf), C.byref(ld), C.byref(sm)))
         self.n_frames, self.sm_count = nf.value, sm.value
@@ -103,10 +112,18 @@ class Engine:
         _lib.check(self.lib.avld_ctx_dft_info(self._h, C.byref(mode), C.byref(alg), C.byref(iss)))
         return {"mode": mode.value.decode(), "algorithmic_flops_per_chunk": alg.value, "issued_flops_per_chunk": iss.value}
 
+    def _norm_args(self, target_rms, rms_min, eps):
+        t, r, e = self.norm
+        return (t if target_rms is None else float(target_rms), r if rms_min is None else float(rms_min),
+                e if eps is None else float(eps))
+
     # ------------------------------------------------------------------ R1 / R2
-    def rms_normalize(self, x: torch.Tensor, target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8,
+    def rms_normalize(self, x: torch.Tensor, target_rms: Optional[float] = None, rms_min: Optional[float] = None,
+                      eps: Optional[float] = None,
                       pcm16: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> ``(y [n,L] f32, ok [n] uint8, rms [n] f32)``; bit-exact with numpy-2 float32 semantics."""
+        """-> ``(y [n,L] f32, ok [n] uint8, rms [n] f32)``; bit-exact with numpy's float32 arithmetic under the engine's
+        ``scalar_semantics``.  Constants default to the engine's (``Engine(target_rms=..., rms_min=..., eps=...)``)."""
+        target_rms, rms_min, eps = self._norm_args(target_rms, rms_min, eps)
         x = self._dev(x, torch.float32, "x")
         if x.ndim != 2 or x.shape[1] != self.chunk_len:
             raise ValueError(f"x must be [n, {self.chunk_len}]")
@@ -128,8 +145,10 @@ class Engine:
         _lib.check(self.lib.avld_logmel(self._h, _ptr(y), _ptr(feat), y.shape[0], _stream()))
         return feat
 
-    def normalize_logmel(self, x: torch.Tensor, target_rms: float = 0.05, rms_min: float = 1e-4, eps: float = 1e-8,
+    def normalize_logmel(self, x: torch.Tensor, target_rms: Optional[float] = None, rms_min: Optional[float] = None,
+                         eps: Optional[float] = None,
                          pcm16: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        target_rms, rms_min, eps = self._norm_args(target_rms, rms_min, eps)
         x = self._dev(x, torch.float32, "x")
         n = x.shape[0]
         feat = torch.empty(n, self.target_frames, self.n_mels, dtype=torch.float32, device=self.device)
@@ -180,10 +199,11 @@ class Engine:
         _lib.check(self.lib.avld_encoder_forward(self._h, _ptr(feat), _ptr(mu), feat.shape[0], _stream()))
         return mu
 
-    def encode(self, x: torch.Tensor, *, pcm16: bool = True, target_rms: float = 0.05, rms_min: float = 1e-4,
-               eps: float = 1e-8) -> Tuple[torch.Tensor, torch.Tensor]:
+    def encode(self, x: torch.Tensor, *, pcm16: bool = True, target_rms: Optional[float] = None,
+               rms_min: Optional[float] = None, eps: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """raw chunks ``[n, L]`` (float32, or int16 PCM_16 samples as the WAV files hold them) -> ``(mu [n, D], ok [n])``:
         normalise (+ PCM_16 round trip of the ``*_norm`` dataset on disk) -> log-mel -> encoder."""
+        target_rms, rms_min, eps = self._norm_args(target_rms, rms_min, eps)
         as_pcm = isinstance(x, torch.Tensor) and x.dtype == torch.int16
         x = self._dev(x, torch.int16 if as_pcm else torch.float32, "x")
         n = x.shape[0]

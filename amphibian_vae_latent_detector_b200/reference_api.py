@@ -28,6 +28,7 @@ import wave
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -42,7 +43,12 @@ PRIORITY_ORDER = [
     "Pleurodema_thaul",
 ]
 
-_ENGINES: Dict[tuple, Engine] = {}
+# Engine cache.  An engine owns a device context (operand scratch of ~3 MB per chunk of `max_batch`, plus the uploaded layer
+# program), so the cache is a small LRU (an evicted engine is freed as soon as nobody else holds it).  Entries with an encoder keep a strong reference to the
+# module (an id() alone could be reused by a new module after garbage collection) and are keyed by a fingerprint of its
+# weights as well (an in-place load_state_dict on the same object must not be served the old program).
+_ENGINE_CACHE_SIZE = 4
+_ENGINES: "OrderedDict[tuple, tuple]" = OrderedDict()     # key -> (engine, encoder or None)
 _IO_POOL = ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 4)))
 _LOADED: Dict[tuple, int] = {}
 
@@ -52,25 +58,64 @@ def _cuda_index(device) -> int:
     return (dev.index or 0) if dev.type == "cuda" else 0
 
 
+def _cache_get(key):
+    hit = _ENGINES.get(key)
+    if hit is None:
+        return None
+    _ENGINES.move_to_end(key)
+    return hit[0]
+
+
+def _cache_put(key, eng: Engine, encoder=None) -> Engine:
+    _ENGINES[key] = (eng, encoder)
+    while len(_ENGINES) > _ENGINE_CACHE_SIZE:
+        _ENGINES.popitem(last=False)      # dropped, not closed: a caller may still hold it; Engine.__del__ frees the context
+    return eng
+
+
+def clear_engine_cache() -> None:
+    """Close every cached engine (frees their device memory)."""
+    while _ENGINES:
+        _, (old, _enc) = _ENGINES.popitem()
+        old.close()
+
+
+def _weights_fingerprint(encoder) -> tuple:
+    """Cheap identity of the module's current weights: (number of tensors, total elements, a float64 checksum of strided
+    samples of every parameter / buffer).  Two state dicts that differ anywhere a sample falls differ here; an in-place
+    update of the weights changes it with overwhelming probability."""
+    n, total, acc = 0, 0, 0.0
+    with torch.no_grad():
+        for t in list(encoder.parameters()) + list(encoder.buffers()):
+            flat = t.detach().reshape(-1)
+            if flat.numel() == 0 or not (flat.is_floating_point() or flat.dtype in (torch.int64, torch.int32)):
+                continue
+            step = max(1, flat.numel() // 64)
+            acc += float(flat[::step].double().sum().item()) * (n + 1)
+            n += 1
+            total += flat.numel()
+    return (n, total, acc)
+
+
 def _engine(chunk_len: int, device=0, *, sr=48000, n_mels=64, fmin=150.0, fmax=15000.0, hop_length=384, n_fft=2048,
             target_frames=192, max_batch: int = 64) -> Engine:
     key = (_cuda_index(device), int(chunk_len), sr, n_mels, float(fmin), float(fmax), hop_length, n_fft, target_frames)
-    eng = _ENGINES.get(key)
+    eng = _cache_get(key)
     if eng is None:
-        eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=max_batch, sr=sr, n_fft=n_fft, hop_length=hop_length,
-                     n_mels=n_mels, fmin=fmin, fmax=fmax, target_frames=target_frames)
-        _ENGINES[key] = eng
+        eng = _cache_put(key, Engine(key[0], chunk_len=int(chunk_len), max_batch=max_batch, sr=sr, n_fft=n_fft,
+                                     hop_length=hop_length, n_mels=n_mels, fmin=fmin, fmax=fmax, target_frames=target_frames))
     return eng
 
 
 def _engine_with_encoder(encoder, chunk_len, device, *, max_batch: int = 64, **mel_kw) -> Engine:
-    """One engine per (geometry, encoder object, pass size); the layer program is exported and uploaded once."""
-    key = (_cuda_index(device), int(chunk_len), tuple(sorted(mel_kw.items())), id(encoder), int(max_batch))
-    eng = _ENGINES.get(key)
+    """One engine per (geometry, encoder object + weights, pass size); the layer program is exported and uploaded once."""
+    key = (_cuda_index(device), int(chunk_len), tuple(sorted(mel_kw.items())), id(encoder), _weights_fingerprint(encoder),
+           int(max_batch))
+    eng = _cache_get(key)
     if eng is None:
         eng = Engine(key[0], chunk_len=int(chunk_len), max_batch=int(max_batch), **mel_kw)
         eng.load_encoder(encoder)
-        _ENGINES[key] = eng
+        _cache_put(key, eng, encoder)
     return eng
 
 
@@ -314,29 +359,69 @@ def build_nn_module(obj: Any) -> torch.nn.Module:
     raise RuntimeError(f"instantiate devolvió {type(obj)}; no pude obtener nn.Module.")
 
 
-def _instantiate(cfg: Dict[str, Any]):
+def _instantiate(cfg):
+    """The part of ``hydra.utils.instantiate`` the encoder YAMLs use (core:171): ``_target_`` (dotted path of a callable),
+    nested ``_target_`` nodes in arguments / lists are instantiated first, ``_partial_: true`` returns a
+    ``functools.partial`` instead of calling, ``_args_`` gives positional arguments; other keys are keyword arguments."""
+    if isinstance(cfg, (list, tuple)):
+        return [_instantiate(v) for v in cfg]
+    if not isinstance(cfg, dict):
+        return cfg
+    if "_target_" not in cfg:
+        return {k: _instantiate(v) for k, v in cfg.items()}
     cfg = dict(cfg)
     target = cfg.pop("_target_")
-    mod_name, _, attr = target.rpartition(".")
-    return getattr(importlib.import_module(mod_name), attr)(**cfg)
+    partial = bool(cfg.pop("_partial_", False))
+    args = [_instantiate(v) for v in cfg.pop("_args_", [])]
+    cfg.pop("_convert_", None)
+    cfg.pop("_recursive_", None)
+    kwargs = {k: _instantiate(v) for k, v in cfg.items()}
+    if callable(target):
+        fn = target
+    else:
+        mod_name, _, attr = str(target).rpartition(".")
+        fn = getattr(importlib.import_module(mod_name), attr)
+    if partial:
+        import functools
+        return functools.partial(fn, *args, **kwargs)
+    return fn(*args, **kwargs)
 
 
-def load_encoder(encoder_pt: Path, encoder_yaml: Path, project_root: Path, device=None) -> torch.nn.Module:
-    """core:150-179.  Returns the ``nn.Module`` (eval mode, on the CPU: it is only walked by
-    ``export_program``; the forward itself runs in the CUDA library)."""
+def load_encoder(encoder_pt: Path, encoder_yaml: Path, project_root: Path, device=None, *,
+                 trust_checkpoint: Optional[bool] = None) -> torch.nn.Module:
+    """core:150-179.  Returns the ``nn.Module`` (eval mode, on the CPU: it is only walked by ``export_program``; the forward
+    itself runs in the CUDA library).
+
+    The reference calls ``torch.load`` with torch 2.1's default (full unpickling) and so also accepts a checkpoint that holds
+    the pickled module itself (core:160-165).  Here a checkpoint is first read with ``weights_only=True`` (tensors and plain
+    containers: every state-dict checkpoint); one that needs arbitrary unpickling is only loaded when the caller says the file
+    is trusted -- ``trust_checkpoint=True`` or ``AVLD_TRUST_CHECKPOINTS=1`` -- because unpickling executes code from the file."""
     if str(project_root) not in sys.path:
         sys.path.insert(0, str(project_root))
     encoder_pt = Path(encoder_pt)
     if not encoder_pt.exists():
         raise FileNotFoundError(f"No existe encoder .pt: {encoder_pt}")
-    ckpt = torch.load(str(encoder_pt), map_location="cpu", weights_only=True)
+    try:
+        ckpt = torch.load(str(encoder_pt), map_location="cpu", weights_only=True)
+    except Exception as exc:                       # pickle.UnpicklingError and friends: not a plain state dict
+        if trust_checkpoint is None:
+            trust_checkpoint = os.environ.get("AVLD_TRUST_CHECKPOINTS", "0") not in ("", "0")
+        if not trust_checkpoint:
+            raise RuntimeError(
+                f"{encoder_pt} is not a plain state-dict checkpoint (torch.load(weights_only=True) refused it: {exc}).  "
+                "Full-module checkpoints execute code when unpickled; pass trust_checkpoint=True (or set "
+                "AVLD_TRUST_CHECKPOINTS=1) if the file comes from a trusted source.") from exc
+        ckpt = torch.load(str(encoder_pt), map_location="cpu", weights_only=False)
     model, state = split_model_and_state(ckpt)
-    if model is None:
-        encoder_yaml = Path(encoder_yaml)
-        if not encoder_yaml.exists():
-            raise FileNotFoundError(f"No existe YAML: {encoder_yaml}")
-        model = build_nn_module(_instantiate(pick_encoder_cfg(load_yaml_cfg(encoder_yaml))))
-        model.load_state_dict(state, strict=False)
+    if model is not None:
+        return build_nn_module(model).eval()
+    if state is None:
+        raise RuntimeError("No encontré state_dict en el checkpoint.")
+    encoder_yaml = Path(encoder_yaml)
+    if not encoder_yaml.exists():
+        raise FileNotFoundError(f"No existe YAML: {encoder_yaml}")
+    model = build_nn_module(_instantiate(pick_encoder_cfg(load_yaml_cfg(encoder_yaml))))
+    model.load_state_dict(state, strict=False)
     return model.eval()
 
 

@@ -149,7 +149,7 @@ def iter_slabs(pcm: np.ndarray, window_len: int, hop_len: int, slab_windows: int
     key = (rows, window_len, pin)
     bufs = _PINNED.get(key)
     if bufs is None:
-        if len(_PINNED) >= 4:
+        if len(_PINNED) >= 2:       # two slab geometries at most (a 2048-window slab of 5 s PCM_16 windows is ~1 GB, twice)
             _PINNED.clear()
         bufs = [torch.empty(rows, window_len, dtype=torch.int16, pin_memory=pin) for _ in range(2)]
         _PINNED[key] = bufs
@@ -209,8 +209,8 @@ def detect_long_wav(wav_path, *, config_path, encoder: torch.nn.Module, window_s
     try:
         pcm = open_pcm16_mono(wav_path, sr)
     except ValueError:
-        # other sample formats / channel counts: decode as librosa.load would, re-quantise is NOT applied here --
-        # the float path of the library takes it from there
+        # other sample formats / channel counts: decode as librosa.load would (float32 samples); the windows then take the
+        # float path of the library, which applies the same normalise + PCM_16 round trip as the chunk-file workflow
         y = api.load_wav(wav_path, sr)
         return _detect_float_stream(y, encoder, centroids, thresholds, sr=sr, window_seconds=win, hop_seconds=hop_seconds,
                                     slab_windows=slab_windows, device=device, **mel_kw)

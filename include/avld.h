@@ -89,6 +89,15 @@ void avld_ctx_destroy(avld_ctx* ctx);
 /* derived sizes: frames per chunk F = 1 + chunk_len / hop, latent dim D (0 before encoder_load) */
 int avld_ctx_info(const avld_ctx* ctx, int32_t* n_frames, int32_t* latent_dim, int32_t* sm_count);
 
+/* Constants and scalar arithmetic of rms_normalize (00_normalize_dataset_rms.py:29-38) for this context.
+ * scalar_semantics 0 (default): numpy >= 2 -- `rms + eps`, `target_rms / (...)` and the `rms < rms_min` gate are float32
+ * operations (a Python float next to a float32 scalar is "weak").  1: numpy 1.x value-based casting, which the reference's
+ * pinned numpy==1.26.4 executes -- the three are float64 operations and the scale is rounded to float32 once (the two modes
+ * differ by one ulp of the scale in about a third of all chunks).  The fused host calls (avld_encode_detect_host*) take
+ * their constants from here; the per-call float parameters of the other entry points must equal (float) of these values
+ * when scalar_semantics is 1.  Defaults: 0, 0.05, 1e-4, 1e-8. */
+int avld_ctx_set_normalization(avld_ctx* ctx, int scalar_semantics, double target_rms, double rms_min, double eps);
+
 /* How the STFT is evaluated on this context (accounting for bench.py's roofline line): `mode` receives a static string
  * ("fold2" twice-folded, "fold"/"fold1" once-folded, "direct"), algorithmic = the flops of the plain windowed DFT GEMM
  * restricted to the bins with mel weight (2 * F * n_fft * 2 * bins), issued = the tensor-core
@@ -156,8 +165,9 @@ int avld_order_stats(avld_ctx* ctx, const float* radii, const int32_t* label, in
 
 /* ---- D2: decision (09_evaluate_wav_detection.py:416-436; 10_benchmark_folder_detection.py:175-199)
  * accept k iff (double)radii[i,k] <= thr[k]; pred[i] = accepted k with the smallest
- * priority_rank[k] or -1 (NO_DETECT); best_d[i] = min_k radii[i,k].  thr dev float64 [K] (NaN =
- * species without threshold: skipped), priority_rank dev int32 [K]. */
+ * priority_rank[k] or -1 (NO_DETECT); best_d[i] = min_k radii[i,k].  thr dev float64 [K] (a NaN
+ * threshold never accepts but its distance still counts for best_d, 10:177-187; a species ABSENT from the
+ * config's thresholds is left out of the arrays by the caller, 09:418-419), priority_rank dev int32 [K]. */
 int avld_decide(avld_ctx* ctx, const float* radii, const double* thr, const int32_t* priority_rank,
                 int32_t* pred, float* best_d, int64_t n, int32_t K, void* stream);
 

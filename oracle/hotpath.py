@@ -35,7 +35,7 @@ PRIORITY_ORDER: List[str] = [  # 09_evaluate_wav_detection.py:61-66
 def rms_normalize(y: np.ndarray, target_rms=0.05, rms_min=1e-4, eps=1e-8,
                   numpy1_scalars: bool = False) -> Tuple[np.ndarray, bool]:
     rms = np.sqrt(np.mean(y ** 2))
-    if rms < rms_min:
+    if (float(rms) < rms_min) if numpy1_scalars else (rms < rms_min):      # numpy 1.x compares in float64 as well
         return y, False
     if numpy1_scalars:  # numpy 1.26.4 value-based casting: float32 scalar (op) python float -> float64
         scale = np.float32(target_rms / (float(rms) + eps))
@@ -47,7 +47,7 @@ def rms_normalize(y: np.ndarray, target_rms=0.05, rms_min=1e-4, eps=1e-8,
 
 
 def rms_normalize_batch(x: np.ndarray, target_rms=0.05, rms_min=1e-4, eps=1e-8,
-                        pcm16: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+                        pcm16: bool = False, numpy1_scalars: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Row-wise R1 (+ optional R2 ``sf.write``/``librosa.load`` PCM_16 round trip,
     00_normalize_dataset_rms.py:55-57 -> map_detector_core.py:210).  Returns ``(y, ok, rms)``."""
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -57,7 +57,7 @@ def rms_normalize_batch(x: np.ndarray, target_rms=0.05, rms_min=1e-4, eps=1e-8,
     for i in range(x.shape[0]):
         row = x[i]
         rms[i] = np.sqrt(np.mean(row ** 2))
-        yn, good = rms_normalize(row, target_rms, rms_min, eps)
+        yn, good = rms_normalize(row, target_rms, rms_min, eps, numpy1_scalars=numpy1_scalars)
         ok[i] = 1 if good else 0
         y[i] = lp.pcm16_roundtrip(yn) if pcm16 else yn
     return y, ok, rms

@@ -98,11 +98,11 @@ def test_decide_random_vs_oracle(engine3s):
     Z, _ = _latents(5000, 64, 8, k=5)
     rng = np.random.default_rng(4)
     cent = (rng.standard_normal((5, 64)) * 3).astype(np.float32)
-    thr = np.array([12.0, 40.0, 13.0, 40.0, np.nan])       # NaN = species without a threshold (09:418-419)
+    thr = np.array([12.0, 40.0, 13.0, 40.0, np.nan])       # NaN threshold: never accepted, still counts for best_d (10:177-187)
     prio = priority_ranks(species, hp.PRIORITY_ORDER)
     r = engine3s.radii(torch.from_numpy(Z).cuda(), torch.from_numpy(cent).cuda())
     pred, best = engine3s.decide(r, torch.from_numpy(thr).cuda(), torch.from_numpy(prio).cuda())
-    po, bo, ro = hp.decide_batch(Z, species[:4], cent[:4], thr[:4])
+    po, bo, ro = hp.decide_batch(Z, species, cent, thr)
     rr = r.cpu().numpy()
     near = np.any(np.abs(rr[:, :4] - thr[None, :4]) / thr[None, :4] <= 1e-5, axis=1)
     assert np.array_equal(pred.cpu().numpy()[~near], po[~near])
