@@ -38,6 +38,16 @@ class Layer(C.Structure):
                 ("bias", C.POINTER(C.c_float))]
 
 
+class Op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("in0", C.c_int32), ("in1", C.c_int32), ("out", C.c_int32), ("c_in", C.c_int32),
+                ("c_out", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("relu", C.c_int32),
+                ("pool", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("weight", C.POINTER(C.c_float)),
+                ("bias", C.POINTER(C.c_float))]
+
+
+OP_CONV, OP_LINEAR, OP_ADD, OP_AFFINE, OP_POOL = range(5)
+
+
 class RankQuery(C.Structure):
     _fields_ = [("species", C.c_int32), ("side", C.c_int32), ("rank", C.c_int64)]
 
@@ -59,6 +69,7 @@ _SIGNATURES = {
     "avld_logmel": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "avld_normalize_logmel": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "avld_encoder_load": (C.c_int, [_P, C.POINTER(Layer), C.c_int32]),
+    "avld_encoder_load_program": (C.c_int, [_P, C.POINTER(Op), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "avld_encoder_forward": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "avld_encode": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "avld_encode_pcm16": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),

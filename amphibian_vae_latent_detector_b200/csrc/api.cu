@@ -27,7 +27,7 @@ extern "C" int avld_encode(avld_ctx* c, const float* x, float* mu, uint8_t* ok, 
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
-  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  AVLD_CHECK(!c->ops.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t i = 0; i < n; i += c->max_batch) {
     const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
@@ -43,7 +43,7 @@ extern "C" int avld_encode_pcm16(avld_ctx* c, const int16_t* pcm, float* mu, uin
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(pcm && mu, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0, AVLD_ERR_INVALID, "negative n");
-  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  AVLD_CHECK(!c->ops.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t i = 0; i < n; i += c->max_batch) {
     const int m = static_cast<int>(std::min<int64_t>(n - i, c->max_batch));
@@ -60,7 +60,7 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
   if (n == 0) return AVLD_OK;                 // an empty batch is valid (and its pointers may be NULL)
   AVLD_CHECK(x_host && centroid && thr && priority_rank && pred_host && best_host, AVLD_ERR_INVALID, "NULL argument");
   AVLD_CHECK(n >= 0 && K >= 1 && K <= 64, AVLD_ERR_INVALID, "bad n / K");
-  AVLD_CHECK(!c->layers.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
+  AVLD_CHECK(!c->ops.empty(), AVLD_ERR_STATE, "avld_encoder_load has not been called");
   const int D = c->latent_dim;
   const size_t xbytes = static_cast<size_t>(c->max_batch) * c->L * sizeof(float);
   for (int b = 0; b < 2; ++b)

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...);
 // kernel families, for the launch counter and the optional per-stage CUDA-event timing
 enum Stage {
   ST_PREP = 0, ST_STFT_MEL, ST_LOGMEL_POST, ST_CONV_DIRECT, ST_CONV_GEMM, ST_DENSE_GEMM, ST_RADII, ST_DECIDE,
-  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_FOLD, ST_MAP, ST_COUNT
+  ST_CENTROID, ST_SELECT, ST_SPLIT, ST_FOLD, ST_MAP, ST_ELEMENTWISE, ST_COUNT
 };   // names: ctx.cu::avld_stage_name
 
 #define AVLD_CUDA(expr)                                                                       \
@@ -55,20 +55,38 @@ struct PairNode {
   int32_t a, b;  // indices into the value array (leaves first, then internal nodes by height)
 };
 
-// encoder layer on the device
-struct LayerDev {
-  int kind;  // 0 conv (tcgen05, one box per tap), 1 linear (tcgen05), 2 conv direct (CUDA cores, tiny C_in),
-             // 3 conv (tcgen05, halo reuse: convh.cu)
-  int c_in, c_out, ksize, stride, pad, relu, pool;
-  int in_h, in_w, out_h, out_w;  // out = after pooling
-  int bn, swz, cblk, cblocks;    // tcgen05 tiling
-  int tw, th, tiles_w, tiles_h;
-  float* w_f32 = nullptr;  // direct conv weights [c_out][k][k][c_in]
-  float* bias = nullptr;   // [c_out]
+// one operation of the encoder program on the device (encoder.cu); tensors are NHWC bf16 hi + lo planes in numbered slots
+struct OpDev {
+  int kind;   // OP_* below
+  int src = -1, src2 = -1, dst = -1;   // tensor ids
+  int c_in = 0, c_out = 0;             // padded channel counts (tensor layouts), logical ones only matter at load time
+  int ksize = 1, stride = 1, pad = 0, relu = 0;
+  int pool = 1;                        // fused 2x2 pooling after the activation (1 = none, 2 = yes), pool_avg: average instead of max
+  int pool_avg = 0;
+  int in_h = 0, in_w = 0, out_h = 0, out_w = 0;   // out = after pooling
+  int bn = 0, swz = 0, cblk = 0, cblocks = 0;     // tcgen05 tiling
+  int tw = 0, th = 0, tiles_w = 0, tiles_h = 0;
+  int conv_h = 0, conv_w = 0;          // convolution output size before pooling
+  float* w_f32 = nullptr;  // first-layer conv weights [c_out][k][k][c_in]; affine: scale [c]
+  float* bias = nullptr;   // [c_out]; affine: shift [c]
   __nv_bfloat16* w_hi = nullptr;
   __nv_bfloat16* w_lo = nullptr;  // [c_out][K]
   int64_t K = 0;
-  CUtensorMap tm_w_hi, tm_w_lo;
+  CUtensorMap tm_w_hi, tm_w_lo, tm_in_hi, tm_in_lo;
+};
+enum {
+  OP_CONV_GEMM = 0,    // implicit GEMM on tcgen05, one TMA box per filter tap (any odd k, stride 1 / 2)
+  OP_LINEAR = 1,       // plain GEMM on tcgen05
+  OP_CONV_FIRST = 2,   // first layer (fp32 single-channel feature image in), CUDA cores
+  OP_CONV_HALO = 3,    // 3x3 stride-1 implicit GEMM with halo reuse (convh.cu)
+  OP_ADD = 4, OP_AFFINE = 5, OP_POOL = 6, OP_GAP = 7
+};
+
+struct TensorDev {
+  int c = 0, h = 0, w = 0;   // logical; vectors: h = w = 1
+  int c_pad = 0;             // channels of the device layout (multiple of 32 / 64, pad channels hold zeros)
+  int slot = -1;             // activation slot (tensor 0 = the fp32 feature image: no slot)
+  size_t elems() const { return static_cast<size_t>(h) * w * c_pad; }
 };
 
 }  // namespace avld
@@ -141,13 +159,15 @@ struct avld_ctx {
   uint8_t* d_ok = nullptr;
   float* d_rms = nullptr;
 
-  // encoder
-  std::vector<avld::LayerDev> layers;
+  // encoder program (avld_encoder_load_program)
+  std::vector<avld::OpDev> ops;
+  std::vector<avld::TensorDev> tensors;
+  int enc_out = -1;                // tensor id of the latent
+  int enc_out_nchw = 0;            // the latent is a feature map: flattened in NCHW order
+  int n_seg = 1, seg_frames = 0;   // segments per chunk (the latent is their mean), frames per segment
   int latent_dim = 0;
-  size_t act_elems = 0;            // per-chunk max activation elements
-  __nv_bfloat16* d_act_hi[2] = {nullptr, nullptr};
-  __nv_bfloat16* d_act_lo[2] = {nullptr, nullptr};
-  std::vector<CUtensorMap> tm_act_hi, tm_act_lo;  // per layer input maps
+  std::vector<__nv_bfloat16*> d_slot_hi, d_slot_lo;   // activation slots, each max_batch * n_seg images of the largest tensor
+  float* d_lat = nullptr;          // [max_batch * n_seg][latent_dim] per-segment latents (n_seg > 1 or a non-linear head)
 
   // host end-to-end path
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -182,7 +202,8 @@ namespace avld {
 int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint64_t dim0, uint64_t dim1,
                    uint64_t stride1_bytes, uint32_t box0, uint32_t box1, uint32_t swizzle_bytes);
 int encode_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, const uint64_t dims[4],
-                   const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t swizzle_bytes);
+                   const uint64_t strides_bytes[3], const uint32_t box[4], uint32_t swizzle_bytes,
+                   const uint32_t* elem_strides = nullptr);   // traversal strides (strided convolutions), default 1
 
 // Opt-in to more than 48 KB of dynamic shared memory, once per (context, kernel).  The attribute belongs to the device the
 // context lives on, so the record is kept in the context (a process-wide flag would leave the kernels of a second GPU's
@@ -223,7 +244,7 @@ int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
 int convh_encode_input_map(CUtensorMap* out, const void* base, int n, int H, int W, int C, int cblk);
 bool convh_supported(int c_in, int c_out, int ksize, int w);
-int launch_convh(avld_ctx* c, const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
+int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
                  __nv_bfloat16* out_lo, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
 int launch_split_f16(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t st);

@@ -27,7 +27,8 @@ struct ConvhParams {
   int resident;                // weights resident in shared memory (loaded once)
   uint32_t idesc;
   int H, W, Cout, relu, pool;  // conv output size (= input size), before pooling
-  int dbg;                     // timing probe (AVLD_CONVH_DBG = 2, wrong results): hi*hi pass only
+  int pool_avg;                // the 2x2 pooling averages (after bias and ReLU) instead of taking the maximum
+  int dbg;                     // AVLD_BRINGUP builds only: timing probe (AVLD_CONVH_DBG = 2, wrong results): hi*hi pass only
   const float* bias;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -256,28 +257,44 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           // per lane; bias and ReLU commute with the max (both monotonic, fl(x + b) is monotonic in x), so the bits are the
           // same as pooling after them.
           const bool odd_w = (lane & 1) != 0, odd_h = (lane & kTW) != 0;
+          const bool avg = P.pool_avg != 0;
+          if (avg) {                          // the average does not commute with bias + ReLU: apply them first
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + j);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float t = __uint_as_float(v[j + u]) + bb[u];
+                if (P.relu) t = relu_nan(t);
+                v[j + u] = __float_as_uint(t);
+              }
+            }
+          }
           float keep[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float lo8 = __uint_as_float(v[j]), hi8 = __uint_as_float(v[j + 8]);
             const float send = odd_w ? lo8 : hi8;
-            keep[j] = max_nan(odd_w ? hi8 : lo8, __shfl_xor_sync(0xffffffffu, send, 1));
+            const float mine = odd_w ? hi8 : lo8, other = __shfl_xor_sync(0xffffffffu, send, 1);
+            keep[j] = avg ? mine + other : max_nan(mine, other);
           }
           float q4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float send = odd_h ? keep[j] : keep[j + 4];
-            q4[j] = max_nan(odd_h ? keep[j + 4] : keep[j], __shfl_xor_sync(0xffffffffu, send, kTW));
+            const float mine = odd_h ? keep[j + 4] : keep[j], other = __shfl_xor_sync(0xffffffffu, send, kTW);
+            q4[j] = avg ? (mine + other) * 0.25f : max_nan(mine, other);
           }
           const int cq = c0 + (odd_w ? 8 : 0) + (odd_h ? 4 : 0);            // first of this lane's four output channels
           if (((h | 1) < P.H) && ((w | 1) < P.W) && cq < P.Cout) {         // the whole window lies inside the image
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cq);
+            const float4 b4 = avg ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_bias + cq);
             float o4[4] = {q4[0] + b4.x, q4[1] + b4.y, q4[2] + b4.z, q4[3] + b4.w};
             __align__(8) __nv_bfloat16 hi[4];
             __align__(8) __nv_bfloat16 lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (P.relu) o4[j] = relu_nan(o4[j]);
+              if (P.relu && !avg) o4[j] = relu_nan(o4[j]);
               hi[j] = __float2bfloat16_rn(o4[j]);
               lo[j] = __float2bfloat16_rn(o4[j] - __bfloat162float(hi[j]));
             }
@@ -359,7 +376,7 @@ bool convh_supported(int c_in, int c_out, int ksize, int w) {
   return ksize == 3 && (c_in == 32 || c_in % 64 == 0) && (c_out == 64 || c_out == 128) && (w % kTW == 0);
 }
 
-int launch_convh(avld_ctx* c, const LayerDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
+int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
                  __nv_bfloat16* out_lo, cudaStream_t st) {
   ConvhParams P{};
   P.tiles_w = L.in_w / kTW;
@@ -367,10 +384,12 @@ int launch_convh(avld_ctx* c, const LayerDev& L, const CUtensorMap& a_hi, const 
   P.n_tiles = n * P.tiles_w * P.tiles_h;
   P.cblocks = L.cblocks;
   P.idesc = avld_make_idesc(1, 1, 128, L.c_out);
-  P.H = L.in_h; P.W = L.in_w; P.Cout = L.c_out; P.relu = L.relu; P.pool = L.pool;
+  P.H = L.in_h; P.W = L.in_w; P.Cout = L.c_out; P.relu = L.relu; P.pool = L.pool; P.pool_avg = L.pool_avg;
   P.bias = L.bias;
+#ifdef AVLD_BRINGUP
   static const int dbg_env = std::getenv("AVLD_CONVH_DBG") ? std::atoi(std::getenv("AVLD_CONVH_DBG")) : 0;
   P.dbg = dbg_env;
+#endif
   P.out_hi = out_hi;
   P.out_lo = out_lo;
   if (L.c_out == 64 && L.cblk == 32) return launch_one<64, 32>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);

@@ -98,13 +98,16 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, u
 }
 
 int encode_tmap_4d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, const uint64_t dims_[4],
-                   const uint64_t strides_bytes[3], const uint32_t box_[4], uint32_t swizzle_bytes) {
+                   const uint64_t strides_bytes[3], const uint32_t box_[4], uint32_t swizzle_bytes,
+                   const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return AVLD_ERR_CUDA;
   cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
   cuuint64_t strides[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
   cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < 4; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_enum(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVLD_CHECK(r == CUDA_SUCCESS, AVLD_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
@@ -490,11 +493,14 @@ extern "C" void avld_ctx_destroy(avld_ctx* c) {
   cudaDeviceSynchronize();
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_chunk_par, c->d_A3, c->d_B3hi, c->d_B3lo,
                   c->d_taps3, c->d_edge, c->d_q16, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok,
-                  c->d_rms, c->d_act_hi[0], c->d_act_hi[1], c->d_act_lo[0], c->d_act_lo[1], c->d_xbuf[0], c->d_xbuf[1],
-                  c->d_cent, c->d_thr, c->d_prio, c->d_pred, c->d_best, c->d_hist};
+                  c->d_rms, c->d_lat, c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr, c->d_prio, c->d_pred, c->d_best, c->d_hist};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (auto& l : c->layers) {
+  for (auto* p : c->d_slot_hi)
+    if (p) cudaFree(p);
+  for (auto* p : c->d_slot_lo)
+    if (p) cudaFree(p);
+  for (auto& l : c->ops) {
     if (l.w_f32) cudaFree(l.w_f32);
     if (l.bias) cudaFree(l.bias);
     if (l.w_hi) cudaFree(l.w_hi);
@@ -558,7 +564,7 @@ extern "C" int avld_stage_count(void) { return ST_COUNT; }
 extern "C" const char* avld_stage_name(int stage) {
   static const char* names[ST_COUNT] = {"prep_kernel", "dftf3_kernel", "logmel_post_kernel", "conv1_kernel", "convh_kernel",
                                         "gemm3_kernel", "radii_kernel", "decide_kernel", "centroid_kernel", "select_hist_kernel",
-                                        "split_kernel", "fold3_kernel", "map_kernels"};
+                                        "split_kernel", "fold3_kernel", "map_kernels", "encoder_elementwise_kernels"};
   return (stage >= 0 && stage < ST_COUNT) ? names[stage] : "?";
 }
 

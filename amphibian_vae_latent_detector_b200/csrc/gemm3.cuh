@@ -15,7 +15,8 @@
 // A tiles are addressed two ways (a_mode):
 //   0  plain row-major [M, K]                      box (k0, m0)
 //   2  NHWC activations [N, H, W, C]: one box per filter tap, shifted by (kh - pad, kw - pad);
-//      TMA out-of-bounds zero fill *is* the convolution's zero padding
+//      TMA out-of-bounds zero fill *is* the convolution's zero padding, the tensor map's element
+//      strides *are* the convolution's stride
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,7 +32,7 @@ struct Gemm3Params {
   uint32_t idesc_hh, idesc_lh, idesc_hl;  // (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
   int a_mode;
   // a_mode 2 geometry
-  int tiles_w, tiles_h, tw, th, ksize, cblocks, cblk, pad;
+  int tiles_w, tiles_h, tw, th, ksize, cblocks, cblk, pad, stride;   // stride: of the convolution (the tensor map traverses with it)
   // common epilogue
   long long M_total;
   int N_total;
@@ -43,6 +44,7 @@ struct Gemm3Params {
   __nv_bfloat16* out_lo;
   // CONV epilogue
   int H, W, Cout, pool;     // H, W: conv output size before pooling
+  int pool_avg;             // the fused 2x2 pooling averages (after the activation) instead of taking the maximum
 };
 
 // non-template dispatcher (all instantiations live in gemm3.cu)
@@ -154,8 +156,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               const int tap = kb / P.cblocks;
               const int cb = kb - tap * P.cblocks;
               const int kh = tap / P.ksize, kw = tap - kh * P.ksize;
-              tma_load_4d(sa_hi, &tmA_hi, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
-              tma_load_4d(sa_lo, &tmA_lo, &full_bar[stage], cb * P.cblk, w0 + kw - P.pad, h0 + kh - P.pad, img);
+              tma_load_4d(sa_hi, &tmA_hi, &full_bar[stage], cb * P.cblk, w0 * P.stride + kw - P.pad, h0 * P.stride + kh - P.pad, img);
+              tma_load_4d(sa_lo, &tmA_lo, &full_bar[stage], cb * P.cblk, w0 * P.stride + kw - P.pad, h0 * P.stride + kh - P.pad, img);
             }
             tma_load_2d(sb_hi, &tmB_hi, &full_bar[stage], kb * Cfg::BK, nt * BN);
             tma_load_2d(sb_lo, &tmB_lo, &full_bar[stage], kb * Cfg::BK, nt * BN);
@@ -295,11 +297,11 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], 1);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
+              for (int j = 0; j < 16; ++j) o[j] = P.pool_avg ? o[j] + u[j] : max_nan(o[j], u[j]);
 #pragma unroll
               for (int j = 0; j < 16; ++j) u[j] = __shfl_xor_sync(0xffffffffu, o[j], P.tw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = max_nan(o[j], u[j]);
+              for (int j = 0; j < 16; ++j) o[j] = P.pool_avg ? (o[j] + u[j]) * 0.25f : max_nan(o[j], u[j]);
             }
             if (writer && n0 < P.Cout) {
               __align__(16) __nv_bfloat16 hi[16];

@@ -274,7 +274,7 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.target_d = c->norm_target;
   P.rms_min_d = c->norm_rms_min;
   P.eps_d = c->norm_eps;
-  if (c->scalar_f64)      // the per-call floats must be the float32 images of the context's doubles
+  if (c->scalar_f64 && normalize)      // the per-call floats must be the float32 images of the context's doubles
     AVLD_CHECK(target_rms == static_cast<float>(c->norm_target) && rms_min == static_cast<float>(c->norm_rms_min) &&
                    eps == static_cast<float>(c->norm_eps),
                AVLD_ERR_INVALID, "numpy-1 scalar mode: target_rms / rms_min / eps differ from avld_ctx_set_normalization");

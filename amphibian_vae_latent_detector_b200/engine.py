@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from .radial_fit import RadialFit, fit_radial
 from .map_fit import MapFit, fit_map
-from .encoder import ConvOp, EncoderProgram, LinearOp, export_program
+from .encoder import AddOp, AffineOp, ConvOp, EncoderProgram, LinearOp, PoolOp, export_program
 
 DEFAULTS = dict(sr=48000, n_fft=2048, hop_length=384, n_mels=64, fmin=150.0, fmax=15000.0, target_frames=192,
                 amin=1e-10, top_db=80.0)
@@ -164,26 +164,48 @@ class Engine:
         already exported :class:`EncoderProgram`."""
         prog = module_or_program if isinstance(module_or_program, EncoderProgram) else \
             export_program(module_or_program, self.target_frames, self.n_mels)
-        layers = (_lib.Layer * len(prog.ops))()
+        if prog.in_hw[0] * prog.n_seg != self.target_frames or prog.in_hw[1] != self.n_mels:
+            raise ValueError(f"the program was exported for {prog.n_seg} x {prog.in_hw} feature segments, the engine makes "
+                             f"[{self.target_frames}, {self.n_mels}] images")
+        ops = (_lib.Op * len(prog.ops))()
         keep = []
+
+        def fptr(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_float))
+
+        null = C.POINTER(C.c_float)()
         for i, op in enumerate(prog.ops):
-            w = np.ascontiguousarray(op.weight, dtype=np.float32)
-            b = np.ascontiguousarray(op.bias, dtype=np.float32)
-            keep += [w, b]
-            L = layers[i]
+            o = ops[i]
+            o.in1, o.ksize, o.stride, o.pad, o.relu, o.pool, o.in_h, o.in_w = -1, 1, 1, 0, 0, 0, 1, 1
+            o.weight, o.bias = null, null
             if isinstance(op, ConvOp):
-                cout, kh, _, cin = w.shape
-                L.kind, L.c_in, L.c_out, L.ksize, L.stride, L.pad = 0, cin, cout, kh, op.stride, op.pad
-                L.relu, L.pool, L.in_h, L.in_w = int(op.relu), op.pool, op.in_hw[0], op.in_hw[1]
+                cout, kh, _, cin = op.weight.shape
+                o.kind, o.in0, o.out, o.c_in, o.c_out = _lib.OP_CONV, op.src, op.dst, cin, cout
+                o.ksize, o.stride, o.pad, o.relu = kh, op.stride, op.pad, int(op.relu)
+                o.pool = 0 if op.pool == 1 else (2 if op.pool_avg else 1)
+                o.in_h, o.in_w = op.in_hw
+                o.weight, o.bias = fptr(op.weight), fptr(op.bias)
             elif isinstance(op, LinearOp):
-                L.kind, L.c_in, L.c_out, L.ksize, L.stride, L.pad = 1, w.shape[1], w.shape[0], 1, 1, 0
-                L.relu, L.pool, L.in_h, L.in_w = int(op.relu), 1, 1, 1
+                o.kind, o.in0, o.out = _lib.OP_LINEAR, op.src, op.dst
+                o.c_in, o.c_out, o.relu = op.weight.shape[1], op.weight.shape[0], int(op.relu)
+                o.weight, o.bias = fptr(op.weight), fptr(op.bias)
+            elif isinstance(op, AddOp):
+                o.kind, o.in0, o.in1, o.out, o.relu = _lib.OP_ADD, op.a, op.b, op.dst, int(op.relu)
+            elif isinstance(op, AffineOp):
+                o.kind, o.in0, o.out, o.relu = _lib.OP_AFFINE, op.src, op.dst, int(op.relu)
+                o.c_in = o.c_out = int(op.scale.shape[0])
+                o.weight, o.bias = fptr(op.scale), fptr(op.shift)
+            elif isinstance(op, PoolOp):
+                o.kind, o.in0, o.out = _lib.OP_POOL, op.src, op.dst
+                o.ksize, o.stride, o.pool = op.k, op.stride, 2 if op.avg else 1
+                o.in_h, o.in_w = op.in_hw
             else:
                 raise TypeError(type(op))
-            L.weight = w.ctypes.data_as(C.POINTER(C.c_float))
-            L.bias = b.ctypes.data_as(C.POINTER(C.c_float))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.avld_encoder_load(self._h, layers, len(prog.ops)))
+            _lib.check(self.lib.avld_encoder_load_program(self._h, ops, len(prog.ops), prog.out, int(prog.out_nchw is not None),
+                                                          prog.in_hw[0], prog.n_seg))
         self.latent_dim = prog.latent_dim
         self.program = prog
         return prog

@@ -72,6 +72,30 @@ typedef struct avld_layer {
   const float* bias;
 } avld_layer;
 
+/* One operation of an encoder PROGRAM: a dataflow graph over numbered tensors (tensor 0 = one feature segment,
+ * [seg_frames, n_mels], single channel; images are NHWC on the device).  What encoder.py::export_program emits for an
+ * nn.Module built from Conv2d / BatchNorm2d / ReLU / Max- / AvgPool2d / AdaptiveAvgPool2d(1) / residual add / Flatten /
+ * Linear; weights are host pointers, copied (and padded to the kernels' channel granularity) at load. */
+enum {
+  AVLD_OP_CONV = 0,    /* out = pool(act(conv(in0) + bias)); weight [c_out][k][k][c_in]; stride 1 or 2; pool 0 none, 1 max 2x2,
+                          2 average 2x2 (after the activation) */
+  AVLD_OP_LINEAR = 1,  /* out = act(in0 . W^T + bias); weight [c_out][c_in], c_in in NHWC-flatten order of in0 */
+  AVLD_OP_ADD = 2,     /* out = act(in0 + in1): the residual connection */
+  AVLD_OP_AFFINE = 3,  /* out = act(in0 * weight[c] + bias[c]): a BatchNorm that cannot be folded, a lone ReLU */
+  AVLD_OP_POOL = 4     /* pool 1 max / 2 average over ksize x ksize windows with `stride`, no padding; ksize 0 = global average */
+};
+typedef struct avld_op {
+  int32_t kind;
+  int32_t in0, in1, out;       /* tensor ids; in1 = -1 unless AVLD_OP_ADD; every id is written exactly once */
+  int32_t c_in, c_out;
+  int32_t ksize, stride, pad;
+  int32_t relu;                /* act = ReLU */
+  int32_t pool;
+  int32_t in_h, in_w;          /* of in0 (checked against the producer) */
+  const float* weight;
+  const float* bias;
+} avld_op;
+
 /* A requested order statistic: the `rank`-th smallest (0-based) of radii[:, species] over the rows
  * whose label == species (side 0, "in class") or label != species and label >= 0 (side 1). */
 typedef struct avld_rank_query {
@@ -136,6 +160,13 @@ int avld_normalize_logmel(avld_ctx* ctx, const float* x, float* feat, uint8_t* o
 /* ---- L1/E1/E2: encoder (map_detector_core.py:150-179, :270-300) --------------------------------
  * encoder_load is synchronous (copies and pre-splits the weights, builds TMA descriptors). */
 int avld_encoder_load(avld_ctx* ctx, const avld_layer* layers, int32_t n_layers);
+/* General form.  out_tensor = id of the latent; out_is_map != 0: the latent is a feature map [C, H, W], flattened in NCHW
+ * order as the reference does for rank > 2 outputs (map_detector_core.py:294-295).  The feature image [target_frames,
+ * n_mels] is cut into n_seg segments of seg_frames frames (seg_frames * n_seg == target_frames), each one runs through
+ * the program, and the chunk's latent is the mean over its segments -- the reference's `t.mean(dim=1)` for encoders that
+ * return [B, n_seg, C] (map_detector_core.py:292-293, 07_encode_wav_to_latent.py:287-291). */
+int avld_encoder_load_program(avld_ctx* ctx, const avld_op* ops, int32_t n_ops, int32_t out_tensor, int32_t out_is_map,
+                              int32_t seg_frames, int32_t n_seg);
 /* feat: dev float32 [n, target_frames, n_mels] -> mu: dev float32 [n, D] (the latent mean). */
 int avld_encoder_forward(avld_ctx* ctx, const float* feat, float* mu, int64_t n, void* stream);
 
