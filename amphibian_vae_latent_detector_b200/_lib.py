@@ -66,6 +66,8 @@ _SIGNATURES = {
     "avld_stage_count": (C.c_int, []),
     "avld_stage_name": (C.c_char_p, [C.c_int]),
     "avld_rms_normalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
+    "avld_resample_len": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "avld_resample": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "avld_logmel": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "avld_normalize_logmel": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "avld_encoder_load": (C.c_int, [_P, C.POINTER(Layer), C.c_int32]),

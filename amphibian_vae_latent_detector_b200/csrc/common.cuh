@@ -182,6 +182,11 @@ struct avld_ctx {
   void* h_stage = nullptr;         // pinned staging for results (a D2H into pageable memory would block the host
   size_t h_stage_bytes = 0;        // thread until the slab's kernels finish and serialise copy against compute)
 
+  // resampling filter table of the last (sr_in, sr_out) pair (resample.cu)
+  double* d_rs_win = nullptr;
+  double* d_rs_delta = nullptr;
+  int rs_sr_in = 0, rs_sr_out = 0;
+
   // order-statistics scratch
   unsigned int* d_hist = nullptr;
   size_t hist_bytes = 0;

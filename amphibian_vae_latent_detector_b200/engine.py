@@ -136,6 +136,16 @@ class Engine:
         return y, ok, rms
 
     # ------------------------------------------------------------------ M2-M5 + E0
+    def resample(self, y: torch.Tensor, sr_in: int, sr_out: int) -> torch.Tensor:
+        """``librosa.resample(y, orig_sr=sr_in, target_sr=sr_out)`` (``kaiser_best``) of a mono float32 signal ``[n]``."""
+        y = self._dev(y, torch.float32, "y")
+        if y.ndim != 1:
+            raise ValueError("y must be a 1-D mono signal")
+        n_out = int(self.lib.avld_resample_len(y.shape[0], int(sr_in), int(sr_out)))
+        out = torch.empty(n_out, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.avld_resample(self._h, _ptr(y), y.shape[0], int(sr_in), int(sr_out), _ptr(out), n_out, _stream()))
+        return out
+
     def logmel(self, y: torch.Tensor) -> torch.Tensor:
         """-> features ``[n, T, M]`` float32 (= ``wav_to_mel(...).T`` per chunk)."""
         y = self._dev(y, torch.float32, "y")

@@ -154,7 +154,8 @@ def _read_ieee_float_wav(path):
 def load_wav(path, sr: int = 48000) -> np.ndarray:
     """``librosa.load(path, sr=sr, mono=True)`` for WAV files: float32 samples exactly as libsndfile converts them
     (PCM_16 / 2^15, PCM_24 / 2^23, PCM_32 / 2^31, PCM_U8 (u - 128) / 2^7, IEEE float as stored), channels averaged.
-    The sample rate must already be ``sr``: resampling is not implemented and raises."""
+    A file whose rate differs from ``sr`` is resampled as librosa 0.9.2 does (``res_type="kaiser_best"``) -- on the GPU
+    (``avld_resample``), after the mono mix, like ``librosa.load``."""
     is_float = False
     try:
         with wave.open(str(path), "rb") as w:
@@ -165,8 +166,6 @@ def load_wav(path, sr: int = 48000) -> np.ndarray:
             raise
         nch, width, rate, raw = _read_ieee_float_wav(path)
         is_float = True
-    if rate != sr:
-        raise RuntimeError(f"{path}: sample rate {rate} != {sr}; resampling is not implemented on this path")
     if is_float:
         x = np.frombuffer(raw, dtype="<f4" if width == 4 else "<f8").astype(np.float32)
     elif width == 2:
@@ -184,7 +183,11 @@ def load_wav(path, sr: int = 48000) -> np.ndarray:
         raise RuntimeError(f"{path}: unsupported sample width {width}")
     if nch > 1:
         x = x.reshape(-1, nch).mean(axis=1).astype(np.float32)     # librosa to_mono
-    return np.ascontiguousarray(x)
+    x = np.ascontiguousarray(x)
+    if sr is not None and rate != sr:                              # librosa.load: resample after to_mono
+        eng = _engine(144000, 0)
+        x = eng.resample(torch.from_numpy(x).to(eng.device), int(rate), int(sr)).cpu().numpy()
+    return x
 
 
 def write_wav_pcm16(path, y: np.ndarray, sr: int) -> None:

@@ -147,6 +147,15 @@ const char* avld_stage_name(int stage);
 int avld_rms_normalize(avld_ctx* ctx, const float* x, float* y, uint8_t* ok, float* rms, int64_t n,
                        float target_rms, float rms_min, float eps, int quantize_pcm16, void* stream);
 
+/* ---- M1: the resampling of `librosa.load(path, sr=sr)` (map_detector_core.py:210, 00_normalize_dataset_rms.py:51) for a
+ * file whose rate differs from sr: librosa 0.9.2 resample(res_type="kaiser_best") = resampy's Kaiser-windowed sinc
+ * interpolation, restated tap for tap (float64 weights, float32 running sum).  x: dev float32 [n_in] mono samples at
+ * sr_in -> y: dev float32 [n_out], n_out = avld_resample_len(n_in, sr_in, sr_out) = ceil(n_in * sr_out / sr_in).
+ * Synchronous (returns after the kernel). */
+int64_t avld_resample_len(int64_t n_in, int32_t sr_in, int32_t sr_out);
+int avld_resample(avld_ctx* ctx, const float* x, int64_t n_in, int32_t sr_in, int32_t sr_out, float* y, int64_t n_out,
+                  void* stream);
+
 /* ---- M2-M5 + E0: wav_to_mel after the load (map_detector_core.py:219-237) and the transpose of
  * map_detector_core.py:267-268.  y: dev float32 [n, chunk_len] -> feat: dev float32
  * [n, target_frames, n_mels] (the encoder's [B,1,T,M] input). */

@@ -235,5 +235,84 @@ def load(path, sr: Optional[int] = 22050, mono: bool = True, offset=0.0, duratio
         y = y[:, : int(round(duration * sr_native))]
     y = np.mean(y, axis=0) if mono else (y[0] if y.shape[0] == 1 else y)
     if sr is not None and sr != sr_native:
-        raise NotImplementedError("oracle load(): resampling is outside the hot path")
+        y = resample(np.ascontiguousarray(y, dtype=dtype), sr_native, sr, res_type=res_type)
     return np.ascontiguousarray(y, dtype=dtype), (sr if sr is not None else sr_native)
+
+
+# ----------------------------------------------------------------------------------------
+# librosa 0.9.2 core/audio.py::resample with res_type="kaiser_best" = resampy 0.2.2 (the versions the reference
+# pins: requirements-thesis-baseline-macos-arm64.txt:33 and the resampy that librosa 0.9.2 depends on).  Neither package
+# is installed here; this restates their published algorithm:
+#   resampy/filters.py::sinc_window   interp_win = taper * rolloff * sinc(rolloff * t), t = linspace(0, num_zeros, n + 1),
+#                                     taper = right half of scipy.signal.kaiser(2 n + 1, beta)
+#                                     kaiser_best: num_zeros 64, precision 9 (512 table samples per zero crossing),
+#                                     rolloff 0.9475937167399596, beta 14.769656459379492
+#   resampy/interpn.py::resample_f    per output sample a left and a right filter wing over the input with linear
+#                                     interpolation between table entries; y (the input's dtype: float32) is updated in
+#                                     place, so every tap's contribution is rounded to float32 as it is added
+#   librosa resample                  n_out = ceil(n * ratio), fix_length, no rescaling (scale=False)
+# PARITY UNPINNED against resampy itself; cross-checked against torchaudio's Kaiser resampler with the same parameters
+# (tests/test_oracle_pinning.py).
+# ----------------------------------------------------------------------------------------
+KAISER_BEST = dict(num_zeros=64, precision=9, rolloff=0.9475937167399596, beta=14.769656459379492)
+
+
+def resampy_filter(num_zeros=64, precision=9, rolloff=0.9475937167399596, beta=14.769656459379492):
+    """-> (interp_win float64 [num_zeros * 2^precision + 1], num_table = 2^precision)."""
+    from scipy.signal.windows import kaiser
+    num_bits = 2 ** precision
+    n = num_bits * num_zeros
+    sinc_win = rolloff * np.sinc(rolloff * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+    taper = kaiser(2 * n + 1, beta)[n:]
+    return taper * sinc_win, num_bits
+
+
+def resample(y: np.ndarray, orig_sr: int, target_sr: int, res_type: str = "kaiser_best") -> np.ndarray:
+    """``librosa.resample(y, orig_sr=, target_sr=, res_type="kaiser_best")`` for a 1-D float32 signal."""
+    if res_type != "kaiser_best":
+        raise NotImplementedError(res_type)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    if orig_sr == target_sr:
+        return y
+    ratio = float(target_sr) / orig_sr
+    n_out = int(np.ceil(y.shape[-1] * ratio))
+    interp_win, num_table = resampy_filter(**KAISER_BEST)
+    interp_win = interp_win.copy()
+    if ratio < 1:
+        interp_win *= ratio
+    interp_delta = np.zeros_like(interp_win)
+    interp_delta[:-1] = np.diff(interp_win)
+    n_res = int(y.shape[0] * ratio)                    # resampy: shape[axis] = int(shape[axis] * sample_ratio)
+    out = np.zeros(n_res, dtype=np.float32)
+    scale = min(1.0, ratio)
+    time_increment = 1.0 / ratio
+    index_step = int(scale * num_table)
+    nwin = interp_win.shape[0]
+    n_orig = y.shape[0]
+    t = np.arange(n_res)
+    time_register = np.zeros(n_res)                    # accumulated by repeated addition in the reference loop
+    acc = 0.0
+    for i in range(n_res):
+        time_register[i] = acc
+        acc += time_increment
+    n = time_register.astype(np.int64)
+    frac = scale * (time_register - n)
+    for wing in (0, 1):
+        if wing == 1:
+            frac = scale - frac
+        index_frac = frac * num_table
+        offset = index_frac.astype(np.int64)
+        eta = index_frac - offset
+        limit = (nwin - offset) // index_step
+        kmax = np.minimum(n + 1, limit) if wing == 0 else np.minimum(n_orig - n - 1, limit)
+        for k in range(int(kmax.max()) if kmax.size else 0):
+            live = k < kmax
+            idx = np.where(live, offset + k * index_step, 0)
+            weight = interp_win[idx] + eta * interp_delta[idx]
+            src = np.where(live, n - k if wing == 0 else n + k + 1, 0)
+            contrib = np.where(live, weight * y[src].astype(np.float64), 0.0)
+            out = np.where(live, (out.astype(np.float64) + contrib).astype(np.float32), out)
+    # librosa: util.fix_length(y_hat, size=n_out)
+    if out.shape[0] < n_out:
+        out = np.pad(out, (0, n_out - out.shape[0]))
+    return np.ascontiguousarray(out[:n_out], dtype=np.float32)

@@ -129,3 +129,26 @@ def test_auto_find_frames_and_report(tmp_path):
     z = api.encode_wav_to_latent(enc, wav, None, duration=3.0, sr=48000, n_mels=64, fmin=150.0, fmax=15000.0,
                                  hop_length=384, n_fft=2048, target_frames=192)
     assert np.max(np.abs(v192 - z)) / np.max(np.abs(z)) < 1e-3
+
+
+def test_load_wav_resamples_like_librosa_kaiser_best(tmp_path):
+    """M1: a file whose rate differs from `sr` (librosa.load(path, sr=sr), core:210): avld_resample against the oracle's
+    restatement of resampy kaiser_best -- the same taps in the same order, so float32 results agree to rounding of the
+    filter table (1e-6 of the peak); up-sampling, down-sampling, stereo (mono mix first), odd lengths."""
+    import wave
+    from amphibian_vae_latent_detector_b200 import reference_api as api
+    from oracle import librosa_port as lp
+    rng = np.random.default_rng(5)
+    for sr_in, nch, n in ((44100, 1, 30011), (96000, 1, 50000), (22050, 2, 12345), (8000, 1, 4000)):
+        v = np.clip(rng.standard_normal((n, nch)) * 6000 + 8000 * np.sin(np.arange(n) * 0.05)[:, None], -32768, 32767).astype("<i2")
+        path = tmp_path / f"r{sr_in}.wav"
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(nch); w.setsampwidth(2); w.setframerate(sr_in); w.writeframes(v.tobytes())
+        got = api.load_wav(path, sr=48000)
+        mono = np.mean((v.astype(np.float32) / np.float32(32768.0)).T, axis=0).astype(np.float32) if nch > 1 else \
+            v[:, 0].astype(np.float32) / np.float32(32768.0)
+        ref = lp.resample(mono, sr_in, 48000)
+        assert got.dtype == np.float32 and got.shape == ref.shape, (got.shape, ref.shape)
+        assert np.max(np.abs(got - ref)) <= 2e-6 * np.max(np.abs(ref)), (sr_in, np.max(np.abs(got - ref)))
+        o, _ = lp.load(path, sr=48000)
+        assert np.array_equal(o, ref)

@@ -108,7 +108,9 @@ def test_rms_numpy1_scalar_semantics_bit_exact(standin_encoder):
     assert np.array_equal(y3.cpu().numpy().view(np.uint32), y3o.view(np.uint32))
     from amphibian_vae_latent_detector_b200 import _lib
     with pytest.raises(_lib.AvldError):                          # per-call constants that contradict the context's
-        eng3.rms_normalize(x.cuda())
+        eng3.rms_normalize(x.cuda(), target_rms=0.05)
+    y3b, _, _ = eng3.rms_normalize(x.cuda())                      # defaults = the engine's own constants
+    assert torch.equal(y3b, y3)
     eng3.load_encoder(standin_encoder)
     cent = np.zeros((4, 128), np.float32)
     thr = np.full(4, 1e9)
