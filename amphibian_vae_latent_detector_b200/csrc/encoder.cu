@@ -564,8 +564,9 @@ extern "C" int avld_encoder_load_program(avld_ctx* c, const avld_op* ops, int32_
     OpDev L{};
     L.src = s.in0; L.src2 = s.in1; L.dst = s.out;
     L.ksize = s.ksize; L.stride = s.stride; L.pad = s.pad; L.relu = s.relu != 0;
-    TensorDev* in = tensor_at(s.in0);
-    AVLD_CHECK(in != nullptr, AVLD_ERR_INVALID, "op %d reads tensor %d before it is written", i, s.in0);
+    AVLD_CHECK(tensor_at(s.in0) != nullptr, AVLD_ERR_INVALID, "op %d reads tensor %d before it is written", i, s.in0);
+    const TensorDev in_copy = *tensor_at(s.in0);      // by value: define() below may grow `tens` and move its elements
+    const TensorDev* in = &in_copy;
     if (s.kind == AVLD_OP_CONV) {
       AVLD_CHECK(s.weight && s.bias, AVLD_ERR_INVALID, "op %d: NULL weights", i);
       AVLD_CHECK(in->w > 1 || in->h > 1 || s.ksize == 1, AVLD_ERR_INVALID, "op %d: convolution on a vector", i);
@@ -646,8 +647,9 @@ extern "C" int avld_encoder_load_program(avld_ctx* c, const avld_op* ops, int32_
       AVLD_TRY(encode_tmap_2d(&L.tm_w_hi, L.w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, co_pad, L.K * 2, 64, L.bn, 128));
       AVLD_TRY(encode_tmap_2d(&L.tm_w_lo, L.w_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, L.K, co_pad, L.K * 2, 64, L.bn, 128));
     } else if (s.kind == AVLD_OP_ADD) {
-      TensorDev* in2 = tensor_at(s.in1);
-      AVLD_CHECK(in2 != nullptr && s.in0 != 0 && s.in1 != 0, AVLD_ERR_INVALID, "op %d: add reads an undefined tensor", i);
+      AVLD_CHECK(tensor_at(s.in1) != nullptr && s.in0 != 0 && s.in1 != 0, AVLD_ERR_INVALID, "op %d: add reads an undefined tensor", i);
+      const TensorDev in2_copy = *tensor_at(s.in1);
+      const TensorDev* in2 = &in2_copy;
       AVLD_CHECK(in2->c == in->c && in2->h == in->h && in2->w == in->w && in2->c_pad == in->c_pad, AVLD_ERR_INVALID, "op %d: add of different shapes", i);
       L.kind = OP_ADD;
       AVLD_TRY(define(s.out, in->c, in->h, in->w, false));

@@ -370,11 +370,12 @@ class Engine:
 
     # ------------------------------------------------------------------ the fit (08:530-558), grid-aware, multi-GPU
     def fit_radial(self, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 0.95,
-                   q_out: float | Sequence[float] = 0.01, *, group=None, semantics: str = "numpy2") -> RadialFit:
+                   q_out: float | Sequence[float] = 0.01, *, group=None, semantics: str = "numpy2",
+                   shard_rows: Optional[int] = None) -> RadialFit:
         """See :func:`radial_fit.fit_radial` (this engine supplies the CUDA kernels)."""
         Z = self._dev(Z, torch.float32, "Z")
         label = self._dev(label, torch.int32, "label")
-        return fit_radial(self, Z, label, K, q_in, q_out, group=group, semantics=semantics)
+        return fit_radial(self, Z, label, K, q_in, q_out, group=group, semantics=semantics, shard_rows=shard_rows)
 
 
 def priority_ranks(species: Sequence[str], priority: Sequence[str]) -> np.ndarray:

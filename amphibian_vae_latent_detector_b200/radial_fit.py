@@ -34,16 +34,23 @@ class RadialFit:
     radii_local: Optional[torch.Tensor] = None   # [n_local, K] radii of this rank's rows to the fitted centroids
 
 
-def all_gather_rows(radii: torch.Tensor, label: torch.Tensor, group) -> Tuple[torch.Tensor, torch.Tensor]:
+def all_gather_rows(radii: torch.Tensor, label: torch.Tensor, group, shard_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-gather of ragged row blocks: pad every rank to the largest block, mark the padding with
-    label -1 (ignored by the selection kernels), gather radii and labels."""
+    label -1 (ignored by the selection kernels), gather radii and labels.  ``shard_rows`` = a block size every rank
+    already agrees on (>= each rank's rows, e.g. ceil(n_total / world) for contiguous shards): no size exchange and no
+    host synchronisation, the gather is stream-ordered behind the radii kernel."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    n_local = torch.tensor([radii.shape[0]], dtype=torch.int64, device=radii.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    n_max = max(int(s.item()) for s in sizes)
+    if shard_rows is not None:
+        if radii.shape[0] > shard_rows:
+            raise ValueError(f"shard_rows = {shard_rows} is smaller than this rank's {radii.shape[0]} rows")
+        n_max = int(shard_rows)
+    else:
+        n_local = torch.tensor([radii.shape[0]], dtype=torch.int64, device=radii.device)
+        sizes = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(sizes, n_local, group=group)
+        n_max = max(int(s.item()) for s in sizes)
     K = radii.shape[1]
     pr = torch.zeros(n_max, K, dtype=radii.dtype, device=radii.device)
     pl = torch.full((n_max,), -1, dtype=label.dtype, device=label.device)
@@ -57,14 +64,17 @@ def all_gather_rows(radii: torch.Tensor, label: torch.Tensor, group) -> Tuple[to
 
 
 def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 0.95,
-               q_out: float | Sequence[float] = 0.01, *, group=None, semantics: str = "numpy2") -> RadialFit:
+               q_out: float | Sequence[float] = 0.01, *, group=None, semantics: str = "numpy2",
+               shard_rows: Optional[int] = None) -> RadialFit:
     """Centroids, in/out radius quantiles and thresholds for every species and every ``q_out``.
 
     With a ``torch.distributed`` ``group`` (one rank per GPU, rows of ``Z`` sharded): per-species
     sums/counts are all-reduced in ONE float64 message (so the centroid does not depend on the rank
     count), every rank forms the same centroids and computes its local radii, and radii + labels are
     all-gathered so that every rank selects the same exact order statistics: thresholds are
-    bit-identical on all ranks and equal to the single-rank result.
+    bit-identical on all ranks and equal to the single-rank result.  With ``shard_rows`` (see :func:`all_gather_rows`) the
+    device work -- centroid kernel, all-reduce, radii kernel, all-gather -- is enqueued without a host synchronisation in
+    between; the host first looks at the counts when it plans the rank queries of the selection.
     """
     import torch.distributed as dist
 
@@ -80,13 +90,13 @@ def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         sums = packed[:K * D].reshape(K, D)
         cnts = packed[K * D:].round().to(torch.int64)
-    counts = cnts.cpu().numpy()
     cent = (sums / cnts.clamp_min(1).to(torch.float64)[:, None]).to(torch.float32)   # mean(...).astype(f32), 08:316
     radii = ops.radii(Z, cent)
     radii_local = radii
     lab = label
     if distributed:
-        radii, lab = all_gather_rows(radii, label, group)
+        radii, lab = all_gather_rows(radii, label, group, shard_rows)
+    counts = cnts.cpu().numpy()            # first host read: everything above is already enqueued
     n_tot = int(counts.sum())
 
     queries: List[Tuple[int, int, int]] = []

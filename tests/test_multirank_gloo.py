@@ -60,6 +60,11 @@ def _worker(rank, world, port, out_dir):
     sl = slice(0, cut) if rank == 0 else slice(cut, None)
     fit = fit_radial(NumpyOps(), torch.from_numpy(Z[sl]), torch.from_numpy(labels[sl]), 4, 0.95,
                      (0.10, 0.15, 0.20, 0.25), group=dist.group.WORLD)
+    # the same with a block size all ranks agree on beforehand (no size exchange, no host sync before the gather)
+    fit2 = fit_radial(NumpyOps(), torch.from_numpy(Z[sl]), torch.from_numpy(labels[sl]), 4, 0.95,
+                      (0.10, 0.15, 0.20, 0.25), group=dist.group.WORLD, shard_rows=1701)
+    assert np.array_equal(fit.rk, fit2.rk, equal_nan=True) and np.array_equal(fit.centroids, fit2.centroids, equal_nan=True)
+    assert np.array_equal(fit.summaries["out"], fit2.summaries["out"], equal_nan=True)
     np.savez(Path(out_dir) / f"rank{rank}.npz", centroids=fit.centroids, rk=fit.rk, rk_in=fit.rk_in, rk_out=fit.rk_out,
              counts=fit.counts, s_in=fit.summaries["in"], s_out=fit.summaries["out"])
     dist.destroy_process_group()
