@@ -11,11 +11,15 @@
 
 using namespace avld;
 
+// `input_consumed` (optional) is recorded once the audio buffer has been read for the last time: the operand kernel is its
+// last reader (it reads the chunk itself in passes without the PCM_16 round trip, prep_kernel's integers otherwise)
 static int encode_pass(avld_ctx* c, const float* x, const int16_t* x16, float* mu, uint8_t* ok, int m, float target_rms,
-                       float rms_min, float eps, int quantize, cudaStream_t st) {
+                       float rms_min, float eps, int quantize, cudaStream_t st, cudaEvent_t input_consumed = nullptr) {
   AVLD_CHECK(c->features_ok, AVLD_ERR_UNSUPPORTED, "chunk_len %d is outside the feature kernels' range", c->L);
   AVLD_TRY(launch_prep(c, x, x16, nullptr, true, true, ok, nullptr, m, target_rms, rms_min, eps, quantize, st));
-  AVLD_TRY(launch_stft_mel(c, m, st));
+  AVLD_TRY(launch_fold3(c, m, st));
+  if (input_consumed) AVLD_CUDA(cudaEventRecord(input_consumed, st));
+  AVLD_TRY(launch_dftf3(c, m, st));
   AVLD_TRY(launch_logmel_post(c, c->d_feat, m, st));
   AVLD_TRY(launch_encoder(c, c->d_feat, mu, m, st));
   return AVLD_OK;
@@ -106,22 +110,28 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
 
   // slab i: H2D on the copy stream into buffer i&1 while the compute stream works on slab i-1;
   // results of slab i are read back on the compute stream right after its kernels.
-  // Slab sizes: full passes in the middle, a quarter pass first and last -- the first copy and the last slab's kernels are
-  // the only parts of the call that nothing overlaps, so they are kept short (the link, not the GPU, paces this call).
+  // Slab sizes.  The copies run back to back (a slab buffer is free again as soon as the operand kernel has read it), so
+  // the call takes the copy time plus whatever is left to compute when the last byte has landed: the last slab's kernels,
+  // and any backlog in front of them.  Full passes first, then a ramp down to a quarter pass in steps the kernels keep up
+  // with (a pass computes ~1.6x faster than it copies, so each slab is done before the next, <= 1.67x smaller one has
+  // arrived); below a quarter pass the kernels lose efficiency faster than the tail shrinks (measured: tools/host_trace_probe.py).
   std::vector<int> sizes;
   {
-    const int64_t mb = c->max_batch, q = std::max<int64_t>(mb / 4, 1);
+    const int64_t mb = c->max_batch;
+    std::vector<int> ramp;
     int64_t left = n;
-    if (n >= 2 * mb) {
-      sizes.push_back(static_cast<int>(q));
-      left -= 2 * q;
-    }
+    if (n >= 3 * mb && mb >= 8)
+      for (int64_t sz : {mb * 5 / 8, mb * 3 / 8, mb / 4}) {
+        ramp.push_back(static_cast<int>(sz));
+        left -= sz;
+      }
     while (left > 0) {
       const int64_t m = std::min(left, mb);
       sizes.push_back(static_cast<int>(m));
       left -= m;
     }
-    if (n >= 2 * mb) sizes.push_back(static_cast<int>(q));
+    if (!ramp.empty() && sizes.size() >= 2 && sizes.back() < mb) std::swap(sizes.back(), sizes.front());   // the odd remainder goes first
+    sizes.insert(sizes.end(), ramp.begin(), ramp.end());
   }
   // one slab; any failure leaves copies / kernels in flight on both streams, so the caller drains them before returning
   auto run_slab = [&](int64_t slab, int64_t i) -> int {
@@ -138,8 +148,7 @@ static int encode_detect_host_impl(avld_ctx* c, const void* x_host, int sample_b
     AVLD_TRY(encode_pass(c, sample_bytes == 4 ? c->d_xbuf[b] : nullptr,
                          sample_bytes == 2 ? reinterpret_cast<const int16_t*>(c->d_xbuf[b]) : nullptr, c->d_mu, c->d_ok, m,
                          static_cast<float>(c->norm_target), static_cast<float>(c->norm_rms_min),
-                         static_cast<float>(c->norm_eps), quantize_pcm16, sc));
-    AVLD_CUDA(cudaEventRecord(c->ev_done[b], sc));                         // x buffer consumed by the prep kernel
+                         static_cast<float>(c->norm_eps), quantize_pcm16, sc, c->ev_done[b]));   // buffer b is free after the operand kernel
     AVLD_TRY(avld_radii(c, c->d_mu, c->d_cent, c->d_radii, m, K, D, sc));
     AVLD_TRY(avld_decide(c, c->d_radii, c->d_thr, c->d_prio, c->d_pred, c->d_best, m, K, sc));
     AVLD_CUDA(cudaMemcpyAsync(s_pred + i, c->d_pred, static_cast<size_t>(m) * sizeof(int32_t), cudaMemcpyDeviceToHost, sc));

@@ -26,6 +26,7 @@ struct ConvhParams {
   int cblocks;                 // channel blocks of CBLK input channels
   int resident;                // weights resident in shared memory (loaded once)
   uint32_t idesc;
+  uint32_t idesc2;              // BN = 64: the N = 2 BN form over the adjacent [W_hi | W_lo] blocks
   int H, W, Cout, relu, pool;  // conv output size (= input size), before pooling
   int pool_avg;                // the 2x2 pooling averages (after bias and ReLU) instead of taking the maximum
   int dbg;                     // AVLD_BRINGUP builds only: timing probe (AVLD_CONVH_DBG = 2, wrong results): hi*hi pass only
@@ -38,7 +39,6 @@ namespace {
 constexpr int kTW = 8, kTH = 16;                    // output tile: 16 rows x 8 columns = 128 pixels
 constexpr int kHW = kTW + 2, kHH = kTH + 2;         // halo
 constexpr int kHaloRows = kHW * kHH;                // 180 pixels
-constexpr int kThreads = 192;
 
 template <int BN, int CBLK>
 struct ConvhCfg {
@@ -53,13 +53,23 @@ struct ConvhCfg {
   static constexpr int HSTAGES_RES = (BUDGET - RES_BYTES) / HSTAGE > 6 ? 6 : (BUDGET - RES_BYTES) / HSTAGE;
   static constexpr int HSTAGES_STR = 2;
   static constexpr int WSTAGES_STR = (BUDGET - HSTAGES_STR * HSTAGE) / WSTAGE > 8 ? 8 : (BUDGET - HSTAGES_STR * HSTAGE) / WSTAGE;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // BN = 64: an N = 64 MMA reads 6 KB of shared memory for 32 cycles of tensor work and is bound by that read.  The hi and
+  // lo weight blocks of a tap are adjacent in shared memory, so A_hi x [W_hi | W_lo] is ONE N = 128 MMA into two column
+  // ranges of the accumulator (A is read once for both), A_lo x W_hi a second one into the first range; the epilogue adds
+  // the two ranges.  Two MMAs and 14 KB per K step instead of three and 18 KB.
+  static constexpr bool CONCAT = BN == 64;
+  static constexpr int ACC_COLS = CONCAT ? 2 * BN : BN;                   // TMEM columns of one accumulator
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = BUDGET + EXTRA + 1024;
+  // epilogue warps: one per TMEM lane quarter (two per quarter, half the columns each, measured no faster with BN = 64:
+  // 280.5 vs 282.3 us per 1024-chunk launch -- the epilogue is not what paces that layer)
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 }  // namespace
 
 template <int BN, int CBLK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(ConvhCfg<BN, CBLK>::THREADS, 1)
 convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const ConvhParams P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL)
@@ -96,7 +106,7 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * Cfg::EPI_WARPS);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -161,7 +171,7 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u, 200 + acc);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * Cfg::ACC_COLS);
         for (int cb = 0; cb < P.cblocks; ++cb) {
           mbar_wait(&h_full[hs], hphase, 300 + hs);
           tcgen05_fence_after();
@@ -185,10 +195,15 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < CBLK / 16; ++k) {
                   const uint64_t koff = static_cast<uint64_t>(k * 2);
-                  umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                  if (lo_passes) {
+                  if constexpr (Cfg::CONCAT) {
+                    umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc2, (cb | tap | k) != 0 ? 1u : 0u);   // [hi*hi | hi*lo]
                     umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
-                    umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                  } else {
+                    umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                    if (lo_passes) {
+                      umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                      umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                    }
                   }
                 }
               }
@@ -207,10 +222,15 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < CBLK / 16; ++k) {
                   const uint64_t koff = static_cast<uint64_t>(k * 2);
-                  umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
-                  if (lo_passes) {
+                  if constexpr (Cfg::CONCAT) {
+                    umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc2, (cb | tap | k) != 0 ? 1u : 0u);   // [hi*hi | hi*lo]
                     umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
-                    umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                  } else {
+                    umma_f16(d_tmem, da_hi + koff, db_hi + koff, P.idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                    if (lo_passes) {
+                      umma_f16(d_tmem, da_lo + koff, db_hi + koff, P.idesc, 1u);
+                      umma_f16(d_tmem, da_hi + koff, db_lo + koff, P.idesc, 1u);
+                    }
                   }
                 }
                 umma_commit(&w_empty[ws]);
@@ -229,8 +249,10 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..5, with BN = 64 also 6..9)
     const int quarter = warp & 3;
+    constexpr int kColsPerWarp = BN / (Cfg::EPI_WARPS / 4);
+    const int col_lo = ((warp - 2) >> 2) * kColsPerWarp;
     const int row = quarter * 32 + lane;                       // pixel (row / 8, row % 8) of the tile
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     int acc = 0;
@@ -244,12 +266,20 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const size_t opix = (static_cast<size_t>(img) * OH + h / P.pool) * OW + w / P.pool;
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tcgen05_fence_after();
-      const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
+      const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * Cfg::ACC_COLS);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = col_lo; c0 < col_lo + kColsPerWarp; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_acc + c0, v);
-        tmem_ld_wait();
+        if constexpr (Cfg::CONCAT) {
+          uint32_t v2[16];
+          tmem_ld16(t_acc + BN + c0, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         if (P.pool == 2) {
           // 2x2 max-pool as a reduce-scatter over the four lanes of a window (partners lane ^ 1 (w) and lane ^ 8 (h), same
           // warp): each exchange halves the columns a lane keeps, so a lane ends with 4 of the 16 columns, pooled, and
@@ -359,7 +389,7 @@ static int launch_one(avld_ctx* c, const CUtensorMap& a_hi, const CUtensorMap& a
   }
   const int grid = std::min(P.n_tiles, sm_count);
   if (grid < 1) return AVLD_OK;
-  kfn<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, P);
+  kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, P);
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }
@@ -384,6 +414,7 @@ int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUt
   P.n_tiles = n * P.tiles_w * P.tiles_h;
   P.cblocks = L.cblocks;
   P.idesc = avld_make_idesc(1, 1, 128, L.c_out);
+  P.idesc2 = avld_make_idesc(1, 1, 128, 2 * L.c_out);
   P.H = L.in_h; P.W = L.in_w; P.Cout = L.c_out; P.relu = L.relu; P.pool = L.pool; P.pool_avg = L.pool_avg;
   P.bias = L.bias;
 #ifdef AVLD_BRINGUP

@@ -310,6 +310,9 @@ static int build_ctx(avld_ctx* c) {
   c->n_levels = static_cast<int>(level_start.size()) - 1;
   AVLD_CHECK(static_cast<size_t>(c->n_leaves + c->n_nodes) * 4 <= 160 * 1024, AVLD_ERR_UNSUPPORTED, "chunk_len too large");
   std::vector<int32_t> off32(off.begin(), off.end()), len32(len.begin(), len.end());
+  c->leaves_regular = c->L % 8 == 0;
+  for (size_t i = 0; i < off32.size(); ++i)
+    c->leaves_regular = c->leaves_regular && off32[i] % 8 == 0 && len32[i] % 8 == 0 && len32[i] >= 8 && len32[i] <= 128;
   AVLD_TRY(dev_alloc(&c->d_leaf_off, off32.size()));
   AVLD_TRY(dev_alloc(&c->d_leaf_len, len32.size()));
   AVLD_TRY(dev_alloc(&c->d_nodes, nodes.size() + 1));

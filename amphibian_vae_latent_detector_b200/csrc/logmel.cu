@@ -28,45 +28,77 @@ struct PostParams {
   float amin, top_db;
 };
 
-template <typename T>
-__device__ __forceinline__ T block_reduce(T v, T* s_buf, bool is_max) {
+// max and NaN flag of the whole block in one exchange (NaN anywhere poisons the chunk exactly like numpy's max would)
+__device__ __forceinline__ float block_max_poison(float mx, bool bad, float* s_buf) {
+  float v = bad ? NAN : mx;
   for (int o = 16; o > 0; o >>= 1) {
-    const T u = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? (u > v ? u : v) : v + u;
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (v != v || u != u) ? NAN : fmaxf(u, v);
   }
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
   __syncthreads();
-  T r = s_buf[0];
-  for (int w = 1; w < (blockDim.x >> 5); ++w) r = is_max ? (s_buf[w] > r ? s_buf[w] : r) : r + s_buf[w];
+  float r = s_buf[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = (r != r || s_buf[w] != s_buf[w]) ? NAN : fmaxf(r, s_buf[w]);
   return r;
 }
 
-__global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
+// sum and sum of squares of the whole block (float64: sum v^2 - n mean^2 loses nothing at 2.4e4 elements of |v| <= 80)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* s_buf) {
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_buf[2 * (threadIdx.x >> 5)] = a; s_buf[2 * (threadIdx.x >> 5) + 1] = b; }
+  __syncthreads();
+  a = s_buf[0]; b = s_buf[1];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) { a += s_buf[2 * w]; b += s_buf[2 * w + 1]; }
+}
+
+// 10 log10(x) through the hardware log2 (MUFU.LG2: |error| < 2e-6 dB over the 100 dB this sees; the features carry the
+// fp16-split GEMM's 1e-5 anyway); explicitly rounded so that `db(x) - db(ref)` is exactly 0 at the reference element
+__device__ __forceinline__ float power_db(float x) { return __fmul_rn(3.01029995663981195f, __log2f(x)); }
+
+// Three sweeps per chunk: (1) sum + clear the per-class planes into shared memory, ref = max; (2) dB, floor, float64 sum and
+// sum of squares; (3) z-score + crop / pad + store.  log_spec.max() is exactly 0 (the dB of the reference element minus
+// itself), so the floor is -top_db and needs no reduction of its own.
+__global__ void __launch_bounds__(512, 2) logmel_post_kernel(const PostParams P) {
   extern __shared__ float s_db[];                 // [F*M]
-  __shared__ double s_red_d[16];
+  __shared__ double s_red_d[32];
   __shared__ float s_red_f[16];
   const int c = blockIdx.x, tid = threadIdx.x;
   const int n = P.F * P.M;
   float* __restrict__ src = P.melpow + static_cast<size_t>(c) * P.R * P.M;   // frames 0..F-1 are contiguous
 
-  // ref = np.max(S); NaN anywhere poisons the chunk exactly like numpy's max would
   float mx = -INFINITY;
   bool has_nan = false;
-  if (P.plane2 && (P.M & 3) == 0 && (P.plane2 & 3) == 0) {
-    // folded STFT: sum the per-class planes in a fixed order and clear them for the next pass, 16 bytes at a time
+  const bool vec = (P.M & 3) == 0 && (P.plane2 & 3) == 0;
+  if (P.n_planes == 3 && vec) {
+    // folded STFT: sum the per-class planes in a fixed order and clear them for the next pass, 16 bytes at a time; the
+    // nine loads of three steps are issued before their first use (the clears would otherwise order every load behind them)
     float4* src4 = reinterpret_cast<float4*>(src);
     const long long p4 = P.plane2 >> 2;
-    for (int i = tid; i < (n >> 2); i += blockDim.x) {
-      float4 v = src4[i];
-      for (int pl = 1; pl < P.n_planes; ++pl) {
-        const float4 u = src4[pl * p4 + i];
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    const int n4 = n >> 2, stride = blockDim.x;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = tid; i0 < n4; i0 += 3 * stride) {
+      float4 a[3], b[3], d[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n4) { a[u] = __ldcs(src4 + i); b[u] = __ldcs(src4 + p4 + i); d[u] = __ldcs(src4 + 2 * p4 + i); }
       }
-      for (int pl = 0; pl < P.n_planes; ++pl) src4[pl * p4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      reinterpret_cast<float4*>(s_db)[i] = v;
-      has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
-      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n4) {
+          float4 v = a[u];
+          v.x += b[u].x; v.y += b[u].y; v.z += b[u].z; v.w += b[u].w;
+          v.x += d[u].x; v.y += d[u].y; v.z += d[u].z; v.w += d[u].w;
+          src4[i] = zero; src4[p4 + i] = zero; src4[2 * p4 + i] = zero;
+          reinterpret_cast<float4*>(s_db)[i] = v;
+          has_nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+          mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+      }
     }
   } else {
     for (int i = tid; i < n; i += blockDim.x) {
@@ -80,49 +112,55 @@ __global__ void __launch_bounds__(512) logmel_post_kernel(const PostParams P) {
       mx = fmaxf(mx, v);
     }
   }
-  mx = block_reduce<float>(mx, s_red_f, true);
-  const float nan_cnt = block_reduce<float>(has_nan ? 1.f : 0.f, s_red_f, false);
-  if (nan_cnt > 0.f) mx = NAN;
+  mx = block_max_poison(mx, has_nan, s_red_f);      // (its barrier also publishes s_db)
+  // an infinite power makes log_spec.max() NaN in numpy (inf - inf at that element): the whole chunk is NaN there too
+  const bool poisoned = !(mx < INFINITY);
 
-  // log_spec = 10*log10(max(amin, S)) - 10*log10(max(amin, ref)); then max over log_spec
-  const float ref_db = 10.0f * log10f(fmaxf(P.amin, mx));
-  float mx_db = -INFINITY;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const float v = 10.0f * log10f(fmaxf(P.amin, s_db[i])) - ref_db;
-    s_db[i] = v;
-    mx_db = fmaxf(mx_db, v);
+  // log_spec = 10*log10(max(amin, S)) - 10*log10(max(amin, ref)), floored at log_spec.max() - top_db = -top_db
+  const float ref_db = power_db(fmaxf(P.amin, mx));
+  const float floor_db = -P.top_db;
+  double sum = 0.0, sq = 0.0;
+  auto to_db = [&](float sv) -> float {
+    const float v = fmaxf(__fsub_rn(power_db(fmaxf(P.amin, sv)), ref_db), floor_db);
+    const double dv = static_cast<double>(v);
+    sum += dv;
+    sq = fma(dv, dv, sq);
+    return v;
+  };
+  if (!poisoned) {
+    if ((n & 3) == 0) {
+      float4* s4 = reinterpret_cast<float4*>(s_db);
+      for (int i = tid; i < (n >> 2); i += blockDim.x) {
+        float4 v = s4[i];
+        v.x = to_db(v.x); v.y = to_db(v.y); v.z = to_db(v.z); v.w = to_db(v.w);
+        s4[i] = v;
+      }
+    } else {
+      for (int i = tid; i < n; i += blockDim.x) s_db[i] = to_db(s_db[i]);
+    }
   }
-  mx_db = block_reduce<float>(mx_db, s_red_f, true);
-  if (nan_cnt > 0.f) mx_db = NAN;
-  const float floor_db = mx_db - P.top_db;         // np.maximum(log_spec, log_spec.max() - top_db)
-
-  double sum = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    float v = s_db[i];
-    v = (v != v || floor_db != floor_db) ? NAN : fmaxf(v, floor_db);
-    s_db[i] = v;
-    sum += static_cast<double>(v);
-  }
-  sum = block_reduce<double>(sum, s_red_d, false);
-  const float mean = static_cast<float>(sum / n);
-  double ss = 0.0;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const double d = static_cast<double>(s_db[i]) - static_cast<double>(mean);
-    ss += d * d;
-  }
-  ss = block_reduce<double>(ss, s_red_d, false);
-  const float sd = static_cast<float>(sqrt(ss / n));
+  block_sum2(sum, sq, s_red_d);                     // (barrier: s_db holds the dB values)
+  const double mean_d = sum / n;
+  const float mean = poisoned ? NAN : static_cast<float>(mean_d);
+  const float sd = static_cast<float>(sqrt(fmax(sq / n - mean_d * mean_d, 0.0)));
   const float denom = sd + 1e-8f;                   // (S_db - mean) / (std + 1e-8)
 
-  // crop_or_pad_time + transpose: feat[c][t][m]
+  // crop_or_pad_time + transpose: feat[c][t][m] = z(S_db[t - pad_left + crop_start][m]); source and destination are both
+  // frame-major, so the copy is one contiguous shift
   float* __restrict__ dst = P.feat + static_cast<size_t>(c) * P.T * P.M;
-  const int total = P.T * P.M;
-  for (int i = tid; i < total; i += blockDim.x) {
-    const int t = i / P.M, m = i - t * P.M;
-    const int f = t - P.pad_left + P.crop_start;
-    float v = 0.f;                                  // np.pad(..., mode="constant") after the z-score
-    if (t >= P.pad_left && t < P.pad_left + P.frames_copy) v = (s_db[f * P.M + m] - mean) / denom;
-    dst[i] = v;
+  const int total = P.T * P.M, lo = P.pad_left * P.M, hi = (P.pad_left + P.frames_copy) * P.M;
+  const int shift = (P.crop_start - P.pad_left) * P.M;
+  if (vec) {
+    for (int i = 4 * tid; i < total; i += 4 * blockDim.x) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // np.pad(..., mode="constant") after the z-score
+      if (i >= lo && i < hi) {
+        const float4 sv = *reinterpret_cast<const float4*>(s_db + i + shift);
+        v = make_float4(__fdiv_rn(sv.x - mean, denom), __fdiv_rn(sv.y - mean, denom), __fdiv_rn(sv.z - mean, denom), __fdiv_rn(sv.w - mean, denom));
+      }
+      __stcs(reinterpret_cast<float4*>(dst + i), v);
+    }
+  } else {
+    for (int i = tid; i < total; i += blockDim.x) dst[i] = (i >= lo && i < hi) ? __fdiv_rn(s_db[i + shift] - mean, denom) : 0.f;
   }
 }
 

@@ -44,13 +44,20 @@ struct PrepParams {
 struct LoadF32 {
   const float* p;
   __device__ __forceinline__ float operator()(int i) const { return p[i]; }
+  __device__ __forceinline__ float4 load4(int i) const { return *reinterpret_cast<const float4*>(p + i); }   // i % 4 == 0, aligned base
 };
 struct LoadPcm16 {
   const int16_t* p;
   __device__ __forceinline__ float operator()(int i) const { return static_cast<float>(p[i]) * (1.0f / 32768.0f); }
+  __device__ __forceinline__ float4 load4(int i) const {
+    const uint2 u = *reinterpret_cast<const uint2*>(p + i);
+    const float k = 1.0f / 32768.0f;
+    return make_float4(static_cast<float>(static_cast<int16_t>(u.x & 0xffffu)) * k, static_cast<float>(static_cast<int16_t>(u.x >> 16)) * k,
+                       static_cast<float>(static_cast<int16_t>(u.y & 0xffffu)) * k, static_cast<float>(static_cast<int16_t>(u.y >> 16)) * k);
+  }
 };
 
-template <typename Load>
+template <bool kWide, typename Load>
 __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, float* s_val, int c);
 
 // One CTA per chunk (a persistent one-CTA-per-SM variant that keeps the second read in L2 measured slower: 89 vs 60 ms
@@ -59,11 +66,24 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams P) {
   extern __shared__ float s_val[];            // [n_leaves + n_nodes]
   const int c = blockIdx.x;
   const size_t base = static_cast<size_t>(c) * P.L;
-  if (P.x16 != nullptr) prep_body(P, LoadPcm16{P.x16 + base}, s_val, c);
-  else prep_body(P, LoadF32{P.x + base}, s_val, c);
+  if (P.x16 != nullptr) prep_body<false>(P, LoadPcm16{P.x16 + base}, s_val, c);
+  else prep_body<false>(P, LoadF32{P.x + base}, s_val, c);
 }
 
-template <typename Load>
+// The same with one CTA of 1024 threads per chunk and therefore one chunk per SM: 148 chunks (85 MB of float32 audio) are in
+// flight instead of 592, so the second sweep finds its chunk in the 126 MB L2 and DRAM sees every sample once.  What the
+// single resident CTA loses in overlap it gets back from wider loads: two threads per leaf, each owning four of numpy's
+// eight interleaved accumulators and loading eight 16-byte rows before the ordered adds (128 KB in flight per SM).
+// Regular leaf plans only (every leaf a multiple of 8 samples at a multiple-of-8 offset: the 3 s and 5 s chunk lengths).
+__global__ void __launch_bounds__(1024, 1) prep_wide_kernel(const PrepParams P) {
+  extern __shared__ float s_val[];
+  const int c = blockIdx.x;
+  const size_t base = static_cast<size_t>(c) * P.L;
+  if (P.x16 != nullptr) prep_body<true>(P, LoadPcm16{P.x16 + base}, s_val, c);
+  else prep_body<true>(P, LoadF32{P.x + base}, s_val, c);
+}
+
+template <bool kWide, typename Load>
 __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, float* s_val, int c) {
   __shared__ float s_red[32];
   __shared__ float s_scale, s_pow2;
@@ -72,6 +92,39 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
 
   // ---------------------------------------------------------------- phase 1: leaves
   float mx = 0.f;
+  if constexpr (kWide) {
+    const int h4 = (tid & 1) * 4;                 // this thread's accumulators: r[h4 .. h4 + 3] of the leaf's eight
+    for (int leaf = tid >> 1; leaf < P.n_leaves; leaf += blockDim.x >> 1) {
+      const int off = P.leaf_off[leaf] + h4, rows = P.leaf_len[leaf] >> 3;     // 1 .. 16 rows of eight samples
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (u < rows) ? xc.load4(off + 8 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float r0 = __fmul_rn(v[0].x, v[0].x), r1 = __fmul_rn(v[0].y, v[0].y), r2 = __fmul_rn(v[0].z, v[0].z), r3 = __fmul_rn(v[0].w, v[0].w);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[0].x), fabsf(v[0].y)), fmaxf(fabsf(v[0].z), fabsf(v[0].w))));
+#pragma unroll
+      for (int u = 1; u < 8; ++u)
+        if (u < rows) {
+          r0 = __fadd_rn(r0, __fmul_rn(v[u].x, v[u].x)); r1 = __fadd_rn(r1, __fmul_rn(v[u].y, v[u].y));
+          r2 = __fadd_rn(r2, __fmul_rn(v[u].z, v[u].z)); r3 = __fadd_rn(r3, __fmul_rn(v[u].w, v[u].w));
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+        }
+      for (int u0 = 8; u0 < rows; u0 += 4) {       // longer leaves (5 s chunks: 14 / 15 rows): four more rows at a time
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (u0 + u < rows) ? xc.load4(off + 8 * (u0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u0 + u < rows) {
+            r0 = __fadd_rn(r0, __fmul_rn(v[u].x, v[u].x)); r1 = __fadd_rn(r1, __fmul_rn(v[u].y, v[u].y));
+            r2 = __fadd_rn(r2, __fmul_rn(v[u].z, v[u].z)); r3 = __fadd_rn(r3, __fmul_rn(v[u].w, v[u].w));
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+          }
+      }
+      // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)): each half locally, the halves across the thread pair
+      float r = __fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3));
+      r = __fadd_rn(r, __shfl_xor_sync(3u << (tid & 30), r, 1));      // pair mask: other lanes may have left the loop
+      if (h4 == 0) s_val[leaf] = r;
+    }
+  } else {
   const int j = tid & 7;
   const unsigned gmask = 0xFFu << (8 * ((tid & 31) >> 3));
   for (int leaf = tid >> 3; leaf < P.n_leaves; leaf += blockDim.x >> 3) {
@@ -121,6 +174,7 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
       }
     }
     if (j == 0) s_val[leaf] = r;
+  }
   }
   // block max of |x| (only used to pick the power-of-two operand scale; any upper bound is valid)
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -283,9 +337,21 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
   P.dft_scale_log2 = c->dft_scale_log2;
   P.headroom_log2 = 13;
   const size_t smem = static_cast<size_t>(c->n_leaves + c->n_nodes + 1) * sizeof(float);
-  AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(prep_kernel), 164 * 1024));
   P.n = n;
-  { LaunchScope ls(c, ST_PREP, st); prep_kernel<<<n, 512, smem, st>>>(P); }
+  // wide form: regular leaf plan, 16-byte aligned rows (chunk rows are L samples apart, L % 8 == 0)
+  bool wide = c->leaves_regular && (x16 ? reinterpret_cast<uintptr_t>(x16) % 8 == 0 : reinterpret_cast<uintptr_t>(x) % 16 == 0);
+#ifdef AVLD_BRINGUP
+  if (std::getenv("AVLD_PREP_NARROW")) wide = false;
+#endif
+  if (wide) {
+    AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(prep_wide_kernel), 164 * 1024));
+    LaunchScope ls(c, ST_PREP, st);
+    prep_wide_kernel<<<n, 1024, smem, st>>>(P);
+  } else {
+    AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(prep_kernel), 164 * 1024));
+    LaunchScope ls(c, ST_PREP, st);
+    prep_kernel<<<n, 512, smem, st>>>(P);
+  }
   AVLD_CUDA(cudaGetLastError());
   return AVLD_OK;
 }

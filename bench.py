@@ -444,7 +444,7 @@ def main():
         ne = min(args.e2e_chunks, n)
         fit = state["fit"]
         cent, thr = np.nan_to_num(fit.centroids), fit.rk[0]
-        grab = min(4096, ne)                   # chunks per host call = one unit of the dynamic pool
+        grab = min(4096 if world > 1 else 8192, ne)   # chunks per host call = one unit of the dynamic pool (one rank: no pool to balance)
         run_id = [0]
 
         def run_e2e(xh, bytes_per_sample, api):
