@@ -113,6 +113,8 @@ struct avld_ctx {
   // numpy pairwise-sum plan
   int n_leaves = 0, n_nodes = 0, n_levels = 0;
   bool leaves_regular = false;       // every leaf is 8 .. 128 samples, a multiple of 8, at a multiple-of-8 offset (3 s and 5 s chunks)
+  int min_leaf_rows = 0;             // shortest leaf / 8
+  bool tree_perfect = false;         // 2^h leaves under a tree of height h: siblings are adjacent leaves / nodes at every level
   int32_t* d_leaf_off = nullptr;
   int32_t* d_leaf_len = nullptr;
   avld::PairNode* d_nodes = nullptr;

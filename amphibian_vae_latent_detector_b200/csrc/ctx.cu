@@ -1,5 +1,6 @@
 // ctx.cu -- context life cycle, host-side tables (numpy pairwise-sum plan, slaney mel taps,
 // windowed DFT matrix) and TMA descriptor encoding.
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -33,7 +34,10 @@ static cudaEvent_t take_event(avld_ctx* c) {
   return e;
 }
 
+// Every kernel launch of the library sits inside an NVTX range named after its stage (header-only NVTX3: a no-op of a few
+// nanoseconds unless a tool such as `ncu --nvtx --nvtx-include "avld/dftf3_kernel/"` or Nsight Systems is attached).
 LaunchScope::LaunchScope(avld_ctx* ctx, int stage, cudaStream_t stream) : c(ctx), st(stream) {
+  nvtxRangePushA(avld_stage_name(stage));
   c->launches[stage] += 1;
   if (c->profiling) {
     cudaEvent_t a = take_event(c);
@@ -44,6 +48,7 @@ LaunchScope::LaunchScope(avld_ctx* ctx, int stage, cudaStream_t stream) : c(ctx)
 }
 LaunchScope::~LaunchScope() {
   if (stop) cudaEventRecord(stop, st);
+  nvtxRangePop();
 }
 
 int ensure_dyn_smem(avld_ctx* c, const void* kernel, int bytes) {
@@ -313,6 +318,9 @@ static int build_ctx(avld_ctx* c) {
   c->leaves_regular = c->L % 8 == 0;
   for (size_t i = 0; i < off32.size(); ++i)
     c->leaves_regular = c->leaves_regular && off32[i] % 8 == 0 && len32[i] % 8 == 0 && len32[i] >= 8 && len32[i] <= 128;
+  c->min_leaf_rows = 1 << 30;
+  for (int32_t v : len32) c->min_leaf_rows = std::min(c->min_leaf_rows, v / 8);
+  c->tree_perfect = c->n_leaves >= 256 && (c->n_leaves & (c->n_leaves - 1)) == 0 && (1 << c->n_levels) == c->n_leaves;
   AVLD_TRY(dev_alloc(&c->d_leaf_off, off32.size()));
   AVLD_TRY(dev_alloc(&c->d_leaf_len, len32.size()));
   AVLD_TRY(dev_alloc(&c->d_nodes, nodes.size() + 1));

@@ -633,7 +633,9 @@ extern "C" int avld_encoder_load_program(avld_ctx* c, const avld_op* ops, int32_
       const int co_pad = tens[s.out].c_pad;
       AVLD_CHECK(co_pad <= 4096, AVLD_ERR_UNSUPPORTED, "op %d: linear out_features > 4096", i);
       L.c_in = static_cast<int>(L.K); L.c_out = co_pad;
-      L.bn = 64;
+      // (m, n)-tile work items: 64-column tiles leave most SMs idle on a full pass when the layer is narrow (1024 rows x 512
+      // columns = 64 CTAs, each paced by its own TMA row rate); 32-column tiles put twice as many on the machine
+      L.bn = ((images + 127) / 128) * (co_pad / 64) < c->sm_count ? 32 : 64;
       L.swz = 128;
       std::vector<float> w(static_cast<size_t>(co_pad) * L.K, 0.f), b(co_pad, 0.f);
       for (int o = 0; o < s.c_out; ++o) {

@@ -8,6 +8,7 @@ template <int EPI>
 static int by_shape(avld_ctx* c, int bn, int swz, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                     const CUtensorMap& b_lo, const Gemm3Params& P, cudaStream_t st) {
   if (swz == 128) {
+    if (bn == 32 && EPI == EPI_PLAIN) return launch_gemm3<32, 128, EPI_PLAIN>(c, a_hi, a_lo, b_hi, b_lo, P, st);
     if (bn == 64) return launch_gemm3<64, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);
     if (bn == 128) return launch_gemm3<128, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);
     if (bn == 256) return launch_gemm3<256, 128, EPI>(c, a_hi, a_lo, b_hi, b_lo, P, st);

@@ -11,7 +11,11 @@
 //
 // Memory: phase 1 streams the chunk once (4*L bytes), phase 2 re-reads it and writes either y (4*L bytes,
 // avld_rms_normalize) or the normalised PCM_16 integers (2*L bytes, feature passes).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
+#include "ptx.cuh"
 #include "sample.cuh"
 
 namespace avld {
@@ -292,6 +296,189 @@ __device__ __forceinline__ void prep_body(const PrepParams& P, const Load xc, fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// prep_cluster_kernel: one chunk per cluster of eight 512-thread CTAs.  Each CTA owns an eighth of the leaves -- a whole
+// subtree of numpy's (perfect) pairwise tree -- reduces it locally with the tree's own pairing (adjacent leaves, then
+// adjacent nodes: warp butterflies), and the eight subtree roots (and block maxima) are exchanged through distributed shared
+// memory with ONE cluster barrier; every CTA then forms the same root and scale and writes the second sweep of its own
+// samples.  Four CTAs of four different chunks share an SM, so sweeps, tree and barrier waits of different chunks overlap
+// like in prep_kernel, but only 74 chunks (43 MB) are in flight instead of 592: the second sweep is an L2 hit.
+// Needs a regular, perfect plan (the 3 s and 5 s chunk lengths); everything else goes to prep_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPrepCluster = 8;
+
+__device__ __forceinline__ void st_cluster_f32(float* local_addr, uint32_t cta, float v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.f32 [ra], %2;\n\t}\n" ::"r"(smem_u32(local_addr)),
+      "r"(cta), "f"(v)
+      : "memory");
+}
+
+template <bool PCM>
+__global__ void __cluster_dims__(kPrepCluster, 1, 1) __launch_bounds__(512, 4) prep_cluster_kernel(const PrepParams P) {
+  __shared__ float s_leaf[512];                 // this CTA's leaf sums
+  __shared__ float s_wroot[16], s_wmax[16];
+  __shared__ float s_xroot[kPrepCluster], s_xmax[kPrepCluster];   // written by every CTA of the cluster
+  __shared__ float s_scale;
+  __shared__ int s_scaled;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int c = blockIdx.x / kPrepCluster;
+  const int lpc = P.n_leaves / kPrepCluster;    // leaves per CTA: 32 .. 512, a power of two
+  const int leaf0 = static_cast<int>(rank) * lpc;
+  const size_t base = static_cast<size_t>(c) * P.L;
+  const float* __restrict__ xf = P.x + (PCM ? 0 : base);
+  const int16_t* __restrict__ xi = P.x16 + (PCM ? base : 0);
+  using In = typename std::conditional<PCM, int16_t, float>::type;
+  const In* __restrict__ xin = PCM ? reinterpret_cast<const In*>(xi) : reinterpret_cast<const In*>(xf);
+  auto cvt = [](In s) -> float { return PCM ? static_cast<float>(s) * (1.0f / 32768.0f) : static_cast<float>(s); };
+
+  // ---- sweep 1: leaf sums (lane j of an 8-lane group owns accumulator j of numpy's eight)
+  float mx = 0.f;
+  const int j = tid & 7;
+  const unsigned gmask = 0xFFu << (8 * (lane >> 3));
+  const int32_t* __restrict__ lo_p = P.leaf_off + leaf0;
+  const int32_t* __restrict__ ll_p = P.leaf_len + leaf0;
+  for (int l = tid >> 3; l < lpc; l += 64) {
+    const int rows = ll_p[l] >> 3;              // >= 8 (launch_prep checks the plan): the first eight rows load unconditionally
+    const In* __restrict__ q = xin + lo_p[l] + j;
+    float v8[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v8[u] = cvt(q[8 * u]);
+    const float v9 = rows > 8 ? cvt(q[64]) : 0.f;       // the ninth row of a 72-sample leaf rides along with the first eight
+    mx = fmaxf(mx, fabsf(v8[0]));
+    float r = __fmul_rn(v8[0], v8[0]);
+#pragma unroll
+    for (int u = 1; u < 8; ++u) {
+      mx = fmaxf(mx, fabsf(v8[u]));
+      r = __fadd_rn(r, __fmul_rn(v8[u], v8[u]));
+    }
+    if (rows > 8) {
+      mx = fmaxf(mx, fabsf(v9));
+      r = __fadd_rn(r, __fmul_rn(v9, v9));
+#pragma unroll 1
+      for (int u = 9; u < rows; ++u) {
+        const float v = cvt(q[8 * u]);
+        mx = fmaxf(mx, fabsf(v));
+        r = __fadd_rn(r, __fmul_rn(v, v));
+      }
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1, 8));      // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
+    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2, 8));
+    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4, 8));
+    if (j == 0) s_leaf[l] = r;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_wmax[warp] = mx;
+  __syncthreads();
+
+  // ---- this CTA's subtree: adjacent pairing at every level = xor butterflies (fl(a + b) = fl(b + a))
+  const int nw = lpc >> 5;                      // warps holding 32 leaf sums each (1 .. 16)
+  if (warp < nw) {
+    float v = s_leaf[tid];
+    for (int o = 1; o < 32; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) s_wroot[warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float v = lane < nw ? s_wroot[lane] : 0.f;
+    for (int o = 1; o < nw; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    v = __shfl_sync(0xffffffffu, v, 0);         // lanes >= nw took no part in the butterfly
+    float m = lane < 16 ? s_wmax[lane] : 0.f;
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    m = __shfl_sync(0xffffffffu, m, 0);
+    if (lane < kPrepCluster) {                  // lane r delivers to CTA r
+      st_cluster_f32(&s_xroot[rank], lane, v);
+      st_cluster_f32(&s_xmax[rank], lane, m);
+    }
+  }
+  cluster_sync_all();                           // release / acquire: the eight roots are visible in every CTA
+
+  if (tid == 0) {
+    const float root = __fadd_rn(__fadd_rn(__fadd_rn(s_xroot[0], s_xroot[1]), __fadd_rn(s_xroot[2], s_xroot[3])),
+                                 __fadd_rn(__fadd_rn(s_xroot[4], s_xroot[5]), __fadd_rn(s_xroot[6], s_xroot[7])));
+    float m = s_xmax[0];
+#pragma unroll
+    for (int r = 1; r < kPrepCluster; ++r) m = fmaxf(m, s_xmax[r]);
+    const float rms = __fsqrt_rn(__fdiv_rn(root, static_cast<float>(P.L)));
+    int scaled = 0;
+    float scale = 1.0f;
+    if (P.scalar_f64) {                         // numpy 1.26.4 scalar rules, see prep_body
+      const double rd = static_cast<double>(rms);
+      if (P.normalize && !(rd < P.rms_min_d)) {
+        scaled = 1;
+        scale = __double2float_rn(__ddiv_rn(P.target_d, __dadd_rn(rd, P.eps_d)));
+      }
+    } else if (P.normalize && !(rms < P.rms_min)) {
+      scaled = 1;
+      scale = __fdiv_rn(P.target_rms, __fadd_rn(rms, P.eps));
+    }
+    s_scale = scale;
+    s_scaled = scaled;
+    if (rank == 0) {
+      const float bound = scaled ? fminf(__fmul_rn(m, scale), 1.0f) : m;
+      int s = 0;
+      if (bound > 0.f && bound < 3.0e38f) {
+        s = P.headroom_log2 - ilogbf(bound);
+        s = s > 60 ? 60 : (s < -60 ? -60 : s);
+      }
+      if (P.inv2) P.inv2[c] = (rms - rms == 0.0f) ? ldexpf(1.0f, -2 * (s + P.dft_scale_log2)) : NAN;   // NaN / Inf chunk: see prep_body
+      if (P.chunk_par) P.chunk_par[c] = make_float4(scale, ldexpf(1.0f, s), scaled ? 1.0f : 0.0f, 0.0f);
+      if (P.ok) P.ok[c] = P.normalize ? static_cast<uint8_t>(scaled) : static_cast<uint8_t>(1);
+      if (P.rms) P.rms[c] = rms;
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const int scaled = s_scaled;
+
+  // ---- sweep 2 over this CTA's own samples [o0, o1): both multiples of 8
+  const int o0 = P.leaf_off[leaf0], o1 = (leaf0 + lpc < P.n_leaves) ? P.leaf_off[leaf0 + lpc] : P.L;
+  const int n8 = (o1 - o0) >> 3;
+  auto load8 = [&](int i, float (&v)[8]) {
+    if (PCM) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xi + o0 + 8 * i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[2 * k] = static_cast<float>(static_cast<int16_t>(w[k] & 0xffffu)) * (1.0f / 32768.0f);
+        v[2 * k + 1] = static_cast<float>(static_cast<int16_t>(w[k] >> 16)) * (1.0f / 32768.0f);
+      }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(xf + o0 + 8 * i), b = *reinterpret_cast<const float4*>(xf + o0 + 8 * i + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  };
+  if (P.q16 != nullptr) {
+    uint16_t* __restrict__ qc = P.q16 + base + o0;
+#pragma unroll 4
+    for (int i = tid; i < n8; i += 512) {
+      float v[8];
+      load8(i, v);
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = static_cast<uint32_t>(pcm16_of(v[2 * k], scale, scaled) + 32768) |
+               (static_cast<uint32_t>(pcm16_of(v[2 * k + 1], scale, scaled) + 32768) << 16);
+      __stcs(reinterpret_cast<uint4*>(qc) + i, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+  }
+  if (P.y != nullptr) {
+    float* __restrict__ yc = P.y + base + o0;
+#pragma unroll 2
+    for (int i = tid; i < n8; i += 512) {
+      float v[8];
+      load8(i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = finish_sample(v[k], scale, scaled, P.quantize);
+      __stcs(reinterpret_cast<float4*>(yc) + 2 * i, make_float4(v[0], v[1], v[2], v[3]));
+      __stcs(reinterpret_cast<float4*>(yc) + 2 * i + 1, make_float4(v[4], v[5], v[6], v[7]));
+    }
+  }
+}
+
 int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, bool write_operand, bool normalize, uint8_t* ok, float* rms,
                 int n, float target_rms, float rms_min, float eps, int quantize, cudaStream_t st) {
   if (n <= 0) return AVLD_OK;
@@ -343,7 +530,18 @@ int launch_prep(avld_ctx* c, const float* x, const int16_t* x16, float* y_out, b
 #ifdef AVLD_BRINGUP
   if (std::getenv("AVLD_PREP_NARROW")) wide = false;
 #endif
-  if (wide) {
+  // cluster form: perfect plan, 16-byte aligned rows on both sides
+  bool clustered = wide && c->tree_perfect && c->min_leaf_rows >= 8 && c->n_leaves / kPrepCluster <= 512 &&
+                   (x16 ? reinterpret_cast<uintptr_t>(x16) % 16 == 0 : true) &&
+                   (y_out == nullptr || reinterpret_cast<uintptr_t>(y_out) % 16 == 0);
+#ifdef AVLD_BRINGUP
+  if (std::getenv("AVLD_PREP_NOCLUSTER")) clustered = false;
+#endif
+  if (clustered) {
+    LaunchScope ls(c, ST_PREP, st);
+    if (x16) prep_cluster_kernel<true><<<n * kPrepCluster, 512, 0, st>>>(P);
+    else prep_cluster_kernel<false><<<n * kPrepCluster, 512, 0, st>>>(P);
+  } else if (wide) {
     AVLD_TRY(ensure_dyn_smem(c, reinterpret_cast<const void*>(prep_wide_kernel), 164 * 1024));
     LaunchScope ls(c, ST_PREP, st);
     prep_wide_kernel<<<n, 1024, smem, st>>>(P);

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 re=$1; cnt=${2:-12}; shift 2
 envs=""; [ $# -gt 0 ] && envs="env AVLD_LIB_PATH=amphibian_vae_latent_detector_b200/libavld_bringup.so $*"
 timeout 600 $envs ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active \
-  --clock-control none -k regex:"$re" -s 8 -c $cnt --csv --log-file gpurun_out/quick.csv python bench.py --chunks 4096 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/quick.log 2>&1
+  --clock-control none -k regex:"$re" -s 2 -c $cnt --csv --log-file gpurun_out/quick.csv python bench.py --chunks 4096 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/quick.log 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(open('gpurun_out/quick.csv')) if len(r)>10]
