@@ -46,6 +46,7 @@ class Op(C.Structure):
 
 
 OP_CONV, OP_LINEAR, OP_ADD, OP_AFFINE, OP_POOL = range(5)
+COMM_ID_BYTES = 128
 
 
 class RankQuery(C.Structure):
@@ -79,6 +80,11 @@ _SIGNATURES = {
     "avld_radii": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "avld_order_stats": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(RankQuery), C.c_int32,
                                    C.POINTER(C.c_float), _P]),
+    "avld_comm_unique_id": (C.c_int, [_P]),
+    "avld_comm_init": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "avld_comm_destroy": (C.c_int, [_P]),
+    "avld_allreduce_centroids": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "avld_allgather_radii": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, _P, _P]),
     "avld_decide": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "avld_map_score": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_double, C.c_int, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "avld_cov_accumulate": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, _P]),

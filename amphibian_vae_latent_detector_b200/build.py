@@ -21,7 +21,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libavld.so"
 OBJ = HERE / "build"
 
-SOURCES = ["ctx.cu", "rms.cu", "gemm3.cu", "fold3.cu", "dftf3.cu", "logmel.cu", "convh.cu", "encoder.cu", "radial.cu", "map.cu", "resample.cu", "api.cu"]
+SOURCES = ["ctx.cu", "rms.cu", "gemm3.cu", "fold3.cu", "dftf3.cu", "logmel.cu", "convh.cu", "encoder.cu", "radial.cu", "map.cu", "resample.cu", "comm.cu", "api.cu"]
 EXTRA_FLAGS = {"rms.cu": ["-fmad=false"]}
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -172,6 +172,13 @@ struct avld_ctx {
   std::vector<__nv_bfloat16*> d_slot_hi, d_slot_lo;   // activation slots, each max_batch * n_seg images of the largest tensor
   float* d_lat = nullptr;          // [max_batch * n_seg][latent_dim] per-segment latents (n_seg > 1 or a non-linear head)
 
+  // optional NCCL communicator of this context (comm.cu)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 0;
+  float* d_gather_r = nullptr;
+  int32_t* d_gather_l = nullptr;
+  int64_t gather_rows = 0;
+
   // host end-to-end path
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

@@ -498,10 +498,13 @@ extern "C" int avld_ctx_create(int device, const avld_params* params, avld_ctx**
   return AVLD_OK;
 }
 
+extern "C" int avld_comm_destroy(avld_ctx* c);
+
 extern "C" void avld_ctx_destroy(avld_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  avld_comm_destroy(c);
   void* ptrs[] = {c->d_leaf_off, c->d_leaf_len, c->d_nodes, c->d_level_start, c->d_chunk_par, c->d_A3, c->d_B3hi, c->d_B3lo,
                   c->d_taps3, c->d_edge, c->d_q16, c->d_win, c->d_inv2, c->d_melpow, c->d_feat, c->d_mu, c->d_radii, c->d_ok,
                   c->d_rms, c->d_lat, c->d_rs_win, c->d_rs_delta, c->d_xbuf[0], c->d_xbuf[1], c->d_cent, c->d_thr, c->d_prio, c->d_pred, c->d_best, c->d_hist};

@@ -280,6 +280,41 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ D2
+    # ------------------------------------------------------------------ multi-GPU fit without torch.distributed
+    comm_world = 0          # > 1 once comm_init has run: fit_radial(group="avld") then uses the context's own communicator
+
+    def comm_unique_id(self) -> bytes:
+        """Rank 0: a fresh NCCL id (128 bytes) to hand to the other ranks by any means (file, socket, queue)."""
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        _lib.check(self.lib.avld_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Collective over all ranks: this context's NCCL communicator (one process and one context per GPU)."""
+        if len(unique_id) != _lib.COMM_ID_BYTES:
+            raise ValueError(f"the id has {len(unique_id)} bytes, not {_lib.COMM_ID_BYTES}")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.avld_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(world)))
+        self.comm_rank, self.comm_world = int(rank), int(world)
+
+    def allreduce_centroids(self, sums: torch.Tensor, cnts: torch.Tensor) -> None:
+        """In place: per-species sums [K, D] float64 and counts [K] int64 summed over the ranks."""
+        sums = self._dev(sums, torch.float64, "sums")
+        cnts = self._dev(cnts, torch.int64, "cnts")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.avld_allreduce_centroids(self._h, _ptr(sums), _ptr(cnts), sums.shape[0], sums.shape[1], _stream()))
+
+    def allgather_radii(self, radii: torch.Tensor, label: torch.Tensor, shard_rows: int):
+        """-> (radii_all [world * shard_rows, K], label_all [world * shard_rows]); padding rows carry label -1."""
+        radii = self._dev(radii, torch.float32, "radii")
+        label = self._dev(label, torch.int32, "label")
+        n, K = radii.shape
+        ra = torch.empty(self.comm_world * shard_rows, K, dtype=torch.float32, device=self.device)
+        la = torch.empty(self.comm_world * shard_rows, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.avld_allgather_radii(self._h, _ptr(radii), _ptr(label), n, int(shard_rows), K, _ptr(ra), _ptr(la), _stream()))
+        return ra, la
+
     def decide(self, radii: torch.Tensor, thr: torch.Tensor, priority_rank: torch.Tensor):
         radii = self._dev(radii, torch.float32, "radii")
         thr = self._dev(thr, torch.float64, "thr")

@@ -84,7 +84,16 @@ def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 
             raise ValueError("q_in and q_out must be in (0,1)")              # 08:369-372
     D = Z.shape[1]
     sums, cnts = ops.centroid_accumulate(Z, label, K)
-    distributed = group is not None and dist.get_world_size(group) > 1
+    # group = "avld": the context's own NCCL communicator (Engine.comm_init -> avld_comm_* of the C ABI) instead of
+    # torch.distributed -- the form a host without PyTorch's process groups uses; same exchanges, same results
+    own_comm = isinstance(group, str) and group == "avld"
+    if own_comm:
+        if getattr(ops, "comm_world", 0) < 1:
+            raise ValueError('group="avld" needs Engine.comm_init first')
+        if shard_rows is None:
+            raise ValueError('group="avld" needs shard_rows (a block size every rank agrees on)')
+        ops.allreduce_centroids(sums, cnts)
+    distributed = (not own_comm) and group is not None and dist.get_world_size(group) > 1
     if distributed:
         packed = torch.cat([sums.reshape(-1), cnts.to(torch.float64)])        # counts < 2^53 are exact in f64
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
@@ -96,6 +105,8 @@ def fit_radial(ops, Z: torch.Tensor, label: torch.Tensor, K: int, q_in: float = 
     lab = label
     if distributed:
         radii, lab = all_gather_rows(radii, label, group, shard_rows)
+    elif own_comm:
+        radii, lab = ops.allgather_radii(radii, label, shard_rows)
     counts = cnts.cpu().numpy()            # first host read: everything above is already enqueued
     n_tot = int(counts.sum())
 

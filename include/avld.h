@@ -203,6 +203,25 @@ int avld_radii(avld_ctx* ctx, const float* Z, const float* centroid, float* radi
 int avld_order_stats(avld_ctx* ctx, const float* radii, const int32_t* label, int64_t n, int32_t K,
                      const avld_rank_query* queries, int32_t n_q, float* out, void* stream);
 
+/* ---- multi-GPU fit without torch.distributed (the two exchanges of 08:530-558 when the rows are sharded over
+ * ranks, one process and one context per GPU).  NCCL is loaded at run time (dlopen of libnccl.so.2); the host ships the
+ * 128-byte id from rank 0 to the other ranks by its own means (file, socket, MPI ...).
+ *   avld_comm_unique_id       rank 0: a fresh id
+ *   avld_comm_init            every rank, collectively: the context's communicator
+ *   avld_allreduce_centroids  sum dev float64 [K, D] and cnt dev int64 [K] (as filled by avld_centroid_accumulate) are
+ *                             summed over the ranks IN PLACE: every rank then forms bit-identical centroids (08:316)
+ *   avld_allgather_radii      radii dev [n_local, K] + label dev [n_local] -> radii_all dev [world * shard_rows, K],
+ *                             label_all dev [world * shard_rows]; n_local <= shard_rows, padding rows get label -1 (skipped
+ *                             by avld_order_stats): every rank then selects the same exact order statistics (08:319, :326)
+ * All stream-ordered and asynchronous. */
+#define AVLD_COMM_ID_BYTES 128
+int avld_comm_unique_id(void* id_out);
+int avld_comm_init(avld_ctx* ctx, const void* nccl_unique_id, int32_t rank, int32_t world);
+int avld_comm_destroy(avld_ctx* ctx);
+int avld_allreduce_centroids(avld_ctx* ctx, double* sum, int64_t* cnt, int32_t K, int32_t D, void* stream);
+int avld_allgather_radii(avld_ctx* ctx, const float* radii, const int32_t* label, int64_t n_local, int64_t shard_rows,
+                         int32_t K, float* radii_all, int32_t* label_all, void* stream);
+
 /* ---- D2: decision (09_evaluate_wav_detection.py:416-436; 10_benchmark_folder_detection.py:175-199)
  * accept k iff (double)radii[i,k] <= thr[k]; pred[i] = accepted k with the smallest
  * priority_rank[k] or -1 (NO_DETECT); best_d[i] = min_k radii[i,k].  thr dev float64 [K] (a NaN

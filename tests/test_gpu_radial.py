@@ -108,3 +108,18 @@ def test_decide_random_vs_oracle(engine3s):
     assert np.array_equal(pred.cpu().numpy()[~near], po[~near])
     assert np.allclose(best.cpu().numpy(), bo, rtol=1e-5)
     assert len(set(po.tolist())) >= 3
+
+
+@pytest.mark.gpu
+def test_own_nccl_collectives_match_single_gpu_fit():
+    """avld_comm_init / avld_allreduce_centroids / avld_allgather_radii (NCCL through dlopen, no torch.distributed): the
+    sharded fit on two GPUs is bit-identical to the single-GPU fit (tools/comm_check.py; needs two visible GPUs)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(repo / "tools" / "comm_check.py"), "2", "200000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"bit_identical_to_single_gpu_fit_on_every_rank": true' in r.stdout
