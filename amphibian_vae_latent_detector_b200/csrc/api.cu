@@ -249,8 +249,10 @@ extern "C" int avld_dbg_gemm(avld_ctx* c, const float* A, const float* B, float*
     const int hb = mode == 0 ? 0 : 1;
     P.idesc_hh = P.idesc_lh = P.idesc_hl = avld_make_idesc(hb, hb, 128, bn);
     P.a_mode = 0;
-    if (const char* e = getenv("AVLD_DBG_SHIFT")) P.dbg_shift = atoi(e);
+#ifdef AVLD_BRINGUP
+    if (const char* e = getenv("AVLD_DBG_SHIFT")) P.dbg_shift = atoi(e);      // tools/probe_shift.py (libavld_bringup.so)
     if (const char* e = getenv("AVLD_DBG_BASEOFF")) P.dbg_baseoff = atoi(e);
+#endif
     P.M_total = M;
     P.N_total = N;
     P.out_f32 = C;

@@ -62,6 +62,17 @@ __device__ __forceinline__ void load8(const float* xf, const int16_t* xi, int sr
 
 // 8 consecutive taps (col % 8 == 0) of one frame row into the tile-major operand: row_base = offset of (tile, K block 0,
 // hi, row), one K block = 2 * 128 * 64 halves, lo = hi + 128 * 64
+// the same to a precomputed destination
+__device__ __forceinline__ void split_store_at(__half* dst, const float (&v)[8]) {
+  __align__(16) __half h[8], l[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    h[q] = __float2half_rn(v[q]);
+    l[q] = __float2half_rn(v[q] - __half2float(h[q]));
+  }
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(dst + 128 * 64) = *reinterpret_cast<const uint4*>(l);
+}
 __device__ __forceinline__ void split_store(__half* a3, size_t row_base, int col, const float (&v)[8]) {
   __align__(16) __half h[8], l[8];
 #pragma unroll
@@ -243,26 +254,46 @@ __global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold3Params P) {
         s2v[q] = z ? 0.f : Rk + Rm;
       }
     }
+    // Destination of an 8-tap block at column col of this frame row: (tile, K block col / 64, hi, row, col % 64).  The six
+    // ascending streams sit at k0 plus a multiple of 64 columns, the two odd-class streams at Q - 8 - k0 (+ Q): two row
+    // pointers, every stream a compile-time offset from one of them (the per-stream address arithmetic was ~50 instructions).
     const size_t base = (static_cast<size_t>(row >> 7) * (N >> 6) * 256 + (row & 127)) * 64;
-    split_store(P.a3, base, k0, oc);
-    split_store(P.a3, base, Q + k0, os);
-    split_store(P.a3, base, Q - k0 - 8, oc2);
-    split_store(P.a3, base, Q + (Q - k0 - 8), os2);
-    split_store(P.a3, base, H + k0, c0);
-    split_store(P.a3, base, H + E + k0, s0v);
-    split_store(P.a3, base, H + Q + k0, c2);
-    split_store(P.a3, base, H + Q + E + k0, s2v);
-    if (k0 == 0) {
-      auto xs = [&](int tap) -> float {
-        const float r = X.raw(reflect_src(pf + tap, H, P.L));
-        return SRC == 2 ? r * wscale : fin(r);
-      };
+    constexpr size_t kBlk = 2 * 128 * 64;                  // halves per K block (hi + lo tiles)
+    const int kr = Q - 8 - k0;
+    __half* const fwd = P.a3 + base + static_cast<size_t>(k0 >> 6) * kBlk + (k0 & 63);
+    __half* const rev = P.a3 + base + static_cast<size_t>(kr >> 6) * kBlk + (kr & 63);
+    split_store_at(fwd, oc);
+    split_store_at(fwd + (Q >> 6) * kBlk, os);
+    split_store_at(rev, oc2);
+    split_store_at(rev + (Q >> 6) * kBlk, os2);
+    split_store_at(fwd + (H >> 6) * kBlk, c0);
+    split_store_at(fwd + ((H + E) >> 6) * kBlk, s0v);
+    split_store_at(fwd + ((H + Q) >> 6) * kBlk, c2);
+    split_store_at(fwd + ((H + Q + E) >> 6) * kBlk, s2v);
+    // ---- edge terms of this frame row: O[Q], P[E], R[E] from the six samples at taps E, N-E, 3E, 5E, Q, 3Q
+    auto xs = [&](int tap) -> float {
+      const float r = X.raw(reflect_src(pf + tap, H, P.L));
+      return SRC == 2 ? r * wscale : fin(r);
+    };
+    auto edge_of = [&](float xe, float x7e, float x3e, float x5e, float xq, float x3q) -> float4 {
       const float wq = P.win[Q], we = P.win[E], w3 = P.win[Q + E];     // w[3E] = w[N - 5E] ...: w[Q+E] = w[H+Q-E+...]
-      const float xe = xs(E), x7e = xs(N - E), x3e = xs(Q + E), x5e = xs(H + E);
-      const float e_odd = __fmul_rn(wq, xs(Q) - xs(H + Q));                                      // O[Q]
+      const float e_odd = __fmul_rn(wq, xq - x3q);                                               // O[Q]
       const float e_m0 = __fadd_rn(__fmul_rn(we, xe + x7e), __fmul_rn(w3, x3e + x5e));           // P[E] = u[E] + u[N-E] + u[3E] + u[5E]
       const float e_m2 = __fsub_rn(__fmul_rn(we, xe - x7e), __fmul_rn(w3, x3e - x5e));           // R[E]
-      P.edge[row] = make_float4(e_odd, e_m0, e_m2, 0.f);                    // class 0 = odd, 1 = 0 mod 4, 2 = 2 mod 4
+      return make_float4(e_odd, e_m0, e_m2, 0.f);                      // class 0 = odd, 1 = 0 mod 4, 2 = 2 mod 4
+    };
+    if (per_frame == 32) {
+      // One warp = one frame row (the loop bounds are multiples of 32).  Left to the k0 = 0 thread alone, i.e. lane 0 of
+      // every warp, these ~100 instructions ran with one active lane and took a tenth of the kernel's issue slots (ncu source
+      // page, r02f); here lanes 0..5 fetch one sample each and lane 0 combines them.
+      const int lane = threadIdx.x & 31;
+      const int tap = E * ((0x625371 >> (4 * lane)) & 0xF);            // E * {1, 7, 3, 5, 2, 6}: E, N-E, 3E, 5E, Q, 3Q
+      const float sv = lane < 6 ? xs(tap) : 0.f;
+      const float xe = __shfl_sync(0xffffffffu, sv, 0), x7e = __shfl_sync(0xffffffffu, sv, 1), x3e = __shfl_sync(0xffffffffu, sv, 2);
+      const float x5e = __shfl_sync(0xffffffffu, sv, 3), xq = __shfl_sync(0xffffffffu, sv, 4), x3q = __shfl_sync(0xffffffffu, sv, 5);
+      if (lane == 0) P.edge[row] = edge_of(xe, x7e, x3e, x5e, xq, x3q);
+    } else if (k0 == 0) {
+      P.edge[row] = edge_of(xs(E), xs(N - E), xs(Q + E), xs(H + E), xs(Q), xs(H + Q));
     }
   }
 }

@@ -19,6 +19,7 @@ if len(sys.argv) > 1:
 else:
     for s in (0, 1, 2, 3, 5):
         for bo in sorted({0, s}):
-            env = dict(os.environ, AVLD_DBG_SHIFT=str(s), AVLD_DBG_BASEOFF=str(bo))
+            env = dict(os.environ, AVLD_DBG_SHIFT=str(s), AVLD_DBG_BASEOFF=str(bo),
+                       AVLD_LIB_PATH=os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'amphibian_vae_latent_detector_b200', 'libavld_bringup.so'))   # the probes live in the bring-up build only
             r = subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True, timeout=120)
             print((r.stdout.strip() or r.stderr.strip()[-300:]))
