@@ -224,18 +224,16 @@ __global__ void __launch_bounds__(256) conv1_kernel(const DirectConvParams P) {
           best[q] = max_nan(best[q], a.x);
           best[q + 1] = max_nan(best[q + 1], a.y);
         }
-    __align__(16) __nv_bfloat16 hi[8];
-    __align__(16) __nv_bfloat16 lo[8];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float t = best[q];
-      if (P.relu) t = relu_nan(t);
-      hi[q] = __float2bfloat16_rn(t);
-      lo[q] = __float2bfloat16_rn(t - __bfloat162float(hi[q]));
+    for (int q = 0; q < 8; q += 2) {
+      float t0 = best[q], t1 = best[q + 1];
+      if (P.relu) { t0 = relu_nan(t0); t1 = relu_nan(t1); }
+      split_bf16x2(t0, t1, hi[q >> 1], lo[q >> 1]);
     }
     const size_t obase = ((static_cast<size_t>(img) * P.OH + orow) * P.OW + oc) * P.Cout + co0;
-    *reinterpret_cast<uint4*>(P.out_hi + obase) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(P.out_lo + obase) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(P.out_hi + obase) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(P.out_lo + obase) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 

@@ -28,6 +28,20 @@ __device__ __forceinline__ float max_nan(float a, float b) {
 }
 __device__ __forceinline__ float relu_nan(float v) { return max_nan(v, 0.f); }
 
+// Two floats -> packed bf16 pair (round to nearest even; `lo` lands in the low half) in ONE full-rate F2FP.  The scalar
+// __float2bfloat16_rn compiles to F2F.BF16.F32 on the quarter-rate XU pipe: sixteen of them per output pixel kept that pipe
+// 83 % busy in conv1_kernel and held the FMA pipe at 59 % (ncu r02f).  Same bits as the scalar form, NaN included.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// hi / lo split of two values: hi = bf16(v), lo = bf16(v - hi), both packed as above
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
