@@ -57,7 +57,7 @@ struct ConvhCfg {
   // lo weight blocks of a tap are adjacent in shared memory, so A_hi x [W_hi | W_lo] is ONE N = 128 MMA into two column
   // ranges of the accumulator (A is read once for both), A_lo x W_hi a second one into the first range; the epilogue adds
   // the two ranges.  Two MMAs and 14 KB per K step instead of three and 18 KB.
-  static constexpr bool CONCAT = BN == 64;
+  static constexpr bool CONCAT = BN == 64 || BN == 128;   // BN = 128: 20 KB instead of 24 KB of operand reads per K step (N = 256 + N = 128)
   static constexpr int ACC_COLS = CONCAT ? 2 * BN : BN;                   // TMEM columns of one accumulator
   static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = BUDGET + EXTRA + 1024;
