@@ -60,9 +60,7 @@ __device__ __forceinline__ void load8(const float* xf, const int16_t* xi, int sr
   }
 }
 
-// 8 consecutive taps (col % 8 == 0) of one frame row into the tile-major operand: row_base = offset of (tile, K block 0,
-// hi, row), one K block = 2 * 128 * 64 halves, lo = hi + 128 * 64
-// the same to a precomputed destination
+// 8 consecutive taps of one frame row into the tile-major operand: fp16 hi / lo split, hi tile at dst, lo tile 128 * 64 halves on
 __device__ __forceinline__ void split_store_at(__half* dst, const float (&v)[8]) {
   __align__(16) __half h[8], l[8];
 #pragma unroll
@@ -73,18 +71,6 @@ __device__ __forceinline__ void split_store_at(__half* dst, const float (&v)[8])
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
   *reinterpret_cast<uint4*>(dst + 128 * 64) = *reinterpret_cast<const uint4*>(l);
 }
-__device__ __forceinline__ void split_store(__half* a3, size_t row_base, int col, const float (&v)[8]) {
-  __align__(16) __half h[8], l[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    h[q] = __float2half_rn(v[q]);
-    l[q] = __float2half_rn(v[q] - __half2float(h[q]));
-  }
-  __half* dst = a3 + row_base + static_cast<size_t>(col >> 6) * (2 * 128 * 64) + (col & 63);
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(dst + 128 * 64) = *reinterpret_cast<const uint4*>(l);
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
