@@ -445,7 +445,8 @@ def main():
         ne = min(args.e2e_chunks, n)
         fit = state["fit"]
         cent, thr = np.nan_to_num(fit.centroids), fit.rk[0]
-        grab = min(4096 if world > 1 else 8192, ne)   # chunks per host call = one unit of the dynamic pool (one rank: no pool to balance)
+        grab = min(4096 if world > 2 else 8192, ne)   # chunks per host call = one unit of the dynamic pool (one or two ranks copy at the
+        # full PCIe rate each -- nothing to balance -- and longer calls amortise the un-overlapped tail of a call)
         run_id = [0]
 
         def run_e2e(xh, bytes_per_sample, api):
