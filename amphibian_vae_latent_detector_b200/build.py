@@ -23,6 +23,7 @@ OBJ = HERE / "build"
 
 SOURCES = ["ctx.cu", "rms.cu", "gemm3.cu", "fold3.cu", "dftf3.cu", "logmel.cu", "convh.cu", "encoder.cu", "radial.cu", "map.cu", "resample.cu", "comm.cu", "api.cu"]
 EXTRA_FLAGS = {"rms.cu": ["-fmad=false"]}
+BRINGUP_ONLY = ["conv1t.cu"]      # experiments that lost their A/B: built into libavld_bringup.so only
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -53,7 +54,8 @@ def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> 
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "avld.h", Path(__file__)]
     jobs = []
-    for src in SOURCES:
+    sources = SOURCES + (BRINGUP_ONLY if bringup else [])
+    for src in sources:
         obj = OBJ / (src + ".o")
         if force or _stale(obj, [CSRC / src] + headers):
             cmd = [nvcc, *COMMON, *EXTRA_FLAGS.get(src, []), *(["-DAVLD_BRINGUP"] if bringup else []), "-c", str(CSRC / src), "-o", str(obj)]
@@ -72,7 +74,7 @@ def build(force: bool = False, verbose: bool = False, bringup: bool = False) -> 
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(run, jobs))
-    objs = [str(OBJ / (s + ".o")) for s in SOURCES]
+    objs = [str(OBJ / (s + ".o")) for s in sources]
     if force or jobs or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                "-Xcompiler", "-fPIC"]   # static cudart: no loader-path dependency on the GPU box

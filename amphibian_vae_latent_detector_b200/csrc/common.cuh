@@ -172,6 +172,8 @@ struct avld_ctx {
   std::vector<__nv_bfloat16*> d_slot_hi, d_slot_lo;   // activation slots, each max_batch * n_seg images of the largest tensor
   float* d_lat = nullptr;          // [max_batch * n_seg][latent_dim] per-segment latents (n_seg > 1 or a non-linear head)
 
+  bool conv1_tensor = false;       // bring-up builds: AVLD_CONV1_TENSOR at context creation sends the first conv to conv1t.cu
+
   // optional NCCL communicator of this context (comm.cu)
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 0;
@@ -259,6 +261,8 @@ int launch_logmel_post(avld_ctx* c, float* feat, int n, cudaStream_t st);
 int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_t st);
 int convh_encode_input_map(CUtensorMap* out, const void* base, int n, int H, int W, int C, int cblk);
 bool convh_supported(int c_in, int c_out, int ksize, int w);
+bool conv1t_supported(int ksize, int stride, int pad, int c_in, int c_out_pad, int h, int w, int pool);
+int launch_conv1t(avld_ctx* c, const float* feat, const OpDev& L, int n, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
                  __nv_bfloat16* out_lo, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);

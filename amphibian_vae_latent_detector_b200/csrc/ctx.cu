@@ -488,6 +488,9 @@ extern "C" int avld_ctx_create(int device, const avld_params* params, avld_ctx**
   c->p = *params;
   c->sm_count = prop.multiProcessorCount;
   if (const char* t = getenv("AVLD_HOST_TRACE")) c->host_trace_path = t;
+#ifdef AVLD_BRINGUP
+  c->conv1_tensor = getenv("AVLD_CONV1_TENSOR") != nullptr;
+#endif
   c->smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   const int r = build_ctx(c);
   if (r != AVLD_OK) {

@@ -364,6 +364,15 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
     const OpDev& L = c->ops[li];
     const TensorDev& T = c->tensors[L.dst];
     const bool last_linear_out = L.kind == OP_LINEAR && L.dst == c->enc_out && li + 1 == c->ops.size();
+#ifdef AVLD_BRINGUP
+    // tensor-core form of the first convolution (conv1t.cu: im2col rows built in shared memory, K = 9 -> 16): correct
+    // (2.3e-5 against torch) but 0.42 ms against 0.20 ms for the CUDA-core kernel below, so it is not in the product build
+    if (L.kind == OP_CONV_FIRST && c->conv1_tensor && conv1t_supported(L.ksize, L.stride, L.pad, 1, L.c_out, L.in_h, L.in_w, L.pool)) {
+      LaunchScope ls(c, ST_CONV_DIRECT, st);
+      AVLD_TRY(launch_conv1t(c, feat, L, N, hi_of(L.dst), lo_of(L.dst), st));
+      continue;
+    }
+#endif
     if (L.kind == OP_CONV_FIRST) {
       DirectConvParams P{};
       P.in = feat;
