@@ -320,16 +320,15 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (((h | 1) < P.H) && ((w | 1) < P.W) && cq < P.Cout) {         // the whole window lies inside the image
             const float4 b4 = avg ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_bias + cq);
             float o4[4] = {q4[0] + b4.x, q4[1] + b4.y, q4[2] + b4.z, q4[3] + b4.w};
-            __align__(8) __nv_bfloat16 hi[4];
-            __align__(8) __nv_bfloat16 lo[4];
+            if (P.relu && !avg) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (P.relu && !avg) o4[j] = relu_nan(o4[j]);
-              hi[j] = __float2bfloat16_rn(o4[j]);
-              lo[j] = __float2bfloat16_rn(o4[j] - __bfloat162float(hi[j]));
+              for (int j = 0; j < 4; ++j) o4[j] = relu_nan(o4[j]);
             }
-            *reinterpret_cast<uint2*>(P.out_hi + opix * P.Cout + cq) = *reinterpret_cast<const uint2*>(hi);
-            *reinterpret_cast<uint2*>(P.out_lo + opix * P.Cout + cq) = *reinterpret_cast<const uint2*>(lo);
+            uint32_t hw[2], lw[2];                       // packed conversions (F2FP), not four XU-pipe F2F per plane
+            split_bf16x2(o4[0], o4[1], hw[0], lw[0]);
+            split_bf16x2(o4[2], o4[3], hw[1], lw[1]);
+            *reinterpret_cast<uint2*>(P.out_hi + opix * P.Cout + cq) = make_uint2(hw[0], hw[1]);
+            *reinterpret_cast<uint2*>(P.out_lo + opix * P.Cout + cq) = make_uint2(lw[0], lw[1]);
           }
           continue;
         }
@@ -347,19 +346,15 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
         }
         if (writer && c0 < P.Cout) {
-          __align__(16) __nv_bfloat16 hi[16];
-          __align__(16) __nv_bfloat16 lo[16];
+          uint32_t hw[8], lw[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            hi[j] = __float2bfloat16_rn(o[j]);
-            lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
-          }
-          __nv_bfloat16* dh = P.out_hi + opix * P.Cout + c0;
-          __nv_bfloat16* dl = P.out_lo + opix * P.Cout + c0;
-          reinterpret_cast<uint4*>(dh)[0] = reinterpret_cast<const uint4*>(hi)[0];
-          reinterpret_cast<uint4*>(dh)[1] = reinterpret_cast<const uint4*>(hi)[1];
-          reinterpret_cast<uint4*>(dl)[0] = reinterpret_cast<const uint4*>(lo)[0];
-          reinterpret_cast<uint4*>(dl)[1] = reinterpret_cast<const uint4*>(lo)[1];
+          for (int j = 0; j < 16; j += 2) split_bf16x2(o[j], o[j + 1], hw[j >> 1], lw[j >> 1]);
+          uint4* dh = reinterpret_cast<uint4*>(P.out_hi + opix * P.Cout + c0);
+          uint4* dl = reinterpret_cast<uint4*>(P.out_lo + opix * P.Cout + c0);
+          dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
         }
       }
       tcgen05_fence_before();
