@@ -264,7 +264,7 @@ bool convh_supported(int c_in, int c_out, int ksize, int w);
 bool conv1t_supported(int ksize, int stride, int pad, int c_in, int c_out_pad, int h, int w, int pool);
 int launch_conv1t(avld_ctx* c, const float* feat, const OpDev& L, int n, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st);
 int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
-                 __nv_bfloat16* out_lo, cudaStream_t st);
+                 __nv_bfloat16* out_lo, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo, cudaStream_t st);
 int launch_split_bf16(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n, cudaStream_t st);
 int launch_split_f16(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t st);
 

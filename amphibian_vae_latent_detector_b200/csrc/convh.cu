@@ -33,6 +33,8 @@ struct ConvhParams {
   const float* bias;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  const __nv_bfloat16* res_hi;  // optional residual (same NHWC shape as the output, no pooling): out = act(conv + bias + res)
+  const __nv_bfloat16* res_lo;
 };
 
 namespace {
@@ -341,6 +343,18 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
+        if (P.res_hi != nullptr && writer && c0 < P.Cout) {          // fused residual add, before the activation
+          const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + opix * P.Cout + c0);
+          const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + opix * P.Cout + c0);
+          const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
+          const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+            o[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+          }
+        }
         if (P.relu) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = relu_nan(o[j]);
@@ -402,7 +416,7 @@ bool convh_supported(int c_in, int c_out, int ksize, int w) {
 }
 
 int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUtensorMap& a_lo, int n, __nv_bfloat16* out_hi,
-                 __nv_bfloat16* out_lo, cudaStream_t st) {
+                 __nv_bfloat16* out_lo, const __nv_bfloat16* res_hi, const __nv_bfloat16* res_lo, cudaStream_t st) {
   ConvhParams P{};
   P.tiles_w = L.in_w / kTW;
   P.tiles_h = (L.in_h + kTH - 1) / kTH;
@@ -418,6 +432,8 @@ int launch_convh(avld_ctx* c, const OpDev& L, const CUtensorMap& a_hi, const CUt
 #endif
   P.out_hi = out_hi;
   P.out_lo = out_lo;
+  P.res_hi = res_hi;
+  P.res_lo = res_lo;
   if (L.c_out == 64 && L.cblk == 32) return launch_one<64, 32>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
   if (L.c_out == 64 && L.cblk == 64) return launch_one<64, 64>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);
   if (L.c_out == 128 && L.cblk == 32) return launch_one<128, 32>(c, a_hi, a_lo, L.tm_w_hi, L.tm_w_lo, P, st);

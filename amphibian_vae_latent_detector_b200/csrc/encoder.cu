@@ -411,7 +411,8 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       AVLD_CUDA(cudaGetLastError());
     } else if (L.kind == OP_CONV_HALO) {
       LaunchScope ls(c, ST_CONV_GEMM, st);
-      AVLD_TRY(launch_convh(c, L, L.tm_in_hi, L.tm_in_lo, N, hi_of(L.dst), lo_of(L.dst), st));
+      AVLD_TRY(launch_convh(c, L, L.tm_in_hi, L.tm_in_lo, N, hi_of(L.dst), lo_of(L.dst), L.src2 >= 0 ? hi_of(L.src2) : nullptr,
+                            L.src2 >= 0 ? lo_of(L.src2) : nullptr, st));
     } else if (L.kind == OP_CONV_GEMM) {
       Gemm3Params P{};
       P.num_m_tiles = N * L.tiles_w * L.tiles_h;
@@ -428,6 +429,8 @@ int launch_encoder(avld_ctx* c, const float* feat, float* mu, int n, cudaStream_
       P.out_hi = hi_of(L.dst);
       P.out_lo = lo_of(L.dst);
       P.H = L.conv_h; P.W = L.conv_w; P.Cout = L.c_out; P.pool = L.pool; P.pool_avg = L.pool_avg;
+      P.res_hi = L.src2 >= 0 ? hi_of(L.src2) : nullptr;
+      P.res_lo = L.src2 >= 0 ? lo_of(L.src2) : nullptr;
       LaunchScope ls(c, ST_CONV_GEMM, st);
       AVLD_TRY(run_gemm3(c, L.bn, L.swz, EPI_CONV, L.tm_in_hi, L.tm_in_lo, L.tm_w_hi, L.tm_w_lo, P, st));
     } else if (L.kind == OP_LINEAR) {
@@ -589,6 +592,15 @@ extern "C" int avld_encoder_load_program(avld_ctx* c, const avld_op* ops, int32_
       AVLD_CHECK(L.pool == 1 || (ch % 2 == 0 && cw % 2 == 0), AVLD_ERR_UNSUPPORTED, "op %d: 2x2 pooling of an odd map", i);
       L.in_h = in->h; L.in_w = in->w; L.conv_h = ch; L.conv_w = cw; L.out_h = ch / L.pool; L.out_w = cw / L.pool;
       AVLD_TRY(define(s.out, s.c_out, L.out_h, L.out_w, false));
+      if (s.in1 >= 0) {            // fused residual add: out = act(conv(in0) + bias + in1)
+        const TensorDev* res = tensor_at(s.in1);
+        AVLD_CHECK(res != nullptr && s.in1 != 0 && s.in1 != s.out, AVLD_ERR_INVALID, "op %d: residual tensor %d is undefined", i, s.in1);
+        AVLD_CHECK(s.in0 != 0 && s.pool == 0, AVLD_ERR_UNSUPPORTED, "op %d: a residual input needs a tensor-core convolution without pooling", i);
+        AVLD_CHECK(res->c == s.c_out && res->h == L.out_h && res->w == L.out_w && res->c_pad == tens[s.out].c_pad, AVLD_ERR_INVALID,
+                   "op %d: residual tensor %d has another shape than the convolution's output", i, s.in1);
+      } else {
+        L.src2 = -1;
+      }
       const int co_pad = tens[s.out].c_pad, ci_pad = s.in0 == 0 ? 1 : in->c_pad;
       L.c_in = ci_pad; L.c_out = co_pad;
       L.K = static_cast<int64_t>(s.ksize) * s.ksize * ci_pad;

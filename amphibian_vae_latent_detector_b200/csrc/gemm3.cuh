@@ -45,6 +45,8 @@ struct Gemm3Params {
   // CONV epilogue
   int H, W, Cout, pool;     // H, W: conv output size before pooling
   int pool_avg;             // the fused 2x2 pooling averages (after the activation) instead of taking the maximum
+  const __nv_bfloat16* res_hi;   // optional residual of the CONV epilogue (output shape, no pooling): out = act(conv + bias + res)
+  const __nv_bfloat16* res_lo;
 };
 
 // non-template dispatcher (all instantiations live in gemm3.cu)
@@ -287,6 +289,18 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               o[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
               o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
               o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (P.res_hi != nullptr && writer && n0 + 16 <= P.Cout) {      // fused residual add, before the activation
+              const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + opix * P.Cout + n0);
+              const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + opix * P.Cout + n0);
+              const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
+              const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+                o[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+              }
             }
             if (P.relu) {
 #pragma unroll

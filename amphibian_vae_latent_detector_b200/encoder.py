@@ -177,6 +177,7 @@ class ConvOp:
     pool_avg: bool = False        # the fused pooling is AvgPool2d(2) instead of MaxPool2d(2)
     src: int = -1
     dst: int = -1
+    residual: int = -1            # tensor added to the convolution's output before the activation (a fused residual add)
 
 
 @dataclass
@@ -560,7 +561,7 @@ def export_program(module: nn.Module, in_frames: int = 192, in_mels: int = 64, v
         if op.dst in needed:
             kept.append(op)
             needed.update([op.a, op.b] if isinstance(op, AddOp) else [op.src])
-    prog.ops = list(reversed(kept))
+    prog.ops = _fuse_residual_adds(list(reversed(kept)), prog.out)
     for op in prog.ops:
         if isinstance(op, ConvOp):
             op.weight = op.weight.permute(0, 2, 3, 1).contiguous().float().numpy()
@@ -572,7 +573,7 @@ def export_program(module: nn.Module, in_frames: int = 192, in_mels: int = 64, v
     if any(isinstance(op, (AddOp, AffineOp, PoolOp, LinearOp)) and 0 in ([op.a, op.b] if isinstance(op, AddOp) else [op.src])
            for op in prog.ops):
         raise UnsupportedEncoder("the feature image must enter the network through a Conv2d")
-    prog.shapes = {k: v for k, v in shapes.items() if k == 0 or any(k in (getattr(o, "dst", None), getattr(o, "src", None), getattr(o, "a", None), getattr(o, "b", None)) for o in prog.ops)}
+    prog.shapes = {k: v for k, v in shapes.items() if k == 0 or any(k in (getattr(o, "dst", None), getattr(o, "src", None), getattr(o, "a", None), getattr(o, "b", None), getattr(o, "residual", None)) for o in prog.ops)}
     osh = shapes[prog.out]
     prog.latent_dim = int(np.prod(osh))
 
@@ -587,6 +588,42 @@ def export_program(module: nn.Module, in_frames: int = 192, in_mels: int = 64, v
     return prog
 
 
+def _inputs_of(op) -> list:
+    if isinstance(op, AddOp):
+        return [op.a, op.b]
+    return [op.src] + ([op.residual] if isinstance(op, ConvOp) and op.residual >= 0 else [])
+
+
+def _fuse_residual_adds(ops: list, out_tid: int) -> list:
+    """`y = conv(x) + r` (a residual block's tail: BatchNorm already folded, ReLU after the sum): the add becomes the
+    convolution's epilogue when the convolution is the LATER of the two producers (so r exists when it runs), has no
+    activation / pooling of its own and feeds nothing else.  Saves one HBM round trip of the feature map per block."""
+    ops = list(ops)
+    changed = True
+    while changed:
+        changed = False
+        uses: dict = {out_tid: 1}
+        for op in ops:
+            for t in _inputs_of(op):
+                uses[t] = uses.get(t, 0) + 1
+        producer = {op.dst: i for i, op in enumerate(ops)}
+        for i, op in enumerate(ops):
+            if not isinstance(op, AddOp):
+                continue
+            pa, pb = producer.get(op.a, -1), producer.get(op.b, -1)
+            cand, other = (pa, op.b) if pa > pb else (pb, op.a)
+            if cand < 0 or other == 0:
+                continue
+            p = ops[cand]
+            if isinstance(p, ConvOp) and not p.relu and p.pool == 1 and p.residual < 0 and p.src != 0 and uses.get(p.dst, 0) == 1 \
+                    and p.dst != other:
+                p.residual, p.relu, p.dst = other, op.relu, op.dst
+                del ops[i]
+                changed = True
+                break
+    return ops
+
+
 def run_program_torch(prog: EncoderProgram, x: torch.Tensor) -> torch.Tensor:
     """fp32 torch replay of an exported program on ``x [B,1,T,M]`` -> ``[B, latent_dim]`` (export self-check and the fp32
     reference the CUDA encoder is compared with in tests)."""
@@ -597,6 +634,8 @@ def run_program_torch(prog: EncoderProgram, x: torch.Tensor) -> torch.Tensor:
         if isinstance(op, ConvOp):
             wt = torch.from_numpy(op.weight).permute(0, 3, 1, 2).contiguous()
             y = F.conv2d(t[op.src], wt, torch.from_numpy(op.bias), stride=op.stride, padding=op.pad)
+            if op.residual >= 0:
+                y = y + t[op.residual]
             if op.relu:
                 y = F.relu(y)
             if op.pool == 2:

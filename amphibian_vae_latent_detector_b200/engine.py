@@ -193,6 +193,7 @@ class Engine:
             if isinstance(op, ConvOp):
                 cout, kh, _, cin = op.weight.shape
                 o.kind, o.in0, o.out, o.c_in, o.c_out = _lib.OP_CONV, op.src, op.dst, cin, cout
+                o.in1 = op.residual                    # fused residual add (-1: none)
                 o.ksize, o.stride, o.pad, o.relu = kh, op.stride, op.pad, int(op.relu)
                 o.pool = 0 if op.pool == 1 else (2 if op.pool_avg else 1)
                 o.in_h, o.in_w = op.in_hw

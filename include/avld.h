@@ -86,7 +86,8 @@ enum {
 };
 typedef struct avld_op {
   int32_t kind;
-  int32_t in0, in1, out;       /* tensor ids; in1 = -1 unless AVLD_OP_ADD; every id is written exactly once */
+  int32_t in0, in1, out;       /* tensor ids; in1 = the second operand of AVLD_OP_ADD, or for AVLD_OP_CONV an optional residual of the output's
+                                * shape added before the activation (no pooling then), else -1; every id is written exactly once */
   int32_t c_in, c_out;
   int32_t ksize, stride, pad;
   int32_t relu;                /* act = ReLU */

@@ -27,7 +27,9 @@ def test_residual_segmented_standin():
     prog = export_program(mod, 384, 64)
     assert prog.n_seg == 2 and prog.in_hw == (192, 64) and prog.latent_dim == 128
     kinds = [type(o) for o in prog.ops]
-    assert kinds.count(AddOp) == 4 and any(isinstance(o, ConvOp) and o.stride == 2 and o.weight.shape[1] == 3 for o in prog.ops)
+    # the four residual adds ride in the epilogue of the later of their two producing convolutions (no AddOp left)
+    assert kinds.count(AddOp) == 0 and sum(isinstance(o, ConvOp) and o.residual >= 0 for o in prog.ops) == 4
+    assert any(isinstance(o, ConvOp) and o.stride == 2 and o.weight.shape[1] == 3 for o in prog.ops)
     assert any(isinstance(o, ConvOp) and o.weight.shape[1] == 1 and o.stride == 2 for o in prog.ops)        # 1x1 stride-2 shortcut
     assert any(isinstance(o, PoolOp) and o.k == 0 for o in prog.ops) and any(isinstance(o, PoolOp) and o.k == 2 and o.avg for o in prog.ops)
     x = torch.randn(3, 1, 384, 64, generator=torch.Generator().manual_seed(1))
@@ -38,6 +40,28 @@ def test_residual_segmented_standin():
     assert _rel(run_program_torch(prog, x), ref) < 1e-5
     # logvar is not on the path to the latent: its head is not exported
     assert sum(isinstance(o, LinearOp) for o in prog.ops) == 2
+
+
+def test_an_add_that_cannot_be_fused_stays_an_op():
+    class TwoBranch(nn.Module):                                   # both operands are activated: neither convolution can absorb the add
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Conv2d(1, 32, 3, 1, 1)
+            self.a = nn.Conv2d(32, 64, 3, 1, 1)
+            self.b = nn.Conv2d(32, 64, 1)
+            self.fc = nn.Linear(64, 16)
+
+        def forward(self, x):
+            h = torch.nn.functional.max_pool2d(torch.relu(self.stem(x)), 2)
+            h = torch.relu(self.a(h)) + torch.relu(self.b(h))
+            return self.fc(h.mean(dim=(2, 3)))
+
+    mod = TwoBranch().eval()
+    prog = export_program(mod, 192, 64)
+    assert sum(isinstance(o, AddOp) for o in prog.ops) == 1 and all(o.residual < 0 for o in prog.ops if isinstance(o, ConvOp))
+    x = torch.randn(2, 1, 192, 64, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        assert _rel(run_program_torch(prog, x), mod(x)) < 1e-5
 
 
 def test_output_conventions_follow_the_reference():

@@ -60,12 +60,14 @@ def test_residual_segmented_encoder_vs_torch_module():
     import yaml
     from pathlib import Path
     from amphibian_vae_latent_detector_b200 import reference_api as api
-    from amphibian_vae_latent_detector_b200.encoder import init_standin_weights, AddOp, PoolOp
+    from amphibian_vae_latent_detector_b200.encoder import init_standin_weights, ConvOp, PoolOp
     cfg = yaml.safe_load((Path(__file__).resolve().parents[1] / "configs" / "bird_net_res_vae_audio_splitted.yaml").read_text())
     mod = init_standin_weights(api.build_nn_module(api._instantiate(api.pick_encoder_cfg(cfg))), seed=321)
     g = torch.Generator().manual_seed(5)
     prog = _check_against_torch(mod, torch.randn(19, 192, 64, generator=g))
-    assert prog.n_seg == 1 and any(isinstance(o, AddOp) for o in prog.ops) and any(isinstance(o, PoolOp) and o.k == 0 for o in prog.ops)
+    # the residual adds are fused into the epilogue of the convolution that produces their later operand
+    assert prog.n_seg == 1 and sum(isinstance(o, ConvOp) and o.residual >= 0 for o in prog.ops) == 4
+    assert any(isinstance(o, PoolOp) and o.k == 0 for o in prog.ops)
     # two segments per chunk: the latent is the mean of the segment latents (core:292-293)
     prog2 = _check_against_torch(mod, torch.randn(9, 384, 64, generator=g), target_frames=384)
     assert prog2.n_seg == 2
@@ -114,3 +116,20 @@ def test_encoder_layer_variety_vs_torch_module():
             return {"embedding": self.f(x)}
 
     _check_against_torch(init_standin_weights(MapLatent(), seed=4), feat)
+
+    class TwoBranch(nn.Module):                                         # an add of two activated branches: stays a kernel of its own
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Conv2d(1, 32, 3, 1, 1)
+            self.a = nn.Conv2d(32, 64, 3, 1, 1)
+            self.b = nn.Conv2d(32, 64, 1)
+            self.fc = nn.Linear(64, 16)
+
+        def forward(self, x):
+            h = torch.nn.functional.max_pool2d(torch.relu(self.stem(x)), 2)
+            h = torch.relu(self.a(h)) + torch.relu(self.b(h))
+            return self.fc(h.mean(dim=(2, 3)))
+
+    from amphibian_vae_latent_detector_b200.encoder import AddOp
+    prog = _check_against_torch(init_standin_weights(TwoBranch(), seed=6), feat)
+    assert any(isinstance(o, AddOp) for o in prog.ops)
