@@ -266,6 +266,10 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const bool inb = (h < P.H) && (w < P.W);
       const bool writer = inb && (P.pool == 1 || (((h | w) & 1) == 0));
       const size_t opix = (static_cast<size_t>(img) * OH + h / P.pool) * OW + w / P.pool;
+      // the residual operand of the first column group is requested before the wait for the accumulator
+      const bool has_res = P.res_hi != nullptr && writer && P.pool == 1;
+      Res16 res_next;
+      if (has_res) res16_load(res_next, P.res_hi, P.res_lo, opix * P.Cout + col_lo);
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tcgen05_fence_after();
       const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * Cfg::ACC_COLS);
@@ -343,17 +347,10 @@ convh_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
           o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
         }
-        if (P.res_hi != nullptr && writer && c0 < P.Cout) {          // fused residual add, before the activation
-          const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + opix * P.Cout + c0);
-          const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + opix * P.Cout + c0);
-          const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
-          const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-            o[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
-          }
+        if (has_res) {                          // fused residual add, before the activation; the next group's loads go out first
+          const Res16 cur = res_next;
+          if (c0 + 16 < col_lo + kColsPerWarp) res16_load(res_next, P.res_hi, P.res_lo, opix * P.Cout + c0 + 16);
+          res16_add(o, cur);
         }
         if (P.relu) {
 #pragma unroll

@@ -225,6 +225,30 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const int nt_begin = P.split_n ? item - mt * P.num_n_tiles : 0;
       const int nt_end = P.split_n ? nt_begin + 1 : P.num_n_tiles;
       for (int nt = nt_begin; nt < nt_end; ++nt) {
+        // EPI_CONV: row = pixel (h_local * tw + w_local) of a th x tw output tile, tw in {8, 16}: the 2x2 pooling partners
+        // are lane ^ 1 (w) and lane ^ tw (h) of the same warp.  The residual operand of the first column group is
+        // requested before the wait for the accumulator: it does not depend on it.
+        int img = 0, h = 0, w = 0, OH = 1, OW = 1;
+        bool inb = false, writer = false, has_res = false;
+        size_t opix = 0;
+        Res16 res[4];                   // ring of four column groups: a whole 64-column tile row, or the next 64 columns
+        if (EPI == EPI_CONV) {
+          const int per_img = P.tiles_w * P.tiles_h;
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          h = (r / P.tiles_w) * P.th + row / P.tw;
+          w = (r % P.tiles_w) * P.tw + row % P.tw;
+          inb = (h < P.H) && (w < P.W);
+          OH = P.H / P.pool; OW = P.W / P.pool;
+          writer = inb && (P.pool == 1 || (((h | w) & 1) == 0));
+          opix = (static_cast<size_t>(img) * OH + h / P.pool) * OW + w / P.pool;
+          has_res = P.res_hi != nullptr && writer && (nt + 1) * BN <= P.Cout;
+          if (has_res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (16 * g < BN) res16_load(res[g], P.res_hi, P.res_lo, opix * P.Cout + nt * BN + 16 * g);
+          }
+        }
         mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
         tcgen05_fence_after();
         const uint32_t t_acc = tmem_base + lane_base + static_cast<uint32_t>(acc * BN);
@@ -255,28 +279,28 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                 }
               }
               if (P.out_hi != nullptr) {
-                for (int j = 0; j < 16 && n0 + j < P.N_total; ++j) {
-                  const __nv_bfloat16 hi = __float2bfloat16_rn(o[j]);
-                  P.out_hi[m * P.ldc + n0 + j] = hi;
-                  P.out_lo[m * P.ldc + n0 + j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi));
+                uint32_t hw[8], lw[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) split_bf16x2(o[j], o[j + 1], hw[j >> 1], lw[j >> 1]);
+                __nv_bfloat16* dh = P.out_hi + m * P.ldc + n0;
+                __nv_bfloat16* dl = P.out_lo + m * P.ldc + n0;
+                if (n0 + 16 <= P.N_total && (P.ldc & 7) == 0) {
+                  reinterpret_cast<uint4*>(dh)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                  reinterpret_cast<uint4*>(dh)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                  reinterpret_cast<uint4*>(dl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                  reinterpret_cast<uint4*>(dl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                } else {
+                  const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(hw);
+                  const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(lw);
+                  for (int j = 0; j < 16 && n0 + j < P.N_total; ++j) { dh[j] = hs[j]; dl[j] = ls[j]; }
                 }
               }
             }
           }
         } else {
-          // EPI_CONV: row = pixel (h_local * tw + w_local) of a th x tw output tile, tw in {8, 16}:
-          // the 2x2 pooling partners are lane ^ 1 (w) and lane ^ tw (h) of the same warp.
-          const int per_img = P.tiles_w * P.tiles_h;
-          const int img = mt / per_img;
-          const int r = mt - img * per_img;
-          const int h = (r / P.tiles_w) * P.th + row / P.tw;
-          const int w = (r % P.tiles_w) * P.tw + row % P.tw;
-          const bool inb = (h < P.H) && (w < P.W);
-          const int OH = P.H / P.pool, OW = P.W / P.pool;
-          const bool writer = inb && (P.pool == 1 || (((h | w) & 1) == 0));
-          const size_t opix = (static_cast<size_t>(img) * OH + h / P.pool) * OW + w / P.pool;
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 16) {
+          // one 16-column group; `slot` holds its residual operand (requested a whole 64-column row ahead: a group ahead was
+          // not enough to cover the DRAM latency -- ncu: the adds waited ~1 000 cycles per group, 4.3 us per 128-pixel tile)
+          auto do_group = [&](const int c0, Res16& slot) {
             uint32_t v[16];
             tmem_ld16(t_acc + c0, v);
             tmem_ld_wait();
@@ -290,17 +314,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               o[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
               o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
             }
-            if (P.res_hi != nullptr && writer && n0 + 16 <= P.Cout) {      // fused residual add, before the activation
-              const uint4* rh = reinterpret_cast<const uint4*>(P.res_hi + opix * P.Cout + n0);
-              const uint4* rl = reinterpret_cast<const uint4*>(P.res_lo + opix * P.Cout + n0);
-              const uint4 h0 = rh[0], h1 = rh[1], l0 = rl[0], l1 = rl[1];
-              const uint32_t hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-              const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                o[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
-                o[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
-              }
+            if (has_res) {                      // fused residual add, before the activation; this slot is refilled four groups ahead
+              const Res16 cur = slot;
+              if (c0 + 64 < BN) res16_load(slot, P.res_hi, P.res_lo, opix * P.Cout + n0 + 64);
+              res16_add(o, cur);
             }
             if (P.relu) {
 #pragma unroll
@@ -318,24 +335,30 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               for (int j = 0; j < 16; ++j) o[j] = P.pool_avg ? (o[j] + u[j]) * 0.25f : max_nan(o[j], u[j]);
             }
             if (writer && n0 < P.Cout) {
-              __align__(16) __nv_bfloat16 hi[16];
-              __align__(16) __nv_bfloat16 lo[16];
+              // packed conversions (one full-rate F2FP per pair): the scalar form is 32 XU-pipe F2F per column group, which
+              // paced layers with little MMA work per tile (a 1x1 shortcut: 4.4 us per 128-pixel tile)
+              uint32_t hw[8], lw[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                hi[j] = __float2bfloat16_rn(o[j]);
-                lo[j] = __float2bfloat16_rn(o[j] - __bfloat162float(hi[j]));
-              }
+              for (int j = 0; j < 16; j += 2) split_bf16x2(o[j], o[j + 1], hw[j >> 1], lw[j >> 1]);
               __nv_bfloat16* dh = P.out_hi + opix * P.Cout + n0;
               __nv_bfloat16* dl = P.out_lo + opix * P.Cout + n0;
               if (n0 + 16 <= P.Cout) {
-                reinterpret_cast<uint4*>(dh)[0] = reinterpret_cast<const uint4*>(hi)[0];
-                reinterpret_cast<uint4*>(dh)[1] = reinterpret_cast<const uint4*>(hi)[1];
-                reinterpret_cast<uint4*>(dl)[0] = reinterpret_cast<const uint4*>(lo)[0];
-                reinterpret_cast<uint4*>(dl)[1] = reinterpret_cast<const uint4*>(lo)[1];
+                reinterpret_cast<uint4*>(dh)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                reinterpret_cast<uint4*>(dh)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                reinterpret_cast<uint4*>(dl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                reinterpret_cast<uint4*>(dl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
               } else {
-                for (int j = 0; j < 16 && n0 + j < P.Cout; ++j) { dh[j] = hi[j]; dl[j] = lo[j]; }
+                const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(hw);
+                const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(lw);
+                for (int j = 0; j < 16 && n0 + j < P.Cout; ++j) { dh[j] = hs[j]; dl[j] = ls[j]; }
               }
             }
+          };
+#pragma unroll 1
+          for (int c64 = 0; c64 < BN; c64 += 64) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (16 * g < BN) do_group(c64 + 16 * g, res[g]);
           }
         }
         tcgen05_fence_before();

@@ -4,6 +4,7 @@
 // CUTLASS headers shipped in this image: cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -40,6 +41,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack_bf16x2(a, b);
   lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
+// Sixteen channels of a bf16 hi / lo NHWC tensor (a fused residual operand of a convolution's epilogue): loaded early, added
+// late -- the loads do not depend on the accumulator, so they are issued before the epilogue waits for it.
+struct Res16 {
+  uint4 h0, h1, l0, l1;
+};
+__device__ __forceinline__ void res16_load(Res16& r, const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off) {
+  const uint4* ph = reinterpret_cast<const uint4*>(hi + off);
+  const uint4* pl = reinterpret_cast<const uint4*>(lo + off);
+  r.h0 = __ldg(ph); r.h1 = __ldg(ph + 1); r.l0 = __ldg(pl); r.l1 = __ldg(pl + 1);
+}
+__device__ __forceinline__ void res16_add(float (&o)[16], const Res16& r) {
+  const uint32_t hh[8] = {r.h0.x, r.h0.y, r.h0.z, r.h0.w, r.h1.x, r.h1.y, r.h1.z, r.h1.w};
+  const uint32_t ll[8] = {r.l0.x, r.l0.y, r.l0.z, r.l0.w, r.l1.x, r.l1.y, r.l1.z, r.l1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[2 * j] += __uint_as_float(hh[j] << 16) + __uint_as_float(ll[j] << 16);
+    o[2 * j + 1] += __uint_as_float(hh[j] & 0xffff0000u) + __uint_as_float(ll[j] & 0xffff0000u);
+  }
 }
 
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
