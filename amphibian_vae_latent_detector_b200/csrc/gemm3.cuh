@@ -71,8 +71,11 @@ struct Gemm3Cfg {
 };
 
 // threads per CTA: TMA warp + MMA warp + 4 epilogue warps
+// The CONV epilogue moves an NHWC row per pixel (output, optionally a residual operand): with four warps only 128 threads carry
+// all of a CTA's memory traffic and layers with little MMA work per tile (1x1 shortcuts) starve -- eight warps, two per TMEM
+// lane quarter with half the columns each.
 template <int EPI>
-struct Gemm3Threads { static constexpr int value = 192; };
+struct Gemm3Threads { static constexpr int epi_warps = EPI == EPI_CONV ? 8 : 4; static constexpr int value = 64 + 32 * epi_warps; };
 
 template <int BN, int SWZ, int EPI>
 __global__ void __launch_bounds__(Gemm3Threads<EPI>::value, 1)
@@ -108,7 +111,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * Gemm3Threads<EPI>::epi_warps);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -216,6 +219,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter + 32) belong to this warp
+    constexpr int kConvCols = BN / (Gemm3Threads<EPI>::epi_warps / 4);   // CONV: columns per epilogue warp (BN >= 32)
+    const int conv_col0 = ((warp - 2) >> 2) * kConvCols;
     const int row = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     int acc = 0;
@@ -246,7 +251,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (has_res) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              if (16 * g < BN) res16_load(res[g], P.res_hi, P.res_lo, opix * P.Cout + nt * BN + 16 * g);
+              if (16 * g < kConvCols) res16_load(res[g], P.res_hi, P.res_lo, opix * P.Cout + nt * BN + conv_col0 + 16 * g);
           }
         }
         mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
@@ -316,7 +321,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
             if (has_res) {                      // fused residual add, before the activation; this slot is refilled four groups ahead
               const Res16 cur = slot;
-              if (c0 + 64 < BN) res16_load(slot, P.res_hi, P.res_lo, opix * P.Cout + n0 + 64);
+              if (c0 + 64 < conv_col0 + kConvCols) res16_load(slot, P.res_hi, P.res_lo, opix * P.Cout + n0 + 64);
               res16_add(o, cur);
             }
             if (P.relu) {
@@ -355,10 +360,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             }
           };
 #pragma unroll 1
-          for (int c64 = 0; c64 < BN; c64 += 64) {
+          for (int c64 = 0; c64 < kConvCols; c64 += 64) {
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              if (16 * g < BN) do_group(c64 + 16 * g, res[g]);
+              if (16 * g < kConvCols) do_group(conv_col0 + c64 + 16 * g, res[g]);
           }
         }
         tcgen05_fence_before();
