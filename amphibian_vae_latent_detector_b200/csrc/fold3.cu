@@ -11,6 +11,7 @@
 // the DRAM rate (profiles/r02a_dft_probes.txt).
 #include <cstdlib>
 #include "common.cuh"
+#include "ptx.cuh"
 #include "sample.cuh"
 
 namespace avld {
@@ -62,14 +63,17 @@ __device__ __forceinline__ void load8(const float* xf, const int16_t* xi, int sr
 
 // 8 consecutive taps of one frame row into the tile-major operand: fp16 hi / lo split, hi tile at dst, lo tile 128 * 64 halves on
 __device__ __forceinline__ void split_store_at(__half* dst, const float (&v)[8]) {
-  __align__(16) __half h[8], l[8];
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    h[q] = __float2half_rn(v[q]);
-    l[q] = __float2half_rn(v[q] - __half2float(h[q]));
+  for (int q = 0; q < 4; ++q) {
+    const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+    const float2 r = sub2(make_float2(v[2 * q], v[2 * q + 1]), __half22float2(hh));
+    const __half2 ll = __floats2half2_rn(r.x, r.y);
+    h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[q] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(dst + 128 * 64) = *reinterpret_cast<const uint4*>(l);
+  __stcs(reinterpret_cast<uint4*>(dst), make_uint4(h[0], h[1], h[2], h[3]));
+  __stcs(reinterpret_cast<uint4*>(dst + 128 * 64), make_uint4(l[0], l[1], l[2], l[3]));
 }
 }  // namespace
 
@@ -86,26 +90,31 @@ __device__ __forceinline__ void split_store_at(__half* dst, const float (&v)[8])
 namespace {
 
 // Sample source of fold3_kernel.  SRC 0: float32 chunk, 1: raw PCM_16 chunk (both normalised on the fly by fin()),
-// 2: the normalised PCM_16 integers q (+32768) left by prep_kernel -- raw() is then q itself and the power-of-two factor
-// pow2 / 32768 goes into the window values instead (exact, so all three give the same bits).
+// 2: the normalised PCM_16 integers q (+32768) left by prep_kernel -- the power-of-two factor pow2 / 32768 then goes into the
+// window values instead (exact, so all three give the same bits).  SRC 2 hands the samples out *biased*: the float
+// kBias + q = 2^23 + (q + 32768), one PRMT away from the stored integer.  The fold only ever needs a sample of an ascending
+// run together with one of a descending run, as a - b and a + b: a - b is the difference of the biased values, a + b is
+// (biased a - 2 kBias) + biased b -- both exact (integers below 2^24), one bias removal per *pair* of samples instead of two.
 template <int SRC>
 struct Samples {
   const float* xf;
   const int16_t* xi;
   const uint16_t* xq;
-  __device__ __forceinline__ float raw(int i) const {
-    if (SRC == 2) return __uint_as_float(0x4B000000u | xq[i]) - 8421376.0f;       // 2^23 + u - (2^23 + 2^15)
+  static constexpr float kBias = SRC == 2 ? 8421376.0f : 0.0f;                        // 2^23 + 2^15
+  __device__ __forceinline__ float biased(int i) const {
+    if (SRC == 2) return __uint_as_float(0x4B000000u | xq[i]);
     return raw_sample<SRC == 1>(xf, xi, i);
   }
-  // 8 consecutive samples from the 16-byte aligned index i
+  __device__ __forceinline__ float raw(int i) const { return SRC == 2 ? biased(i) - kBias : biased(i); }
+  // 8 consecutive (biased) samples from the 16-byte aligned index i
   __device__ __forceinline__ void load8(int i, float (&r)[8]) const {
     if (SRC == 2) {
       const uint4 u = *reinterpret_cast<const uint4*>(xq + i);
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        r[2 * j] = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7610)) - 8421376.0f;
-        r[2 * j + 1] = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7632)) - 8421376.0f;
+        r[2 * j] = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7610));
+        r[2 * j + 1] = __uint_as_float(__byte_perm(w[j], 0x4B000000u, 0x7632));
       }
     } else {
       avld::load8<SRC == 1>(xf, xi, i, r);
@@ -117,13 +126,13 @@ struct Samples {
     load8(i0, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = v[j];
-    r[8] = raw(i0 + 8);
+    r[8] = biased(i0 + 8);
   }
   // 9 samples x[i0 - j], j = 0..8 (descending): scalar at i0 + aligned vector of 8 below it
   __device__ __forceinline__ void load9_down(int i0, float (&r)[9]) const {
     float v[8];
     load8(i0 - 8, v);
-    r[0] = raw(i0);
+    r[0] = biased(i0);
 #pragma unroll
     for (int j = 1; j < 9; ++j) r[j] = v[8 - j];
   }
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold3Params P) {
       X.load9_down(s0 + H + Q - k0, x8);
     } else {
       const int plen = P.L + N;
-      auto get = [&](int p) -> float { return (p >= 0 && p < plen) ? X.raw(reflect_src(p, H, P.L)) : 0.f; };
+      auto get = [&](int p) -> float { return (p >= 0 && p < plen) ? X.biased(reflect_src(p, H, P.L)) : (SRC == 2 ? Samples<SRC>::kBias : 0.f); };
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
         const int k = k0 + q;
@@ -189,56 +198,74 @@ __global__ void __launch_bounds__(128, MINB) fold3_kernel(const Fold3Params P) {
       w78[0] = t6.x; w78[1] = t6.y; w78[2] = t6.z; w78[3] = t6.w; w78[4] = t7.x; w78[5] = t7.y; w78[6] = t7.z; w78[7] = t7.w;
       w58[8] = t8.x; w78[8] = t8.y;
     }
-    if (SRC == 2) {
+    if (SRC == 2) {                                      // exact (a power of two), two taps per FMUL2
+      const float2 ws2 = make_float2(wscale, wscale);
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        const float2 a = mul2(make_float2(w58[q], w58[q + 1]), ws2), b = mul2(make_float2(w78[q], w78[q + 1]), ws2);
+        const float2 c = mul2(make_float2(wk8[q], wk8[q + 1]), ws2), d = mul2(make_float2(wh8[q], wh8[q + 1]), ws2);
+        w58[q] = a.x; w58[q + 1] = a.y; w78[q] = b.x; w78[q + 1] = b.y;
+        wk8[q] = c.x; wk8[q + 1] = c.y; wh8[q] = d.x; wh8[q + 1] = d.y;
+      }
+      w58[8] *= wscale;
+      w78[8] *= wscale;
+    }
+    // SRC 0 / 1: finish every sample (scale, clip, PCM_16 round trip, power of two); SRC 2: nothing to do, the bias stays on
+    constexpr float kB = Samples<SRC>::kBias;
+    if (SRC != 2) {
 #pragma unroll
       for (int q = 0; q < 9; ++q) {
-        w58[q] *= wscale;
-        w78[q] *= wscale;
-        if (q < 8) {
-          wk8[q] *= wscale;
-          wh8[q] *= wscale;
-        }
+        x5[q] = fin(x5[q]); x6[q] = fin(x6[q]); x7[q] = fin(x7[q]); x8[q] = fin(x8[q]);
+        if (q < 8) { x1[q] = fin(x1[q]); x2[q] = fin(x2[q]); x3[q] = fin(x3[q]); x4[q] = fin(x4[q]); }
       }
     }
+    if (k0 == 0) {                                       // k = 0: u[0] and u[H] pair with nothing, u[Q] and u[3Q] are one pair, not two
+      x2[0] = kB; x4[0] = kB; x7[0] = kB; x8[0] = kB;
+    }
+    // Two taps per instruction (FADD2 / FFMA2): the integer sums and differences are exact, only the window products round
+    // (each separately, mul2_rn), so the bits are those of the scalar form.  Ascending runs: x1, x4, x6, x7.
+    const float2 b2 = make_float2(2.0f * kB, 2.0f * kB);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) {
-      const int k = k0 + q;
-      const float w5 = w58[q], w7 = w78[q];
-      const float a5 = fin(x5[q]);
-      const float a6 = fin(x6[q]);
-      float a7 = fin(x7[q]);
-      float a8 = fin(x8[q]);
-      if (k == 0) {                                      // u[Q] and u[3Q] are one pair, not two
-        a7 = 0.f;
-        a8 = 0.f;
+    for (int q = 0; q < 8; q += 2) {
+      const float2 W5 = make_float2(w58[q], w58[q + 1]), W7 = make_float2(w78[q], w78[q + 1]);
+      const float2 WK = make_float2(wk8[q], wk8[q + 1]), WH = make_float2(wh8[q], wh8[q + 1]);
+      const float2 A1 = make_float2(x1[q], x1[q + 1]), A2 = make_float2(x2[q], x2[q + 1]), A3 = make_float2(x3[q], x3[q + 1]);
+      const float2 A4 = make_float2(x4[q], x4[q + 1]), A5 = make_float2(x5[q], x5[q + 1]), A6 = make_float2(x6[q], x6[q + 1]);
+      const float2 A7 = make_float2(x7[q], x7[q + 1]), A8 = make_float2(x8[q], x8[q + 1]);
+      const float2 s56 = SRC == 2 ? add2(sub2(A6, b2), A5) : add2(A5, A6), s78 = SRC == 2 ? add2(sub2(A7, b2), A8) : add2(A7, A8);
+      const float2 fp = mul2_rn(W5, s56), fm = mul2_rn(W7, s78);
+      const float2 gp = mul2_rn(W5, sub2(A5, A6)), gm = mul2_rn(W7, sub2(A7, A8));
+      const float2 o2c = sub2(fp, fm), o2s = add2(gp, gm);      // odd bins at k' = Q - k: block element 8 - q of [Q-k0-8, Q-k0)
+      if (q >= 1) {
+        oc2[8 - q] = o2c.x;
+        os2[8 - q] = o2s.x;
       }
-      const float fp = __fmul_rn(w5, a5 + a6), fm = __fmul_rn(w7, a7 + a8);   // integer sums are exact; only the window products round
-      const float gp = __fmul_rn(w5, a5 - a6), gm = __fmul_rn(w7, a7 - a8);
-      if (q >= 1) {                                      // odd bins at k' = Q - k: block element 8 - q of [Q-k0-8, Q-k0)
-        oc2[8 - q] = fp - fm;
-        os2[8 - q] = gp + gm;
-      }
-      if (q < 8) {
-        const float wk = wk8[q], wh = wh8[q];
-        const float a1 = fin(x1[q]);
-        float a2 = fin(x2[q]);
-        const float a3 = fin(x3[q]);
-        float a4 = fin(x4[q]);
-        if (k == 0) {                                    // u[0] and u[H] pair with nothing
-          a2 = 0.f;
-          a4 = 0.f;
-        }
-        const float ep = __fmul_rn(wk, a1 + a2), em = __fmul_rn(wh, a3 + a4);
-        const float op = __fmul_rn(wk, a1 - a2), om = __fmul_rn(wh, a3 - a4);
-        const float Pk = ep + em, Pm = fp + fm, Rk = op - om, Rm = gp - gm;
-        const bool z = k == 0;
-        oc[q] = ep - em;
-        os[q] = z ? 0.f : op + om;
-        c0[q] = Pk + Pm;
-        c2[q] = Pk - Pm;
-        s0v[q] = z ? 0.f : Rk - Rm;
-        s2v[q] = z ? 0.f : Rk + Rm;
-      }
+      oc2[7 - q] = o2c.y;
+      os2[7 - q] = o2s.y;
+      const float2 s12 = SRC == 2 ? add2(sub2(A1, b2), A2) : add2(A1, A2), s34 = SRC == 2 ? add2(sub2(A4, b2), A3) : add2(A3, A4);
+      const float2 ep = mul2_rn(WK, s12), em = mul2_rn(WH, s34);
+      const float2 op = mul2_rn(WK, sub2(A1, A2)), om = mul2_rn(WH, sub2(A3, A4));
+      const float2 Pk = add2(ep, em), Pm = add2(fp, fm), Rk = sub2(op, om), Rm = sub2(gp, gm);
+      const float2 voc = sub2(ep, em), vos = add2(op, om), vc0 = add2(Pk, Pm), vc2 = sub2(Pk, Pm);
+      const float2 vs0 = sub2(Rk, Rm), vs2 = add2(Rk, Rm);
+      oc[q] = voc.x;  oc[q + 1] = voc.y;
+      os[q] = vos.x;  os[q + 1] = vos.y;
+      c0[q] = vc0.x;  c0[q + 1] = vc0.y;
+      c2[q] = vc2.x;  c2[q + 1] = vc2.y;
+      s0v[q] = vs0.x; s0v[q + 1] = vs0.y;
+      s2v[q] = vs2.x; s2v[q + 1] = vs2.y;
+    }
+    {                                                    // the ninth tap only feeds the odd class (k' = Q - k0 - 8)
+      const float s56 = SRC == 2 ? (x6[8] - 2.0f * kB) + x5[8] : x5[8] + x6[8], s78 = SRC == 2 ? (x7[8] - 2.0f * kB) + x8[8] : x7[8] + x8[8];
+      const float fp = __fmul_rn(w58[8], s56), fm = __fmul_rn(w78[8], s78);
+      const float gp = __fmul_rn(w58[8], x5[8] - x6[8]), gm = __fmul_rn(w78[8], x7[8] - x8[8]);
+      oc2[0] = fp - fm;
+      os2[0] = gp + gm;
+    }
+    if (k0 == 0) {                                       // the sine parts have no tap 0
+      os[0] = 0.f;
+      s0v[0] = 0.f;
+      s2v[0] = 0.f;
     }
     // Destination of an 8-tap block at column col of this frame row: (tile, K block col / 64, hi, row, col % 64).  The six
     // ascending streams sit at k0 plus a multiple of 64 columns, the two odd-class streams at Q - 8 - k0 (+ Q): two row

@@ -21,6 +21,34 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
+// Packed fp32 add / subtract / multiply (FADD2 / FFMA2, sm_100): per component the same bits as __fadd_rn / __fsub_rn /
+// __fmul_rn.  ptxas contracts a `mul.rn.f32x2` (and an fma with a -0 addend) into a following packed add -- unlike the scalar
+// .rn forms -- so the separately rounded product is an fma with a +0 addend, which it keeps apart (cuobjdump: FFMA2 .., RZ then
+// FADD2).  The +0 turns an exact -0 product into +0: harmless for operands that are only ever summed.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// plain packed multiply (FMUL2): may be contracted into a following packed add -- use it only where nothing can be
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) { return fma2(a, b, make_float2(0.f, 0.f)); }
+
 // NaN-propagating max / ReLU (torch semantics) in one FMNMX.NAN each
 __device__ __forceinline__ float max_nan(float a, float b) {
   float d;
