@@ -16,7 +16,7 @@ lib = Path(sys.argv[1]) if len(sys.argv) > 1 else Path(__file__).resolve().paren
 out = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
 WATCH = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMALDG.MULTICAST", "UTMASTG", "UTCBAR", "UTCBAR.MULTICAST", "UBLKCP",
-         "SYNCS", "UTCATOMSWS", "FFMA", "FFMA2", "HMMA", "DFMA", "ATOMG", "REDG", "RED"]
+         "SYNCS", "UTCATOMSWS", "FFMA", "FFMA2", "FADD2", "FMUL2", "HMMA", "DFMA", "ATOMG", "REDG", "RED"]
 kern, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
