@@ -335,40 +335,54 @@ __global__ void __cluster_dims__(kPrepCluster, 1, 1) __launch_bounds__(512, 4) p
   const In* __restrict__ xin = PCM ? reinterpret_cast<const In*>(xi) : reinterpret_cast<const In*>(xf);
   auto cvt = [](In s) -> float { return PCM ? static_cast<float>(s) * (1.0f / 32768.0f) : static_cast<float>(s); };
 
-  // ---- sweep 1: leaf sums (lane j of an 8-lane group owns accumulator j of numpy's eight)
+  // ---- sweep 1: leaf sums.  A thread owns two adjacent accumulators (2 jj, 2 jj + 1) of numpy's eight, four lanes own a
+  // leaf: 8-byte loads, twice the bytes in flight per thread of the one-accumulator form, and the first level of the final
+  // combination ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) is thread-local.
   float mx = 0.f;
-  const int j = tid & 7;
-  const unsigned gmask = 0xFFu << (8 * (lane >> 3));
+  const int jj = tid & 3;
+  const unsigned gmask = 0xFu << (4 * (lane >> 2));
   const int32_t* __restrict__ lo_p = P.leaf_off + leaf0;
   const int32_t* __restrict__ ll_p = P.leaf_len + leaf0;
-  for (int l = tid >> 3; l < lpc; l += 64) {
+  using In2 = typename std::conditional<PCM, uint32_t, float2>::type;
+  auto cvt2 = [](In2 s) -> float2 {
+    if constexpr (PCM) {
+      return make_float2(static_cast<float>(static_cast<int16_t>(s & 0xffffu)) * (1.0f / 32768.0f),
+                         static_cast<float>(static_cast<int16_t>(s >> 16)) * (1.0f / 32768.0f));
+    } else {
+      return s;
+    }
+  };
+  for (int l = tid >> 2; l < lpc; l += 128) {
     const int rows = ll_p[l] >> 3;              // >= 8 (launch_prep checks the plan): the first eight rows load unconditionally
-    const In* __restrict__ q = xin + lo_p[l] + j;
-    float v8[8];
+    const In2* __restrict__ q = reinterpret_cast<const In2*>(xin + lo_p[l] + 2 * jj);      // row u at q[4 u]
+    float2 v8[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v8[u] = cvt(q[8 * u]);
-    const float v9 = rows > 8 ? cvt(q[64]) : 0.f;       // the ninth row of a 72-sample leaf rides along with the first eight
-    mx = fmaxf(mx, fabsf(v8[0]));
-    float r = __fmul_rn(v8[0], v8[0]);
+    for (int u = 0; u < 8; ++u) v8[u] = cvt2(q[4 * u]);
+    const float2 v9 = rows > 8 ? cvt2(q[32]) : make_float2(0.f, 0.f);   // the ninth row of a 72-sample leaf rides along with the first eight
+    mx = fmaxf(mx, fmaxf(fabsf(v8[0].x), fabsf(v8[0].y)));
+    float r0 = __fmul_rn(v8[0].x, v8[0].x), r1 = __fmul_rn(v8[0].y, v8[0].y);
 #pragma unroll
     for (int u = 1; u < 8; ++u) {
-      mx = fmaxf(mx, fabsf(v8[u]));
-      r = __fadd_rn(r, __fmul_rn(v8[u], v8[u]));
+      mx = fmaxf(mx, fmaxf(fabsf(v8[u].x), fabsf(v8[u].y)));
+      r0 = __fadd_rn(r0, __fmul_rn(v8[u].x, v8[u].x));
+      r1 = __fadd_rn(r1, __fmul_rn(v8[u].y, v8[u].y));
     }
     if (rows > 8) {
-      mx = fmaxf(mx, fabsf(v9));
-      r = __fadd_rn(r, __fmul_rn(v9, v9));
+      mx = fmaxf(mx, fmaxf(fabsf(v9.x), fabsf(v9.y)));
+      r0 = __fadd_rn(r0, __fmul_rn(v9.x, v9.x));
+      r1 = __fadd_rn(r1, __fmul_rn(v9.y, v9.y));
 #pragma unroll 1
       for (int u = 9; u < rows; ++u) {
-        const float v = cvt(q[8 * u]);
-        mx = fmaxf(mx, fabsf(v));
-        r = __fadd_rn(r, __fmul_rn(v, v));
+        const float2 v = cvt2(q[4 * u]);
+        mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+        r0 = __fadd_rn(r0, __fmul_rn(v.x, v.x));
+        r1 = __fadd_rn(r1, __fmul_rn(v.y, v.y));
       }
     }
-    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1, 8));      // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
-    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2, 8));
-    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 4, 8));
-    if (j == 0) s_leaf[l] = r;
+    float r = __fadd_rn(r0, r1);                             // ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7))
+    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 1, 4));
+    r = __fadd_rn(r, __shfl_xor_sync(gmask, r, 2, 4));
+    if (jj == 0) s_leaf[l] = r;
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) s_wmax[warp] = mx;
