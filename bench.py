@@ -81,7 +81,11 @@ def measured_peaks():
             out["fp16_sustained"], out["fp16_source"] = float(d["fp16_tflops_sustained"]), "profiles/r02_dense_peaks.json (torch.matmul fp16 8192^3, 4 s back to back)"
         except Exception:
             pass
-    out["fp32_fma_tflops"] = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+    out["fp32_fma_tflops"] = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 lanes x 2 flop x 1.965 GHz ...
+    try:                                                             # ... which a pure FFMA2 stream reaches (tools/fma_peak.cu)
+        out["fp32_fma_tflops"] = float(json.loads((REPO / "profiles" / "r02j_fma_peak.json").read_text())["ffma2_tflops"])
+    except Exception:
+        pass
     return out
 
 
