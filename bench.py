@@ -449,10 +449,10 @@ def main():
         ne = min(args.e2e_chunks, n)
         fit = state["fit"]
         cent, thr = np.nan_to_num(fit.centroids), fit.rk[0]
-        # chunks per host call = one unit of the dynamic pool.  One rank has nothing to balance: the whole step is one call (the
-        # un-overlapped tail of a call, ~1 ms of kernels after the last byte has landed, is paid once per call); two ranks copy at
-        # the full PCIe rate each and take 8192-chunk units, more ranks share the host bridges and balance in 4096-chunk units
-        grab = min(ne if world == 1 else (8192 if world == 2 else 4096), ne)
+        # chunks per host call = one unit of the dynamic pool.  One or two ranks copy at the full PCIe rate each and have nothing to
+        # balance: a rank's step is one call (the un-overlapped tail of a call, ~1 ms of kernels after the last byte has landed, is
+        # paid once per call); more ranks share the host bridges and balance in 4096-chunk units
+        grab = min(ne if world <= 2 else 4096, ne)
         run_id = [0]
 
         def run_e2e(xh, bytes_per_sample, api):
