@@ -124,7 +124,7 @@ int avld_ctx_info(const avld_ctx* ctx, int32_t* n_frames, int32_t* latent_dim, i
 int avld_ctx_set_normalization(avld_ctx* ctx, int scalar_semantics, double target_rms, double rms_min, double eps);
 
 /* How the STFT is evaluated on this context (accounting for bench.py's roofline line): `mode` receives a static string
- * ("fold2" twice-folded, "fold"/"fold1" once-folded, "direct"), algorithmic = the flops of the plain windowed DFT GEMM
+ * ("fold3": the three-times folded GEMM of dftf3.cu, the only form the library carries), algorithmic = the flops of the plain windowed DFT GEMM
  * restricted to the bins with mel weight (2 * F * n_fft * 2 * bins), issued = the tensor-core
  * flops the selected kernel actually issues per chunk (all split-precision passes, padded tiles included). */
 int avld_ctx_dft_info(const avld_ctx* ctx, const char** mode, double* algorithmic_flops_per_chunk,
